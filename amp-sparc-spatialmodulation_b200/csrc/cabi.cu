@@ -1,0 +1,421 @@
+// C-ABI entry points of libampsm_b200.so (declared in include/ampsm_b200.h): argument checking, kernel selection,
+// and the host-buffer variants that overlap chunked host<->device copies with the kernels on two streams.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+namespace ampsm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+static int make_geom(const ampsm_problem* p, const ampsm_alphabet* a, Geom* g, DevAlphabet* al, bool need_R) {
+    if (!p || !a) { set_error("problem / alphabet pointer is NULL"); return AMPSM_EINVAL; }
+    if (a->K < 1 || a->K > AMPSM_MAX_K) { set_error("alphabet size K=%d outside 1..%d", a->K, AMPSM_MAX_K); return AMPSM_EINVAL; }
+    if (p->n < 1 || p->N < 1 || p->Nt < 1 || p->Na < 1 || p->Nr < 1 || p->Lin < 1 || p->Lout < 1 || p->max_iters < 1) {
+        set_error("non-positive dimension in ampsm_problem"); return AMPSM_EINVAL;
+    }
+    if (p->Nt % p->Na != 0) { set_error("Na=%d must divide Nt=%d (sectioned modes)", p->Na, p->Nt); return AMPSM_EINVAL; }
+    if (p->N != p->Nt * p->Lin || p->n != p->Nr * p->Lout) {
+        set_error("N must equal Nt*Lin and n must equal Nr*Lout (got N=%d n=%d)", p->N, p->n); return AMPSM_EINVAL;
+    }
+    if (need_R && (p->R < 1 || p->R > p->N)) { set_error("R=%d outside 1..N", p->R); return AMPSM_EINVAL; }
+    if (p->shift_mode == 1 && !p->exp_f64) { set_error("shift_mode=1 (reference shift) needs exp_f64=1"); return AMPSM_EINVAL; }
+    if (p->index_bits_kept < 0 || p->index_bits_kept > 64) { set_error("index_bits_kept outside 0..64"); return AMPSM_EINVAL; }
+    g->n = p->n; g->N = p->N; g->R = p->R;
+    g->Nt = p->Nt; g->Na = p->Na; g->Nr = p->Nr; g->Lin = p->Lin; g->Lout = p->Lout;
+    g->M = p->Nt / p->Na; g->L = p->Na * p->Lin;
+    g->max_iters = p->max_iters; g->early_exit = p->early_exit; g->shift_mode = p->shift_mode;
+    g->decision = p->decision; g->index_bits_kept = p->index_bits_kept; g->frame_base = p->frame_base;
+    al->K = a->K;
+    int sb = 0;
+    while ((1 << (sb + 1)) <= a->K) ++sb;            // int(log2(K)), config.py:119
+    al->sbits = sb;
+    for (int k = 0; k < AMPSM_MAX_K; ++k) {
+        const bool in = k < a->K;
+        al->gray[k] = in ? a->gray[k] : 0;
+        al->re[k] = in ? a->re[k] : 0.0;
+        al->im[k] = in ? a->im[k] : 0.0;
+        al->ref[k] = (float)al->re[k];
+        al->imf[k] = (float)al->im[k];
+    }
+    return 0;
+}
+
+static int check_loss_io(const void* x_true, const int64_t* sym, const int64_t* idx) {
+    const int have = (x_true != nullptr) + (sym != nullptr) + (idx != nullptr);
+    if (have != 0 && have != 3) { set_error("x_true, sym_true and idx_true must be given together"); return AMPSM_EINVAL; }
+    return 0;
+}
+
+// ---- host-buffer runner: chunks of frames, two streams, grow-only per-device arenas ---------------------------
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t cap = 0;
+    size_t used = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        if (int e = check_cuda(cudaMalloc((void**)&base, bytes), "cudaMalloc(host-path arena)")) return e;
+        cap = bytes;
+        return 0;
+    }
+    void* take(size_t bytes) {
+        unsigned char* p = base + used;
+        used += (bytes + 255) & ~size_t(255);
+        return p;
+    }
+};
+struct DeviceCtx {
+    std::mutex mu;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    Arena slot[2], shared;
+};
+static DeviceCtx* device_ctx(int device) {
+    static std::mutex mu;
+    static std::vector<DeviceCtx*> ctx;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)ctx.size() <= device) ctx.resize(device + 1, nullptr);
+    if (!ctx[device]) ctx[device] = new DeviceCtx();
+    return ctx[device];
+}
+
+struct Field {
+    const void* h_in;
+    void* h_out;
+    size_t bpf;      // bytes per frame
+};
+using LaunchFn = std::function<int(long long f0, long long nf, void* const* d, unsigned long long* d_counters,
+                                   void* scratch, cudaStream_t st)>;
+
+static int run_host(int device, long long frames, const std::vector<Field>& fields,
+                    const std::vector<std::pair<const void*, size_t>>& shared_in, std::vector<void*>* shared_dev,
+                    size_t scratch_per_frame, size_t scratch_fixed, uint64_t* h_counters, const LaunchFn& launch) {
+    if (int e = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return e;
+    DeviceCtx* cx = device_ctx(device);
+    std::lock_guard<std::mutex> lk(cx->mu);
+    for (int s = 0; s < 2; ++s)
+        if (!cx->stream[s])
+            if (int e = check_cuda(cudaStreamCreateWithFlags(&cx->stream[s], cudaStreamNonBlocking), "cudaStreamCreate")) return e;
+    size_t per_frame = scratch_per_frame;
+    for (const Field& f : fields) per_frame += ((f.h_in || f.h_out) ? f.bpf : 0);
+    if (per_frame == 0) per_frame = 1;
+    const size_t target = (size_t)96 << 20;                        // ~96 MiB of traffic per chunk
+    long long chunk = (long long)(target / per_frame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > frames) chunk = frames;
+    // shared inputs + counters
+    size_t shared_bytes = 256 + AMPSM_NUM_COUNTERS * 8;
+    for (auto& s : shared_in) shared_bytes += (s.second + 255) & ~size_t(255);
+    if (int e = cx->shared.reserve(shared_bytes)) return e;
+    cx->shared.used = 0;
+    unsigned long long* d_counters = (unsigned long long*)cx->shared.take(AMPSM_NUM_COUNTERS * 8);
+    if (int e = check_cuda(cudaMemsetAsync(d_counters, 0, AMPSM_NUM_COUNTERS * 8, cx->stream[0]), "memset counters")) return e;
+    shared_dev->clear();
+    for (auto& s : shared_in) {
+        void* d = s.first ? cx->shared.take(s.second) : nullptr;
+        if (d)
+            if (int e = check_cuda(cudaMemcpyAsync(d, s.first, s.second, cudaMemcpyHostToDevice, cx->stream[0]), "H2D shared")) return e;
+        shared_dev->push_back(d);
+    }
+    if (int e = check_cuda(cudaStreamSynchronize(cx->stream[0]), "sync shared inputs")) return e;
+    size_t slot_bytes = scratch_fixed + 256 + (size_t)chunk * scratch_per_frame + 256;
+    for (const Field& f : fields) slot_bytes += (((size_t)chunk * f.bpf) + 255) & ~size_t(255);
+    for (int s = 0; s < 2; ++s)
+        if (int e = cx->slot[s].reserve(slot_bytes)) return e;
+    int rc = 0;
+    int which = 0;
+    for (long long f0 = 0; f0 < frames && rc == 0; f0 += chunk, which ^= 1) {
+        const long long nf = (frames - f0 < chunk) ? frames - f0 : chunk;
+        Arena& ar = cx->slot[which];
+        cudaStream_t st = cx->stream[which];
+        ar.used = 0;                                              // stream order protects the previous use of this slot
+        std::vector<void*> d(fields.size(), nullptr);
+        for (size_t i = 0; i < fields.size(); ++i) {
+            const Field& f = fields[i];
+            if (!f.h_in && !f.h_out) continue;
+            d[i] = ar.take((size_t)chunk * f.bpf);
+            if (f.h_in)
+                rc = check_cuda(cudaMemcpyAsync(d[i], (const unsigned char*)f.h_in + (size_t)f0 * f.bpf, (size_t)nf * f.bpf,
+                                                cudaMemcpyHostToDevice, st), "H2D chunk");
+            if (rc) break;
+        }
+        if (rc) break;
+        void* scratch = (scratch_per_frame || scratch_fixed) ? ar.take(scratch_fixed + (size_t)chunk * scratch_per_frame) : nullptr;
+        rc = launch(f0, nf, d.data(), d_counters, scratch, st);
+        if (rc) break;
+        for (size_t i = 0; i < fields.size(); ++i) {
+            const Field& f = fields[i];
+            if (!f.h_out) continue;
+            rc = check_cuda(cudaMemcpyAsync((unsigned char*)f.h_out + (size_t)f0 * f.bpf, d[i], (size_t)nf * f.bpf,
+                                            cudaMemcpyDeviceToHost, st), "D2H chunk");
+            if (rc) break;
+        }
+    }
+    for (int s = 0; s < 2; ++s) {
+        const int e = check_cuda(cudaStreamSynchronize(cx->stream[s]), "sync host path");
+        if (!rc) rc = e;
+    }
+    if (!rc && h_counters) {
+        unsigned long long tmp[AMPSM_NUM_COUNTERS];
+        rc = check_cuda(cudaMemcpy(tmp, d_counters, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H counters");
+        if (!rc) {
+            for (int i = 0; i < 16; ++i) h_counters[i] += tmp[i];
+            for (int i = 16; i < 20; ++i) {
+                double a, b;
+                memcpy(&a, &h_counters[i], 8);
+                memcpy(&b, &tmp[i], 8);
+                a += b;
+                memcpy(&h_counters[i], &a, 8);
+            }
+        }
+    }
+    return rc;
+}
+
+}  // namespace ampsm
+
+using namespace ampsm;
+
+extern "C" {
+
+const char* ampsm_version(void) { return "ampsm_b200 0.1 (sm_100a)"; }
+const char* ampsm_last_error(void) { return g_err; }
+
+int ampsm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes) {
+    cudaDeviceProp prop;
+    if (int e = check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return e;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (smem_optin_bytes) *smem_optin_bytes = (int64_t)prop.sharedMemPerBlockOptin;
+    return 0;
+}
+
+int64_t ampsm_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int ampsm_probe_fp32_tflops(int device, double* tflops) { return probe_fp32(device, tflops); }
+
+// ---------------------------------------------------------------- BAMP
+int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H,
+                      int64_t H_frame_stride, const void* y, double sigma2, const float* sigma2_per_frame,
+                      const void* x_true, const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse,
+                      float* var, int32_t* iters, float* traj, uint64_t* counters, void* stream) {
+    BampArgs k{};
+    if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || (frames > 0 && (!H || !y))) { set_error("BAMP: H / y is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (H_frame_stride != 0 && H_frame_stride < (int64_t)p->n * p->N) { set_error("BAMP: H_frame_stride smaller than n*N"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    k.H = (const float2*)H; k.H_stride = H_frame_stride; k.y = (const float2*)y;
+    k.sigma2 = (float)sigma2; k.sigma2_pf = sigma2_per_frame;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0) {
+        const int rc = launch_bamp_fast(k, st);
+        if (rc != AMPSM_ENOFIT) return rc;
+        if (p->kernel == 2) return rc;
+    } else if (p->kernel == 2) {
+        set_error("BAMP fast kernel supports exp_f64=0, shift_mode=0 only");
+        return AMPSM_ENOFIT;
+    }
+    return launch_bamp_generic(k, p->exp_f64 != 0, st);
+}
+
+int ampsm_bamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H,
+                           int64_t H_frame_stride, const void* y, double sigma2, const float* sigma2_per_frame,
+                           const void* x_true, const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse,
+                           float* var, int32_t* iters, float* traj, uint64_t* counters, int device) {
+    if (!p || !a) { set_error("problem / alphabet pointer is NULL"); return AMPSM_EINVAL; }
+    if (frames <= 0) return frames < 0 ? AMPSM_EINVAL : 0;
+    const size_t nN = (size_t)p->n * p->N, L = (size_t)p->Na * p->Lin;
+    const bool per_frame_H = H_frame_stride != 0;
+    if (per_frame_H && H_frame_stride != (int64_t)nN) { set_error("host path needs densely packed per-frame H"); return AMPSM_EINVAL; }
+    std::vector<Field> f = {
+        {per_frame_H ? H : nullptr, nullptr, nN * 8},          // 0
+        {y, nullptr, (size_t)p->n * 8},                        // 1
+        {sigma2_per_frame, nullptr, 4},                        // 2
+        {x_true, nullptr, (size_t)p->N * 8},                   // 3
+        {sym_true, nullptr, L * 8},                            // 4
+        {idx_true, nullptr, L * 8},                            // 5
+        {nullptr, xmap, (size_t)p->N * 8},                     // 6
+        {nullptr, xmmse, (size_t)p->N * 8},                    // 7
+        {nullptr, var, (size_t)p->N * 4},                      // 8
+        {nullptr, iters, 4},                                   // 9
+        {nullptr, traj, (size_t)p->max_iters * 12},            // 10
+    };
+    std::vector<std::pair<const void*, size_t>> shared = {{per_frame_H ? nullptr : H, nN * 8}};
+    std::vector<void*> sd;
+    return run_host(device, frames, f, shared, &sd, 0, 0, counters,
+                    [&](long long f0, long long nf, void* const* d, unsigned long long* dc, void*, cudaStream_t st) {
+                        ampsm_problem q = *p;
+                        q.frame_base = p->frame_base + f0;
+                        return ampsm_bamp_detect(&q, a, nf, per_frame_H ? d[0] : sd[0], per_frame_H ? (int64_t)nN : 0, d[1], sigma2,
+                                                 (const float*)d[2], d[3], (const int64_t*)d[4], (const int64_t*)d[5], d[6], d[7],
+                                                 (float*)d[8], (int32_t*)d[9], (float*)d[10], (uint64_t*)dc, st);
+                    });
+}
+
+// ---------------------------------------------------------------- VAMP
+int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double, const void* U,
+                      int64_t U_frame_stride, const void* s, int64_t s_frame_stride, const void* Vh, int64_t Vh_frame_stride,
+                      const void* y, double sigma2, const float* sigma2_per_frame, double sparsity, const void* x_true,
+                      const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* var, int32_t* iters,
+                      float* traj, uint64_t* counters, void* stream) {
+    VampArgs k{};
+    if (int e = make_geom(p, a, &k.g, &k.al, true)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || (frames > 0 && (!U || !s || !Vh || !y))) { set_error("VAMP: U / s / Vh / y is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    k.U = U; k.U_stride = U_frame_stride; k.s = s; k.s_stride = s_frame_stride; k.Vh = Vh; k.Vh_stride = Vh_frame_stride;
+    k.y = y; k.sigma2_d = sigma2; k.sigma2_pf = sigma2_per_frame; k.sparsity = sparsity;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
+    return launch_vamp_generic(k, is_double != 0, p->exp_f64 != 0, (cudaStream_t)stream);
+}
+
+int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double, const void* U,
+                           int64_t U_frame_stride, const void* s, int64_t s_frame_stride, const void* Vh,
+                           int64_t Vh_frame_stride, const void* y, double sigma2, const float* sigma2_per_frame,
+                           double sparsity, const void* x_true, const int64_t* sym_true, const int64_t* idx_true, void* xmap,
+                           void* xmmse, float* var, int32_t* iters, float* traj, uint64_t* counters, int device) {
+    if (!p || !a) { set_error("problem / alphabet pointer is NULL"); return AMPSM_EINVAL; }
+    if (frames <= 0) return frames < 0 ? AMPSM_EINVAL : 0;
+    const size_t cs = is_double ? 16 : 8, rs = is_double ? 8 : 4;
+    const size_t nR = (size_t)p->n * p->R, RN = (size_t)p->R * p->N, L = (size_t)p->Na * p->Lin;
+    const bool pfU = U_frame_stride != 0, pfs = s_frame_stride != 0, pfV = Vh_frame_stride != 0;
+    if ((pfU && U_frame_stride != (int64_t)nR) || (pfs && s_frame_stride != p->R) || (pfV && Vh_frame_stride != (int64_t)RN)) {
+        set_error("host path needs densely packed per-frame factors"); return AMPSM_EINVAL;
+    }
+    std::vector<Field> f = {
+        {pfU ? U : nullptr, nullptr, nR * cs},                 // 0
+        {pfs ? s : nullptr, nullptr, (size_t)p->R * rs},       // 1
+        {pfV ? Vh : nullptr, nullptr, RN * cs},                // 2
+        {y, nullptr, (size_t)p->n * cs},                       // 3
+        {sigma2_per_frame, nullptr, 4},                        // 4
+        {x_true, nullptr, (size_t)p->N * 8},                   // 5
+        {sym_true, nullptr, L * 8},                            // 6
+        {idx_true, nullptr, L * 8},                            // 7
+        {nullptr, xmap, (size_t)p->N * cs},                    // 8
+        {nullptr, xmmse, (size_t)p->N * 8},                    // 9
+        {nullptr, var, (size_t)p->N * 4},                      // 10
+        {nullptr, iters, 4},                                   // 11
+        {nullptr, traj, (size_t)p->max_iters * 12},            // 12
+    };
+    std::vector<std::pair<const void*, size_t>> shared = {
+        {pfU ? nullptr : U, nR * cs}, {pfs ? nullptr : s, (size_t)p->R * rs}, {pfV ? nullptr : Vh, RN * cs}};
+    std::vector<void*> sd;
+    return run_host(device, frames, f, shared, &sd, 0, 0, counters,
+                    [&](long long f0, long long nf, void* const* d, unsigned long long* dc, void*, cudaStream_t st) {
+                        ampsm_problem q = *p;
+                        q.frame_base = p->frame_base + f0;
+                        return ampsm_vamp_detect(&q, a, nf, is_double, pfU ? d[0] : sd[0], pfU ? (int64_t)nR : 0, pfs ? d[1] : sd[1],
+                                                 pfs ? p->R : 0, pfV ? d[2] : sd[2], pfV ? (int64_t)RN : 0, d[3], sigma2,
+                                                 (const float*)d[4], sparsity, d[5], (const int64_t*)d[6], (const int64_t*)d[7], d[8],
+                                                 d[9], (float*)d[10], (int32_t*)d[11], (float*)d[12], (uint64_t*)dc, st);
+                    });
+}
+
+// ---------------------------------------------------------------- SCAMP
+int64_t ampsm_scamp_workspace_bytes(const ampsm_problem* p, int64_t frames) {
+    Geom g{};
+    DevAlphabet al{};
+    ampsm_alphabet dummy{};
+    dummy.K = 1;
+    if (make_geom(p, &dummy, &g, &al, false)) return -1;
+    return scamp_workspace_bytes(g, frames);
+}
+
+int ampsm_scamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const float* W, const void* A,
+                       const void* y, double sigma2, const float* sigma2_per_frame, const void* x_true,
+                       const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* psi, int32_t* iters,
+                       float* traj, uint64_t* counters, void* workspace, void* stream) {
+    ScampArgs k{};
+    if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || (frames > 0 && (!W || !A || !y))) { set_error("SCAMP: W / A / y is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    k.W = W; k.A = (const float2*)A; k.y = (const float2*)y; k.sigma2 = (float)sigma2; k.sigma2_pf = sigma2_per_frame;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.psi = psi; k.iters = iters; k.traj = traj; k.frames = frames;
+    k.workspace = workspace;
+    return launch_scamp(k, p->exp_f64 != 0, (cudaStream_t)stream);
+}
+
+int ampsm_scamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const float* W, const void* A,
+                            const void* y, double sigma2, const float* sigma2_per_frame, const void* x_true,
+                            const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* psi,
+                            int32_t* iters, float* traj, uint64_t* counters, int device) {
+    if (!p || !a) { set_error("problem / alphabet pointer is NULL"); return AMPSM_EINVAL; }
+    if (frames <= 0) return frames < 0 ? AMPSM_EINVAL : 0;
+    const size_t L = (size_t)p->Na * p->Lin;
+    std::vector<Field> f = {
+        {y, nullptr, (size_t)p->n * 8},                        // 0
+        {sigma2_per_frame, nullptr, 4},                        // 1
+        {x_true, nullptr, (size_t)p->N * 8},                   // 2
+        {sym_true, nullptr, L * 8},                            // 3
+        {idx_true, nullptr, L * 8},                            // 4
+        {nullptr, xmap, (size_t)p->N * 8},                     // 5
+        {nullptr, xmmse, (size_t)p->N * 8},                    // 6
+        {nullptr, psi, (size_t)p->Lin * 4},                    // 7
+        {nullptr, iters, 4},                                   // 8
+        {nullptr, traj, (size_t)p->max_iters * 12},            // 9
+    };
+    std::vector<std::pair<const void*, size_t>> shared = {{W, (size_t)p->Lout * p->Lin * 4}, {A, (size_t)p->n * p->N * 8}};
+    std::vector<void*> sd;
+    // workspace per frame: see ws_layout (Xh, Z, Zs, Xmap, scalars, denoiser scratch) -- bounded by this estimate
+    const size_t ws_pf = (size_t)p->N * (8 + 8 + 24) + (size_t)p->n * 16 + (size_t)(p->Lin + p->Lout) * 8 + 64;
+    const size_t ws_fixed = ((size_t)(p->n / 32 + 1) * (p->N / 32 + 1)) + 16 * 256;
+    return run_host(device, frames, f, shared, &sd, ws_pf, ws_fixed, counters,
+                    [&](long long f0, long long nf, void* const* d, unsigned long long* dc, void* scratch, cudaStream_t st) {
+                        ampsm_problem q = *p;
+                        q.frame_base = p->frame_base + f0;
+                        if (ampsm_scamp_workspace_bytes(&q, nf) > (int64_t)(ws_fixed + (size_t)nf * ws_pf)) scratch = nullptr;
+                        return ampsm_scamp_detect(&q, a, nf, (const float*)sd[0], sd[1], d[0], sigma2, (const float*)d[1], d[2],
+                                                  (const int64_t*)d[3], (const int64_t*)d[4], d[5], d[6], (float*)d[7],
+                                                  (int32_t*)d[8], (float*)d[9], (uint64_t*)dc, scratch, st);
+                    });
+}
+
+// ---------------------------------------------------------------- Loss
+int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* xmap, const void* xmmse,
+                     const void* x_true, const int64_t* sym_true, const int64_t* idx_true, const int32_t* iters,
+                     uint64_t* counters, void* stream) {
+    LossArgs k{};
+    if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
+    if (!xmap || !xmmse || !x_true || !sym_true || !idx_true || !counters) { set_error("Loss: NULL pointer"); return AMPSM_EINVAL; }
+    if (frames <= 0) return frames < 0 ? AMPSM_EINVAL : 0;
+    k.xmap = (const float2*)xmap; k.xmmse = (const float2*)xmmse; k.iters = iters;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.frames = frames;
+    return launch_loss(k, (cudaStream_t)stream);
+}
+
+}  // extern "C"

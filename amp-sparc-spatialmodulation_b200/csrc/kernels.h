@@ -1,0 +1,84 @@
+// Kernel argument blocks and launchers (internal; the public surface is include/ampsm_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace ampsm {
+
+struct BampArgs {
+    Geom g;
+    DevAlphabet al;
+    const float2* H;
+    long long H_stride;          // complex elements between frames, 0 = shared
+    const float2* y;
+    float sigma2;
+    const float* sigma2_pf;
+    LossIO io;
+    float2* xmap;
+    float2* xmmse;
+    float* var;
+    int* iters;
+    float* traj;
+    long long frames;
+    int stage_H;
+};
+
+struct VampArgs {
+    Geom g;
+    DevAlphabet al;
+    const void* U;               // [n][R] complex64 / complex128
+    long long U_stride;
+    const void* s;               // [R] float / double
+    long long s_stride;
+    const void* Vh;              // [R][N]
+    long long Vh_stride;
+    const void* y;               // [frames][n]
+    double sigma2_d;             // python float in the reference (vamp.py:19)
+    const float* sigma2_pf;
+    double sparsity;
+    LossIO io;
+    void* xmap;                  // complex64, or complex128 in the double variant
+    float2* xmmse;
+    float* var;
+    int* iters;
+    float* traj;
+    long long frames;
+    int stage_Vh;
+};
+
+struct ScampArgs {
+    Geom g;
+    DevAlphabet al;
+    const float* W;              // [Lout][Lin]
+    const float2* A;             // [n][N]
+    const float2* y;             // [frames][n]
+    float sigma2;
+    const float* sigma2_pf;
+    LossIO io;
+    float2* xmap;
+    float2* xmmse;
+    float* psi;
+    int* iters;
+    float* traj;
+    long long frames;
+    void* workspace;
+};
+
+struct LossArgs {
+    Geom g;
+    DevAlphabet al;
+    const float2* xmap;
+    const float2* xmmse;
+    const int* iters;
+    LossIO io;
+    long long frames;
+};
+
+int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
+int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
+int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
+int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
+long long scamp_workspace_bytes(const Geom& g, long long frames);
+int launch_loss(const LossArgs& a, cudaStream_t stream);
+int probe_fp32(int device, double* tflops);
+
+}  // namespace ampsm

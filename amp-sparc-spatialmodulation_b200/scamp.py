@@ -1,0 +1,45 @@
+"""SCAMP (SPARC-AMP) detector with the reference call signature (/root/reference/scamp.py:70-108), on sm_100a.
+
+``SCAMP(config)(W, A, y, SNR, x, symbol, index) -> Loss``: base matrix W (Lout, Lin), design matrix A (n, N)
+shared by the F frames of the call, so both mat-vecs of an iteration become complex GEMMs over the frame batch
+(csrc/scamp.cu); zero tiles of the band-structured A are skipped.
+"""
+import torch
+
+from . import _cabi
+from ._detect import Detection, Detector, ptr
+
+
+class SCAMP(Detector):
+    def detect(self, W, A, y, SNR, x=None, symbol=None, index=None, frame_base=0) -> Detection:
+        dev = self._cuda_device(y, A)
+        cfg = self.config
+        n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
+        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        F = y.shape[0]
+        W = W.to(dev, torch.float32).contiguous()
+        A = A.to(dev, torch.complex64).contiguous()
+        if tuple(A.shape) != (n, N) or tuple(W.shape) != (cfg.Lout, cfg.Lin):
+            raise RuntimeError(f"expected W ({cfg.Lout}, {cfg.Lin}) and A ({n}, {N}); got {tuple(W.shape)}, {tuple(A.shape)}")
+        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        sym, idx = self._labels(symbol, index, dev) if xt is not None else (None, None)
+        counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        iters = torch.empty(F, dtype=torch.int32, device=dev)
+        xmap = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        xmmse = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        psi = torch.empty(F, cfg.Lin, 1, dtype=torch.float32, device=dev) if self.outputs else None
+        traj = torch.empty(F, cfg.N_Layers, 3, dtype=torch.float32, device=dev) if self.trajectory else None
+        prob = self._problem(F, frame_base=frame_base)
+        lib = _cabi.lib()
+        ws = torch.empty(int(lib.ampsm_scamp_workspace_bytes(prob, F)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ampsm_scamp_detect(
+                prob, self._alphabet, F, W.data_ptr(), A.data_ptr(), y.data_ptr(), float(self.E / SNR), None, ptr(xt),
+                ptr(sym), ptr(idx), ptr(xmap), ptr(xmmse), ptr(psi), iters.data_ptr(), ptr(traj), counters.data_ptr(),
+                ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ampsm_scamp_detect")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return Detection(F, counters, iters, xmap, xmmse, psi, traj)
+
+    def forward(self, W, A, y, SNR, x, symbol, index):
+        return self._wrap(self.detect(W, A, y, SNR, x, symbol, index))

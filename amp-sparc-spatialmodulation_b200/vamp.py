@@ -1,0 +1,56 @@
+"""VAMP detector with the reference call signature (/root/reference/vamp.py:151-191), running on sm_100a.
+
+``VAMP(config)(U, s, Vh, y, SNR, x, symbols, indices) -> Loss`` with the caller's thin SVD (vamp_model.py:58).
+Factors may be shared by the call -- U (n, R), s (R,), Vh (R, N) -- or given per frame with a leading frame
+axis.  complex128 factors select the float64 linear stage (the reference fed with upcast inputs); ``xmmse`` /
+``var`` are complex64 / float32 in both cases (vamp.py:119).  Loss is fed ``r`` as xmap (vamp.py:187).
+"""
+import torch
+
+from . import _cabi
+from ._detect import Detection, Detector, ptr
+
+
+class VAMP(Detector):
+    def __init__(self, config, **kw) -> None:
+        super().__init__(config, **kw)
+        self.sparsity = config.Na / config.Nt              # vamp.py:155
+
+    def detect(self, U, s, Vh, y, SNR, x=None, symbols=None, indices=None, frame_base=0) -> Detection:
+        dev = self._cuda_device(y, Vh, U)
+        cfg = self.config
+        n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
+        dbl = Vh.dtype == torch.complex128
+        ct, rt = (torch.complex128, torch.float64) if dbl else (torch.complex64, torch.float32)
+        y = y.to(dev, ct).reshape(-1, n).contiguous()
+        F = y.shape[0]
+        U, s, Vh = U.to(dev, ct).contiguous(), s.to(dev, rt).contiguous(), Vh.to(dev, ct).contiguous()
+        R = Vh.shape[-2]
+        if tuple(Vh.shape[-2:]) != (R, N) or tuple(U.shape[-2:]) != (n, R) or s.shape[-1] != R:
+            raise RuntimeError(f"factor shapes U{tuple(U.shape)} s{tuple(s.shape)} Vh{tuple(Vh.shape)} do not match n={n}, N={N}")
+        def stride(t, base_dim, size):
+            if t.dim() == base_dim:
+                return 0
+            if t.dim() == base_dim + 1 and t.shape[0] == F:
+                return size
+            raise RuntimeError(f"factor with shape {tuple(t.shape)} is neither shared nor per-frame for {F} frames")
+        sU, ss, sV = stride(U, 2, n * R), stride(s, 1, R), stride(Vh, 2, R * N)
+        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
+        counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        iters = torch.empty(F, dtype=torch.int32, device=dev)
+        xmap = torch.empty(F, N, 1, dtype=ct, device=dev) if self.outputs else None
+        xmmse = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        var = torch.empty(F, N, 1, dtype=torch.float32, device=dev) if self.outputs else None
+        traj = torch.empty(F, cfg.N_Layers, 3, dtype=torch.float32, device=dev) if self.trajectory else None
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().ampsm_vamp_detect(
+                self._problem(F, R=R, frame_base=frame_base), self._alphabet, F, 1 if dbl else 0, U.data_ptr(), sU,
+                s.data_ptr(), ss, Vh.data_ptr(), sV, y.data_ptr(), float(self.E / SNR), None, float(self.sparsity),
+                ptr(xt), ptr(sym), ptr(idx), ptr(xmap), ptr(xmmse), ptr(var), iters.data_ptr(), ptr(traj),
+                counters.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ampsm_vamp_detect")
+        return Detection(F, counters, iters, xmap, xmmse, var, traj)
+
+    def forward(self, U, s, Vh, y, SNR, x, symbols, indices):
+        return self._wrap(self.detect(U, s, Vh, y, SNR, x, symbols, indices))

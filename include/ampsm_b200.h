@@ -1,0 +1,178 @@
+/*
+ * ampsm_b200.h -- C ABI of libampsm_b200.so: B200 (sm_100a) kernels for the BAMP / SCAMP / VAMP
+ * spatial-modulation detector hot path of AhmedKishki/AMP-SPARC-SpatialModulation.
+ *
+ * The reference has no FFI: the path sits behind Python nn.Module objects.  Each entry
+ * point below names the reference interface it replaces; the Python classes in
+ * amp-sparc-spatialmodulation_b200/{bamp,vamp,scamp,loss}.py bind these symbols with ctypes and keep the
+ * reference's call signatures.  INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - complex64 = interleaved float {re,im}; complex128 = interleaved double; matrices row-major.
+ *   - "frame" = one reference call with batch=1 (per-frame soft-max shift, exit test and pooled variance).
+ *   - *_detect  : every pointer is DEVICE memory, work is enqueued on `stream` (a cudaStream_t) and the call
+ *                 returns without synchronising; the caller owns all buffers; calls on different streams may run
+ *                 concurrently.  Optional outputs may be NULL.
+ *   - *_detect_host : every pointer is HOST memory; the call copies inputs to the device in chunks (copies
+ *                 overlapped with the kernels), runs the same kernels, copies the results back and
+ *                 synchronises before returning.
+ *   - return value: 0 on success, otherwise a negative AMPSM_E* code or a positive cudaError_t;
+ *     ampsm_last_error() returns a message for the calling thread.
+ */
+#ifndef AMPSM_B200_H
+#define AMPSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPSM_MAX_K 16          /* largest alphabet of the reference (config.py:78-115) */
+#define AMPSM_NUM_COUNTERS 24   /* 64-bit words in a counter block, see below */
+
+#define AMPSM_EINVAL   (-1)     /* bad argument (dimension, NULL pointer, unsupported combination) */
+#define AMPSM_ENOFIT   (-2)     /* problem does not fit the requested kernel */
+#define AMPSM_ENODEV   (-3)     /* no sm_100 device */
+
+/* Constellation exactly as config.symbols (complex128, config.py:117) and config.gray. */
+typedef struct {
+    int32_t K;
+    int32_t gray[AMPSM_MAX_K];
+    double  re[AMPSM_MAX_K];
+    double  im[AMPSM_MAX_K];
+} ampsm_alphabet;
+
+/* Problem geometry and behaviour switches shared by all detectors. */
+typedef struct {
+    int32_t n;               /* rows of H / A:  Nr*Lout                                  (config.py:137) */
+    int32_t N;               /* columns:        Nt*Lin                                                    */
+    int32_t R;               /* VAMP only: number of singular values, min(n, N)         (vamp.py:28)      */
+    int32_t Nt, Na, Nr;      /* antennas; section size M = Nt/Na, sections per frame L = Na*Lin            */
+    int32_t Lin, Lout;       /* time slots in / out (SCAMP: Lc, Lr)                     (config.py:62-66) */
+    int32_t max_iters;       /* config.N_Layers                                          (config.py:147)  */
+    int32_t early_exit;      /* 1: per-frame torch.allclose exit (bamp.py:140), 0: exactly max_iters       */
+    int32_t shift_mode;      /* 0: per-section max shift (finite everywhere);
+                                1: frame-global max|x| in float64 as bamp.py:70 (NaN-faithful, slower)     */
+    int32_t exp_f64;         /* 1: denoiser exponents/exp in float64 as the reference; 0: float32 exp      */
+    int32_t decision;        /* 0: MAP decision (loss.py:282-302, mode 'sparc'); 1: segmented (223-250)    */
+    int32_t index_bits_kept; /* low bits of the index XOR that Loss.de2bi keeps (loss.py:20,168)           */
+    int32_t kernel;          /* 0: auto, 1: generic shared-memory kernel, 2: register-resident fast kernel */
+    int32_t reserved0;
+    int64_t frame_base;      /* global index of the first frame of this call (flat indices, loss.py:300)   */
+} ampsm_problem;
+
+/*
+ * Counter block (AMPSM_NUM_COUNTERS 64-bit words), ACCUMULATED into by every call (zero it first):
+ *   [0] frames          [1] frames with any wrong entry (loss.py:150)
+ *   [2] wrong time slots (loss.py:133)   [3] slot 0   [4] slot Lin/2   [5] last slot (loss.py:134-136)
+ *   [6] wrong indices (loss.py:165)      [7] wrong Gray labels (loss.py:166)
+ *   [8] index bit errors (loss.py:168)   [9] symbol bit errors (loss.py:172)
+ *   [10] executed iterations summed over frames   [11] frames whose estimate holds a NaN
+ *   [12..15] reserved
+ *   [16] sum |xmmse - x|^2 (double)  [17] slot 0  [18] slot Lin/2  [19] last slot (loss.py:116-119)
+ *   [20..23] reserved
+ */
+
+/* Library / device info. */
+const char* ampsm_version(void);
+const char* ampsm_last_error(void);
+int ampsm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+
+/*
+ * BAMP -- replaces bamp.BAMP.forward (bamp.py:116-143): Tracker init (12-25), up to max_iters BAMPLayer
+ * iterations (59-64) with the section-wise denoiser (66-77), the allclose exit (140) and, when x_true is
+ * given, Loss on (xmap, xmmse) (142; loss.py:67-179).
+ *   H      : complex64 [n][N] shared by all frames (H_frame_stride = 0) or [frames][n][N]
+ *            (H_frame_stride = n*N, in complex elements)
+ *   y      : complex64 [frames][n]
+ *   sigma2 : noise variance (Na/Nr)/SNR (bamp.py:111,134); sigma2_per_frame (device float[frames]) overrides
+ *            the scalar when not NULL
+ *   x_true : complex64 [frames][N], sym_true/idx_true : int64 [frames][L] Gray labels / flat non-zero
+ *            positions as returned by Data.generate_message (data.py:88-90); all three NULL => no Loss
+ *   xmap, xmmse : complex64 [frames][N];  var : float [frames][N];  iters : int32 [frames]
+ *   traj   : float [frames][max_iters][3] = {mean tau, mean var, mean |xmmse-x|^2} per executed iteration
+ *   counters : uint64 [AMPSM_NUM_COUNTERS] (see above)
+ */
+int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                      const void* H, int64_t H_frame_stride, const void* y,
+                      double sigma2, const float* sigma2_per_frame,
+                      const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                      void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                      uint64_t* counters, void* stream);
+
+int ampsm_bamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                           const void* H, int64_t H_frame_stride, const void* y,
+                           double sigma2, const float* sigma2_per_frame,
+                           const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                           void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                           uint64_t* counters, int device);
+
+/*
+ * VAMP -- replaces vamp.VAMP.forward (vamp.py:159-191): Tracker (12-28), VAMPLayer iterations (66-94) with
+ * the un-halved scalar-variance denoiser (96-119), exit on var (185), Loss on (r, xmmse) (187).
+ *   U [n][R], s [R], Vh [R][N]: the caller's thin SVD (vamp_model.py:58), shared (stride 0) or per frame
+ *   (strides in elements).  is_double = 1: U, Vh, y are complex128 and s is float64 (the reference fed with
+ *   upcast inputs); xmap is then complex128, xmmse/var stay complex64/float32 (vamp.py:119).
+ *   sparsity = Na/Nt (vamp.py:25-26).  traj : float [frames][max_iters][3] = {sigma2_tilde, mean var, mse}.
+ */
+int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double,
+                      const void* U, int64_t U_frame_stride, const void* s, int64_t s_frame_stride,
+                      const void* Vh, int64_t Vh_frame_stride, const void* y,
+                      double sigma2, const float* sigma2_per_frame, double sparsity,
+                      const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                      void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                      uint64_t* counters, void* stream);
+
+int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double,
+                           const void* U, int64_t U_frame_stride, const void* s, int64_t s_frame_stride,
+                           const void* Vh, int64_t Vh_frame_stride, const void* y,
+                           double sigma2, const float* sigma2_per_frame, double sparsity,
+                           const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                           void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                           uint64_t* counters, int device);
+
+/*
+ * SCAMP -- replaces scamp.SCAMP.forward (scamp.py:77-108): Tracker (8-25), SCAMPLayer iterations (43-59) with
+ * the mean-only denoiser (61-68), exit on psi (105), Loss on (xmap, xmmse) (107).
+ *   W : float [Lout][Lin] base matrix; A : complex64 [n][N] design matrix shared by all frames of the call
+ *   workspace : device scratch of ampsm_scamp_workspace_bytes(p, frames) bytes (NULL: the library allocates
+ *   and frees on the stream).  psi : float [frames][Lin] optional output.
+ *   traj : float [frames][max_iters][3] = {mean tau, mean psi, mse}.
+ */
+int64_t ampsm_scamp_workspace_bytes(const ampsm_problem* p, int64_t frames);
+int ampsm_scamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                       const float* W, const void* A, const void* y,
+                       double sigma2, const float* sigma2_per_frame,
+                       const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                       void* xmap, void* xmmse, float* psi, int32_t* iters, float* traj,
+                       uint64_t* counters, void* workspace, void* stream);
+
+int ampsm_scamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                            const float* W, const void* A, const void* y,
+                            double sigma2, const float* sigma2_per_frame,
+                            const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                            void* xmap, void* xmmse, float* psi, int32_t* iters, float* traj,
+                            uint64_t* counters, int device);
+
+/*
+ * Loss -- replaces loss.Loss.error_rate (loss.py:67-103) for estimates already on the device: hard decision
+ * (MAP 282-302 or segmented 223-250) and the counters above.  iters may be NULL.
+ */
+int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                     const void* xmap, const void* xmmse, const void* x_true,
+                     const int64_t* sym_true, const int64_t* idx_true, const int32_t* iters,
+                     uint64_t* counters, void* stream);
+
+/*
+ * Measurement helpers (bench.py): FP32 FFMA throughput of the device in TFLOP/s (the roofline denominator for
+ * the shared-memory / register resident iterations, which MEASURED_PEAKS.json does not hold), and the number of
+ * kernel launches this library has made since the last reset (bench.py's gpu_launches).
+ */
+int ampsm_probe_fp32_tflops(int device, double* tflops);
+int64_t ampsm_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPSM_B200_H */

@@ -1,0 +1,304 @@
+"""CPU oracle for the BAMP / SCAMP / VAMP iteration loops -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A numpy restatement of the reference's detector hot path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this package; the shipped detectors never
+do (they call the CUDA library and fail loudly when it is missing).
+
+What it follows (reference file:line, all under /root/reference):
+  * ``sm_denoiser``   -> bamp.py:66-77 (mean + variance, tau halved), scamp.py:61-68 (mean only, tau halved),
+                         vamp.py:96-119 (scalar tau, NOT halved)
+  * ``bamp_detect``   -> bamp.py:12-25 (state), 59-64 (one iteration), 116-143 (loop + allclose exit)
+  * ``scamp_detect``  -> scamp.py:8-25, 43-59, 77-108
+  * ``vamp_detect``   -> vamp.py:12-28, 66-94, 159-191
+
+Frame semantics: the reference couples the frames of a batch (batch-global soft-max shift bamp.py:70, batch-global
+exit bamp.py:140, batch-pooled variance vamp.py:85) and is numerically unusable for B>1, so a
+"frame" here is ONE reference call with ``batch=1``: per-frame shift, per-frame exit, per-frame pooled variance.
+The functions are vectorised over frames but every frame evolves exactly as its own batch=1 call would.
+
+Arithmetic follows the reference's dtypes: mat-vecs and state in complex64/float32, the denoiser internals in
+float64 on the complex64-rounded ``s/tau`` (symbols are complex128 in the reference, bamp.py:41), results rounded
+back to complex64/float32 every iteration.  Summation order inside BLAS differs between libraries, so agreement
+with the reference is to rounding (1e-6 relative per iteration), not bit-exact.
+
+Parity pinning: the reference ships no tests or golden vectors for this path.  This oracle is
+pinned against outputs of the reference itself, run in the build container on fixed-seed inputs and committed
+under ``tests/golden`` by ``tests/golden/make_golden.py`` (see tests/test_oracle_golden.py).
+"""
+import numpy as np
+
+F32 = np.float32
+C64 = np.complex64
+
+# torch.allclose defaults (bamp.py:140)
+RTOL, ATOL = F32(1e-5), F32(1e-8)
+# vamp.py:51-54
+VAR_RATIO_MIN = F32(1.0e-5)
+VAR_RATIO_MAX = F32(1.0) - F32(1.0e-5)
+VAR_MIN, VAR_MAX = F32(1.0e-9), F32(1.0e5)
+
+
+def _allclose_rows(new, old):
+    """Per-frame torch.allclose(new, old): all |new-old| <= atol + rtol*|old|; NaN never closes."""
+    with np.errstate(invalid='ignore'):
+        ok = np.abs(new - old) <= ATOL + RTOL * np.abs(old)
+    return ok.reshape(ok.shape[0], -1).all(axis=1)
+
+
+def sm_denoiser(s, tau, symbols, L, M, halve_tau, shift='reference', want_var=True):
+    """Section-wise spatial-modulation posterior mean (and variance).
+
+    s: (F, L*M) complex64; tau: broadcastable to (F, L*M) float32; symbols: (K,) complex128.
+    shift='reference' subtracts the frame-global max|x| (bamp.py:70, can yield NaN for L>1 at high SNR,
+    SURVEY.md App. B.2); shift='section' subtracts each section's own maximum (finite everywhere, identical
+    wherever the reference is finite).
+    """
+    F = s.shape[0]
+    K = symbols.shape[0]
+    s4 = np.ascontiguousarray(s, dtype=C64).reshape(F, L, M, 1)
+    tau4 = np.broadcast_to(np.asarray(tau, dtype=F32).reshape(F, -1), (F, L * M)).reshape(F, L, M, 1)
+    if halve_tau:
+        tau4 = tau4 / F32(2)
+    with np.errstate(all='ignore'):
+        q = (s4 / tau4).astype(C64)                                   # complex64 division, as the reference
+        sym = symbols.astype(np.complex128).reshape(1, 1, 1, K)
+        x = (q.astype(np.complex128) * sym.conj()).real               # float64 from here on
+        if shift == 'reference':
+            ref = np.abs(x).reshape(F, -1).max(axis=1).reshape(F, 1, 1, 1)
+        else:
+            ref = x.reshape(F, L, M * K).max(axis=2).reshape(F, L, 1, 1)
+        eta = np.exp(x - ref)
+        per_antenna = eta.sum(axis=-1)                                 # (F, L, M)
+        norm = per_antenna.sum(axis=2, keepdims=True)                  # (F, L, 1)
+        xmmse = (sym * eta).sum(axis=-1) / norm
+        out_mean = xmmse.reshape(F, L * M).astype(C64)
+        if not want_var:
+            return out_mean
+        var0 = np.abs(xmmse) ** 2 * (1 - per_antenna / norm)
+        spread = (np.abs(xmmse[..., None] - sym) ** 2 * eta).sum(axis=-1) / norm
+        var = var0 + spread
+    return out_mean, var.reshape(F, L * M).astype(F32)
+
+
+def _mse(xmmse, x_true):
+    d = xmmse - x_true
+    return (d.real.astype(np.float64) ** 2 + d.imag.astype(np.float64) ** 2).mean(axis=1)
+
+
+def bamp_detect(H, y, sigma2, symbols, L, M, max_iters, early_exit=True, shift='reference', x_true=None):
+    """BAMP over F frames.  H: (n,N) shared or (F,n,N) per frame, complex64; y: (F,n) complex64.
+
+    Returns dict(xmap, xmmse, var, iters, traj) -- ``traj`` holds per-iteration per-frame
+    ``tau`` (mean effective noise variance), ``var`` (mean posterior variance) and, when ``x_true`` is given,
+    ``mse``; entries of frames that already exited repeat their last value.
+    """
+    y = np.ascontiguousarray(y, dtype=C64)
+    F, n = y.shape
+    H = np.ascontiguousarray(H, dtype=C64)
+    shared = H.ndim == 2
+    N = H.shape[-1]
+    P = (np.abs(H) ** 2).astype(F32)                                   # bamp.py:18
+    Hh = np.conj(np.swapaxes(H, -1, -2))
+    Pt = np.swapaxes(P, -1, -2)
+    sigma2 = np.broadcast_to(np.asarray(sigma2, dtype=F32).reshape(-1, 1), (F, 1))
+
+    xmmse = np.zeros((F, N), C64)
+    var = np.ones((F, N), F32)
+    z = y.copy()
+    u = np.zeros((F, n), F32) + sigma2                                 # v=0 at start (bamp.py:22,25)
+    xmap = np.zeros((F, N), C64)
+    cov = np.zeros((F, N), F32)
+    iters = np.zeros(F, np.int32)
+    active = np.arange(F)
+    traj = {k: np.full((max_iters, F), np.nan) for k in ('tau', 'var', 'mse')}
+
+    def mv(Mat, vec, idx):
+        if shared:
+            return vec @ Mat.T
+        return np.matmul(Mat[idx], vec[..., None])[..., 0]
+
+    for t in range(max_iters):
+        a = active
+        if a.size == 0:
+            break
+        with np.errstate(all='ignore'):
+            v = mv(P, var[a], a).astype(F32)                           # bamp.py:59
+            resid = y[a] - z[a]
+            z_new = (mv(H, xmmse[a], a) - v * resid / u[a]).astype(C64)  # bamp.py:60 (old u, new v)
+            u_new = (v + sigma2[a]).astype(F32)                        # bamp.py:61
+            cov_a = (F32(1) / mv(Pt, (F32(1) / u_new).astype(F32), a)).astype(F32)   # bamp.py:62
+            g = ((y[a] - z_new) / u_new).astype(C64)
+            xmap_a = (xmmse[a] + cov_a * mv(Hh, g, a)).astype(C64)     # bamp.py:63
+            xm, vr = sm_denoiser(xmap_a, cov_a, symbols, L, M, True, shift)   # bamp.py:64
+        done = _allclose_rows(vr, var[a])
+        z[a], u[a], xmap[a], cov[a], xmmse[a], var[a] = z_new, u_new, xmap_a, cov_a, xm, vr
+        iters[a] = t + 1
+        traj['tau'][t:, a] = cov_a.mean(axis=1, dtype=np.float64)
+        traj['var'][t:, a] = vr.mean(axis=1, dtype=np.float64)
+        if x_true is not None:
+            traj['mse'][t:, a] = _mse(xm, x_true[a])
+        if early_exit:
+            active = a[~done]
+    return dict(xmap=xmap, xmmse=xmmse, var=var, cov=cov, iters=iters, traj=traj)
+
+
+def scamp_detect(W, A, y, sigma2, symbols, cfg, max_iters, early_exit=True, shift='reference', x_true=None):
+    """SCAMP over F frames with a shared design matrix.  W: (Lr,Lc) float32; A: (n,N) complex64; y: (F,n).
+
+    ``cfg`` supplies Na, Nt (=Mc), Nr (=Mr), Lin (=Lc), Lout (=Lr).
+    """
+    Na, Mc, Mr, Lc, Lr = cfg['Na'], cfg['Nt'], cfg['Nr'], cfg['Lin'], cfg['Lout']
+    M, L = Mc // Na, Na * Lc
+    W = np.ascontiguousarray(W, dtype=F32)
+    A = np.ascontiguousarray(A, dtype=C64)
+    Ah = np.conj(A.T)
+    y = np.ascontiguousarray(y, dtype=C64)
+    F, n = y.shape
+    N = A.shape[1]
+    sigma2 = np.broadcast_to(np.asarray(sigma2, dtype=F32).reshape(-1, 1), (F, 1))
+
+    z = y.copy()
+    psi = np.ones((F, Lc), F32)
+    phi = np.full((F, Lr), np.inf, F32)
+    xmmse = np.zeros((F, N), C64)
+    xmap = np.zeros((F, N), C64)
+    iters = np.zeros(F, np.int32)
+    active = np.arange(F)
+    traj = {k: np.full((max_iters, F), np.nan) for k in ('tau', 'psi', 'mse')}
+    for t in range(max_iters):
+        a = active
+        if a.size == 0:
+            break
+        with np.errstate(all='ignore'):
+            gma = ((psi[a] @ W.T) / F32(Lc)).astype(F32)               # scamp.py:45
+            b = (gma / phi[a]).astype(F32)                             # scamp.py:47
+            z_new = (y[a] - xmmse[a] @ A.T + np.repeat(b, Mr, axis=1) * z[a]).astype(C64)   # scamp.py:48
+            phi_new = (sigma2[a] + gma).astype(F32)                    # scamp.py:50
+            tau = (F32(L) / ((F32(1) / phi_new) @ W) / F32(Mr)).astype(F32)                 # scamp.py:52
+            tau_use = np.repeat(tau, Mc, axis=1)
+            phi_use = np.repeat(phi_new, Mr, axis=1)
+            xmap_a = (xmmse[a] + tau_use * ((z_new / phi_use).astype(C64) @ Ah.T)).astype(C64)   # scamp.py:56
+            xm = sm_denoiser(xmap_a, tau_use, symbols, L, M, True, shift, want_var=False)   # scamp.py:57
+            p = (np.abs(xm) ** 2).astype(F32).reshape(-1, Lc, Mc).sum(axis=-1, dtype=F32)
+            psi_new = (F32(1) - p / F32(Na)).astype(F32)               # scamp.py:59
+        done = _allclose_rows(psi_new, psi[a])
+        z[a], phi[a], xmap[a], xmmse[a], psi[a] = z_new, phi_new, xmap_a, xm, psi_new
+        iters[a] = t + 1
+        traj['tau'][t:, a] = tau.mean(axis=1, dtype=np.float64)
+        traj['psi'][t:, a] = psi_new.mean(axis=1, dtype=np.float64)
+        if x_true is not None:
+            traj['mse'][t:, a] = _mse(xm, x_true[a])
+        if early_exit:
+            active = a[~done]
+    return dict(xmap=xmap, xmmse=xmmse, psi=psi, iters=iters, traj=traj)
+
+
+def vamp_detect(U, s, Vh, y, sigma2, sparsity, symbols, L, M, max_iters, early_exit=True,
+                shift='reference', x_true=None, double=False):
+    """VAMP over F frames.  U: (n,R) or (F,n,R); s: (R,) or (F,R); Vh: (R,N) or (F,R,N); y: (F,n).
+
+    ``double=True`` follows the reference fed with complex128 factors (SURVEY.md hard part "complex128"):
+    the linear stage runs in complex128 but the denoiser's outputs are still rounded to complex64/float32
+    every iteration (vamp.py:119).
+    """
+    CT, RT = (np.complex128, np.float64) if double else (C64, F32)
+    y = np.ascontiguousarray(y, dtype=CT)
+    F, n = y.shape
+    U = np.ascontiguousarray(U, dtype=CT)
+    Vh = np.ascontiguousarray(Vh, dtype=CT)
+    s = np.ascontiguousarray(s, dtype=RT)
+    shared = Vh.ndim == 2
+    R, N = Vh.shape[-2:]
+    sF = np.broadcast_to(s.reshape(-1, R), (F, R))
+    s2 = (sF ** 2).astype(RT)
+    noise_var = np.broadcast_to(np.asarray(sigma2, dtype=np.float64).reshape(-1), (F,)).copy()   # python float per frame
+    eta = R / N
+
+    def mv(Mat, vec, idx, adj=False):
+        if shared:
+            Mm = np.conj(Mat.T) if adj else Mat
+            return vec @ Mm.T
+        Mm = np.conj(np.swapaxes(Mat[idx], -1, -2)) if adj else Mat[idx]
+        return np.matmul(Mm, vec[..., None])[..., 0]
+
+    all_idx = np.arange(F)
+    y_tilde = (sF * mv(U, y, all_idx, adj=True)).astype(CT)            # vamp.py:22
+    r = np.zeros((F, N), CT)
+    var = np.ones((F, N), F32)
+    r_tilde = np.full((F, N), sparsity, CT)
+    s2t0 = sparsity ** 2 * (1 - sparsity) + (1 - sparsity) ** 2 * sparsity      # vamp.py:26, python float
+    sigma2_tilde = np.full(F, s2t0, np.float64)                        # float64 holder; rounded to RT after it. 0
+    xmmse = np.zeros((F, N), C64)
+    iters = np.zeros(F, np.int32)
+    active = all_idx
+    traj = {k: np.full((max_iters, F), np.nan) for k in ('tau', 'var', 'mse', 'sigma2')}
+    for t in range(max_iters):
+        a = active
+        if a.size == 0:
+            break
+        with np.errstate(all='ignore'):
+            if t == 0:
+                ratio = (noise_var[a] / sigma2_tilde[a]).astype(RT)    # float64 division, then the op's dtype
+                s2t = sigma2_tilde[a].astype(RT)
+            else:
+                s2t = sigma2_tilde[a].astype(RT)
+                ratio = (noise_var[a].astype(RT) / s2t).astype(RT)     # python float / 0-dim tensor (vamp.py:66)
+            nv = noise_var[a].astype(RT)
+            ratio_c = ratio[:, None]
+            q = mv(Vh, r_tilde[a], a).astype(CT)                       # vamp.py:67
+            scale = (RT(1) / (s2[a] + ratio_c)).astype(RT)             # vamp.py:68
+            xt = (scale * (y_tilde[a] + ratio_c * q)).astype(CT)       # vamp.py:70
+            var_lmmse = (scale.mean(axis=1, dtype=RT) * nv).astype(RT)  # vamp.py:71
+            xt = (mv(Vh, (xt - q).astype(CT), a, adj=True) + r_tilde[a]).astype(CT)   # vamp.py:72
+            xt_var = (RT(eta) * var_lmmse + RT(1 - eta) * s2t).astype(RT)             # vamp.py:73
+            alpha = (xt_var / s2t).astype(RT)
+            alpha = np.minimum(np.maximum(alpha, RT(VAR_RATIO_MIN)), RT(VAR_RATIO_MAX))
+            al = alpha[:, None]
+            r_a = ((xt - al * r_tilde[a]) / (RT(1) - al)).astype(CT)   # vamp.py:79
+            sig2 = (alpha / (RT(1) - alpha) * s2t).astype(RT)
+            sig2 = np.minimum(np.maximum(sig2, RT(VAR_MIN)), RT(VAR_MAX))
+            # the denoiser divides in the input's complex dtype, works in float64, rounds its outputs (vamp.py:111-119)
+            if double:
+                xm, vr = _denoise_double(r_a, sig2, symbols, L, M, shift)
+            else:
+                xm, vr = sm_denoiser(r_a, sig2[:, None], symbols, L, M, False, shift)
+            dxdr = (vr.mean(axis=1, dtype=F32).astype(RT) / sig2).astype(RT)          # vamp.py:85
+            dxdr = np.minimum(np.maximum(dxdr, RT(VAR_RATIO_MIN)), RT(VAR_RATIO_MAX))
+            norm = (RT(1) / (RT(1) - dxdr)).astype(RT)
+            rt_new = ((xm.astype(CT) - dxdr[:, None] * r_a) * norm[:, None]).astype(CT)   # vamp.py:91
+            s2t_new = (sig2 * dxdr * norm).astype(RT)
+            s2t_new = np.minimum(np.maximum(s2t_new, RT(VAR_MIN)), RT(VAR_MAX))
+        done = _allclose_rows(vr, var[a])
+        r[a], xmmse[a], var[a], r_tilde[a] = r_a, xm, vr, rt_new
+        sigma2_tilde[a] = s2t_new
+        iters[a] = t + 1
+        traj['tau'][t:, a] = sig2
+        traj['sigma2'][t:, a] = s2t_new
+        traj['var'][t:, a] = vr.mean(axis=1, dtype=np.float64)
+        if x_true is not None:
+            traj['mse'][t:, a] = _mse(xm, x_true[a])
+        if early_exit:
+            active = a[~done]
+    return dict(xmap=r.astype(C64) if not double else r, xmmse=xmmse, var=var, iters=iters, traj=traj,
+                y_tilde=y_tilde)
+
+
+def _denoise_double(r, sig2, symbols, L, M, shift):
+    """vamp.py:96-119 when ``r`` is complex128: the division happens in complex128, outputs round to c64/f32."""
+    F = r.shape[0]
+    K = symbols.shape[0]
+    with np.errstate(all='ignore'):
+        q = r.reshape(F, L, M, 1) / sig2.reshape(F, 1, 1, 1)
+        sym = symbols.astype(np.complex128).reshape(1, 1, 1, K)
+        x = (q * sym.conj()).real
+        if shift == 'reference':
+            ref = np.abs(x).reshape(F, -1).max(axis=1).reshape(F, 1, 1, 1)
+        else:
+            ref = x.reshape(F, L, M * K).max(axis=2).reshape(F, L, 1, 1)
+        eta = np.exp(x - ref)
+        per_antenna = eta.sum(axis=-1)
+        norm = per_antenna.sum(axis=2, keepdims=True)
+        xmmse = (sym * eta).sum(axis=-1) / norm
+        var0 = np.abs(xmmse) ** 2 * (1 - per_antenna / norm)
+        spread = (np.abs(xmmse[..., None] - sym) ** 2 * eta).sum(axis=-1) / norm
+    return xmmse.reshape(F, L * M).astype(C64), (var0 + spread).reshape(F, L * M).astype(F32)

@@ -1,0 +1,233 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE itself (build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference (read-only) and CPU torch/numpy
+
+The reference ships no tests, seeds or golden vectors, so the pins are manufactured here:
+fixed-seed inputs drawn by the reference's own ``Channel`` / ``Data`` (numpy + torch global RNGs), detectors run
+once per frame with ``batch=1`` (the reference's real operating mode), per-iteration trajectories captured by
+stepping ``amp.layers[t](T)`` by hand, final ``xmap`` / ``xmmse`` / exit iteration and the ``Loss.loss`` dicts.
+Nothing here is imported at test time; the tests only read the ``.npz`` files this script writes.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("AMPSM_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+import bamp as ref_bamp      # noqa: E402
+import scamp as ref_scamp    # noqa: E402
+import vamp as ref_vamp      # noqa: E402
+from channel import Channel  # noqa: E402
+from config import Config    # noqa: E402
+from data import Data        # noqa: E402
+from loss import Loss        # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS = ['fer', 'nMSE', 'nMSEf', 'nMSEm', 'nMSEL', 'ver', 'verf', 'verm', 'verL', 'ber', 'iber', 'sber', 'ier', 'ser']
+torch.set_grad_enabled(False)
+
+
+def cfg(Nt, Na, Nr, Lin, Lh, alphabet, trunc='trunc', mode='sparc', iters=20, batch=1):
+    return Config(Nt, Na, Nr, Lin, Lh, batch=batch, generator_mode=mode, iterations=iters, alphabet=alphabet,
+                  channel_profile='uniform', channel_truncation=trunc, device='cpu')
+
+
+def loss_vec(L):
+    return np.array([float(np.asarray(L.loss[k]).reshape(-1)[0]) for k in KEYS], dtype=np.float64)
+
+
+def mse_of(xmmse, x):
+    return float((xmmse - x).abs().pow(2).mean())
+
+
+def batch_loss(config_args, frames, xmap, xmmse, x, sym, idx, N):
+    """The reference's own Loss evaluated on the stacked frames with B = number of frames."""
+    c = cfg(*config_args[0], **dict(config_args[1], batch=frames))
+    L = Loss(c)
+    gidx = np.concatenate([i + f * N for f, i in enumerate(idx)])
+    L(torch.tensor(np.stack(xmap)).reshape(frames, N, 1), torch.tensor(np.stack(xmmse)).reshape(frames, N, 1),
+      torch.tensor(np.stack(x)).reshape(frames, N, 1), np.concatenate(sym), gidx, 0)
+    return loss_vec(L), gidx
+
+
+def run_bamp(name, args, kwargs, snrs_db, frames, seed, matrix='channel'):
+    c = cfg(*args, **kwargs)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ch, da, amp = Channel(c), Data(c), ref_bamp.BAMP(c)
+    N, n, T = c.Nt * c.Lin, c.Nr * c.Lout, c.N_Layers
+    out = {k: [] for k in ('H', 'y', 'x', 'sym', 'idx', 'sigma2', 'snr_db', 'xmap', 'xmmse', 'var', 'iters', 'tau', 'varm',
+                           'mse', 'loss')}
+    for snr_db in snrs_db:
+        snr = 10 ** (snr_db / 10)
+        for _ in range(frames):
+            H = ch.generate_channel() if matrix == 'channel' else ch.generate_as_sparc()[1]
+            x, s, i = da.generate_message()
+            y = H @ x + ch.awgn(snr)
+            tr = ref_bamp.Tracker(x, y, H, amp.E / snr)
+            tau, varm, mse = np.full(T, np.nan), np.full(T, np.nan), np.full(T, np.nan)
+            for t, layer in enumerate(amp.layers):
+                prev = tr.var
+                layer(tr)
+                tau[t:] = float((1 / (tr.abs2T @ (1 / tr.u))).real.mean())
+                varm[t:] = float(tr.var.mean())
+                mse[t:] = mse_of(tr.xmmse, x)
+                if torch.allclose(tr.var, prev):
+                    break
+            L = amp(H, y, snr, x, s, i)                      # the stock forward; must agree with the stepping
+            assert L.loss['T'] == t + 1
+            for k, v in (('H', H.numpy()), ('y', y.numpy().reshape(n)), ('x', x.numpy().reshape(N)), ('sym', s),
+                         ('idx', i), ('sigma2', amp.E / snr), ('snr_db', snr_db), ('xmap', tr.xmap.numpy().reshape(N)),
+                         ('xmmse', tr.xmmse.numpy().reshape(N)), ('var', tr.var.numpy().reshape(N)), ('iters', t + 1),
+                         ('tau', tau), ('varm', varm), ('mse', mse), ('loss', loss_vec(L))):
+                out[k].append(v)
+    F = len(out['H'])
+    bl, gidx = (None, None)
+    if c.mode == 'sparc':
+        bl, gidx = batch_loss((args, kwargs), F, out['xmap'], out['xmmse'], out['x'], out['sym'], out['idx'], N)
+    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, matrix=matrix, seed=seed, alg='bamp'))
+
+
+def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False):
+    c = cfg(*args, **kwargs)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ch, da, amp = Channel(c), Data(c), ref_vamp.VAMP(c)
+    N, n, T = c.Nt * c.Lin, c.Nr * c.Lout, c.N_Layers
+    out = {k: [] for k in ('A', 'U', 's', 'Vh', 'y', 'x', 'sym', 'idx', 'sigma2', 'snr_db', 'xmap', 'xmmse', 'var', 'iters',
+                           'tau', 'varm', 'mse', 'sigma2t', 'loss')}
+    for snr_db in snrs_db:
+        snr = 10 ** (snr_db / 10)
+        for _ in range(frames):
+            _, A = ch.generate_as_sparc()
+            U, s, Vh = torch.linalg.svd(A, full_matrices=False)
+            x, sym, i = da.generate_message()
+            y = A @ x + ch.awgn(snr)
+            if double:
+                Ui, si, Vhi, yi, xi = U.to(torch.complex128), s.to(torch.float64), Vh.to(torch.complex128), \
+                    y.to(torch.complex128), x.to(torch.complex128)
+            else:
+                Ui, si, Vhi, yi, xi = U, s, Vh, y, x
+            tr = ref_vamp.Tracker(Ui, si, Vhi, yi, xi, amp.E / snr, amp.sparsity)
+            tau, varm, mse, s2t = (np.full(T, np.nan) for _ in range(4))
+            for t, layer in enumerate(amp.layers):
+                prev = tr.var
+                layer(tr)
+                s2t[t:] = float(tr.sigma2_tilde)
+                varm[t:] = float(tr.var.mean())
+                mse[t:] = mse_of(tr.xmmse, x)
+                if torch.allclose(tr.var, prev):
+                    break
+            L = amp(Ui, si, Vhi, yi, snr, xi, sym, i)
+            assert L.loss['T'] == t + 1
+            for k, v in (('A', A.numpy()), ('U', U.numpy()), ('s', s.numpy()), ('Vh', Vh.numpy()), ('y', y.numpy().reshape(n)),
+                         ('x', x.numpy().reshape(N)), ('sym', sym), ('idx', i), ('sigma2', amp.E / snr), ('snr_db', snr_db),
+                         ('xmap', tr.r.numpy().reshape(N)), ('xmmse', tr.xmmse.numpy().reshape(N)),
+                         ('var', tr.var.numpy().reshape(N)), ('iters', t + 1), ('tau', tau), ('varm', varm), ('mse', mse),
+                         ('sigma2t', s2t), ('loss', loss_vec(L))):
+                out[k].append(v)
+    F = len(out['U'])
+    xm32 = [np.asarray(v).astype(np.complex64) for v in out['xmap']]
+    bl, gidx = batch_loss((args, kwargs), F, xm32, out['xmmse'], out['x'], out['sym'], out['idx'], N)
+    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='vamp', double=double))
+
+
+def run_scamp(name, args, kwargs, snrs_db, frames, seed, res):
+    c = cfg(*args, **kwargs)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ch, da, amp = Channel(c), Data(c), ref_scamp.SCAMP(c)
+    N, n, T = c.Nt * c.Lin, c.Nr * c.Lout, c.N_Layers
+    out = {k: [] for k in ('W', 'A', 'a_of_frame', 'y', 'x', 'sym', 'idx', 'sigma2', 'snr_db', 'xmap', 'xmmse', 'psi', 'iters',
+                           'tau', 'psim', 'mse', 'loss')}
+    for snr_db in snrs_db:
+        snr = 10 ** (snr_db / 10)
+        for f in range(frames):
+            if f % res == 0:
+                W, A = ch.generate_as_sparc()
+                out['W'].append(W.numpy())
+                out['A'].append(A.numpy())
+            x, sym, i = da.generate_message()
+            y = A @ x + ch.awgn(snr)
+            tr = ref_scamp.Tracker(W, A, y, amp.E / snr, x)
+            lay = amp.layers[0]
+            tau, psim, mse = (np.full(T, np.nan) for _ in range(3))
+            for t, layer in enumerate(amp.layers):
+                prev = tr.psi
+                layer(tr)
+                tau[t:] = float((lay.L / (tr.W.T @ (1 / tr.phi)) / lay.Mr).mean())
+                psim[t:] = float(tr.psi.mean())
+                mse[t:] = mse_of(tr.xmmse, x)
+                if torch.allclose(tr.psi, prev):
+                    break
+            L = amp(W, A, y, snr, x, sym, i)
+            assert L.loss['T'] == t + 1
+            for k, v in (('a_of_frame', len(out['A']) - 1), ('y', y.numpy().reshape(n)), ('x', x.numpy().reshape(N)),
+                         ('sym', sym), ('idx', i), ('sigma2', amp.E / snr), ('snr_db', snr_db),
+                         ('xmap', tr.xmap.numpy().reshape(N)), ('xmmse', tr.xmmse.numpy().reshape(N)),
+                         ('psi', tr.psi.numpy().reshape(-1)), ('iters', t + 1), ('tau', tau), ('psim', psim), ('mse', mse),
+                         ('loss', loss_vec(L))):
+                out[k].append(v)
+    F = len(out['y'])
+    bl, gidx = batch_loss((args, kwargs), F, out['xmap'], out['xmmse'], out['x'], out['sym'], out['idx'], N)
+    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='scamp', res=res))
+
+
+def run_loss_only(name, args, kwargs, frames, seed):
+    """Reference Loss on synthetic estimates with B>1: pins decisions, tie-breaks and the index-bit truncation."""
+    c = cfg(*args, **dict(kwargs, batch=frames))
+    rng = np.random.RandomState(seed)
+    np.random.seed(seed)
+    da = Data(c)
+    x, sym, idx = da.generate_message()
+    N = c.Nt * c.Lin
+    noise = (rng.normal(size=(frames, N, 1)) + 1j * rng.normal(size=(frames, N, 1))) * 0.35
+    xmap = (x.numpy() + noise).astype(np.complex64)
+    xmap[0, :, 0] = 0                                   # exact ties: the first (antenna, symbol) must win
+    xmmse = (x.numpy() * 0.9 + 0.1 * noise).astype(np.complex64)
+    L = Loss(c)
+    L(torch.tensor(xmap), torch.tensor(xmmse), x, sym, idx, 0)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), xmap=xmap.reshape(frames, N), xmmse=xmmse.reshape(frames, N),
+                        x=x.numpy().reshape(frames, N), sym=sym, idx=idx, loss=loss_vec(L),
+                        meta=np.array(repr(dict(args=args, kwargs=kwargs, seed=seed, alg='loss'))))
+    print(name, 'loss', dict(zip(KEYS, loss_vec(L).round(5))))
+
+
+def save(name, out, batch_loss_vec, gidx, meta):
+    arrays = {}
+    for k, v in out.items():
+        if k in ('sym', 'idx'):
+            arrays[k] = np.stack(v).astype(np.int64)
+        else:
+            arrays[k] = np.stack([np.asarray(e) for e in v]) if len(v) else np.zeros(0)
+    if batch_loss_vec is not None:
+        arrays['batch_loss'] = batch_loss_vec
+        arrays['batch_idx'] = gidx
+    arrays['meta'] = np.array(repr(meta))
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    it = arrays['iters']
+    print(f"{name}: frames={len(it)} mean T={it.mean():.2f} nan_frames={int(np.isnan(arrays['xmmse'].real).any(axis=1).sum())}"
+          f" size={os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    # C1: BAMP 8x4 QPSK, one active antenna (L=1)
+    run_bamp('bamp_c1', (8, 1, 4, 1, 1, 'QPSK'), {}, [0, 10, 20], 48, seed=0)
+    # C2: BAMP 64x32 16-QAM (L=1) -- the headline config
+    run_bamp('bamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 12, seed=0)
+    # multi-section ISI frame, matrix drawn as in bamp_model.py:56 (generate_as_sparc)
+    run_bamp('bamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [2, 8], 12, seed=1, matrix='sparc')
+    # 'segmented' decision rule (B=1 only in the reference)
+    run_bamp('bamp_seg', (16, 2, 8, 3, 2, '8PSK'), dict(trunc='tail', mode='segmented'), [4, 10], 8, seed=2, matrix='sparc')
+    # C3: VAMP 128x64, Na=4, QPSK; complex64 and the complex128-input variant
+    run_vamp('vamp_c3', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 3, seed=3)
+    run_vamp('vamp_c3_c128', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 2, seed=3, double=True)
+    run_vamp('vamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [4, 10], 8, seed=4)
+    # SCAMP: small coupled instance, design matrix shared by groups of 4 frames (res=4)
+    run_scamp('scamp_small', (32, 2, 8, 8, 3, 'QPSK'), dict(trunc='tail'), [4, 8], 8, seed=5, res=4)
+    # Loss alone at B>1
+    run_loss_only('loss_qpsk', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), 24, seed=6)
+    run_loss_only('loss_16qam', (64, 1, 32, 1, 1, '16QAM'), {}, 64, seed=7)
