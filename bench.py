@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Headline benchmark: BAMP frame-iterations/s at Nt x Nr = 64 x 32, 16-QAM spatial modulation (BASELINE.json
+configs[1]: 1M frames per SNR point, iterations = 20, complex64), one B200 or N of them.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one SNR point: every frame of the per-GPU pool is detected once (per-frame channel matrix, early exit as
+the reference, fused hard decision + error counters), followed by the NCCL all-reduce of the counter block.
+`value` = frame-iterations executed by all ranks / device time (CUDA events, max over ranks), inputs resident
+in HBM.  `e2e` = the same metric through the C-ABI host entry point (ampsm_bamp_detect_host) with pinned host
+buffers, host<->device copies inside the timed region.  `cpu_baseline` / `--impl reference` time the numpy oracle
+port of the reference's path on the host cores (the reference is Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT, NA, NR, LIN, LH, ALPHABET, ITERS = 64, 1, 32, 1, 1, '16QAM', 20
+FLOP_PER_FRAME_ITER = 20 * NR * NT + 18 * NT * 16 + 30 * NR + 20 * NT      # 61 632
+BYTES_PER_FRAME = 8 * NR * NT + 8 * NR + 8 * NT                             # H, y, x_true: 17 152
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step (1M = one SNR point)")
+    ap.add_argument("--snr-db", type=float, default=15.0)
+    ap.add_argument("--e2e-frames", type=int, default=1 << 17)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixed-t", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU side (oracle)
+def _cpu_inputs(frames, snr_db, seed):
+    """Synthetic frames of the C2 shape, drawn like channel.py:53-55 / data.py:74-91 / channel.py:113-115."""
+    from amp_sparc_spatialmodulation_b200.config import Config
+    cfg = Config(NT, NA, NR, LIN, LH, batch=frames, generator_mode='sparc', iterations=ITERS, alphabet=ALPHABET,
+                 channel_profile='uniform', device='cpu')
+    rng = np.random.default_rng(seed)
+    n, N = cfg.n, cfg.N
+    H = ((rng.standard_normal((frames, n, N), dtype=np.float32) + 1j * rng.standard_normal((frames, n, N), dtype=np.float32))
+         * np.float32(np.sqrt(1 / NR / 2))).astype(np.complex64)
+    ant = rng.integers(0, N, frames)
+    k = rng.integers(0, cfg.K, frames)
+    x = np.zeros((frames, N), np.complex64)
+    x[np.arange(frames), ant] = cfg.symbols[k]
+    sigma2 = (NA / NR) / 10 ** (snr_db / 10)
+    noise = ((rng.standard_normal((frames, n), dtype=np.float32) + 1j * rng.standard_normal((frames, n), dtype=np.float32))
+             * np.float32(np.sqrt(sigma2 / 2))).astype(np.complex64)
+    y = (np.matmul(H, x[..., None])[..., 0] + noise).astype(np.complex64)
+    return cfg, H, y, x, sigma2
+
+
+def _cpu_worker(args):
+    frames, snr_db, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import amp_oracle, loss_oracle
+    cfg, H, y, x, sigma2 = _cpu_inputs(frames, snr_db, seed)
+    t0 = time.perf_counter()
+    r = amp_oracle.bamp_detect(H, y, sigma2, cfg.symbols, cfg.L, cfg.M, ITERS, shift='section')
+    loss_oracle.map_decision(r["xmap"], cfg.symbols, cfg.gray, cfg.M)
+    return int(r["iters"].sum()), time.perf_counter() - t0
+
+
+class CpuPool:
+    """Process pool over the host cores running the numpy oracle port; one slice of frames per process."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context("spawn").Pool(workers)
+        self.pool.map(_cpu_worker, [(8, 10.0, 1)] * workers)                # start-up + imports, untimed
+
+    def rate(self, frames_total, snr_db, seed=7):
+        per = max(1, frames_total // self.workers)
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [(per, snr_db, seed + w) for w in range(self.workers)])
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res) / wall, per * self.workers, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    """--impl reference: the oracle port of the reference's CPU path, all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = args.cpu_frames or 4096 * cores
+    pool = CpuPool(cores)
+    for _ in range(args.warmup):
+        pool.rate(max(cores * 16, frames // 8), args.snr_db)
+    rates = []
+    t_all = time.perf_counter()
+    for s in range(args.steps):
+        rate, used, wall = pool.rate(frames, args.snr_db, seed=100 + s)
+        rates.append(rate)
+    ms = (time.perf_counter() - t_all) / max(args.steps, 1) * 1e3
+    pool.close()
+    v = float(np.mean(rates))
+    sample = f"{used} frames/step of BAMP 64x32 16-QAM at {args.snr_db} dB, numpy oracle port, {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": "BAMP frame-iterations/s", "value": v, "unit": "frame-iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex64 (denoiser float64)", "data": "synthetic",
+        "config": workload_config(args, frames, 1),
+        "cpu_baseline": {"value": v, "unit": "frame-iter/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frame-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, frames, world):
+    return {"workload": f"BAMP Nt={NT} Nr={NR} Na={NA} 16-QAM SM, per-frame i.i.d. Rayleigh H, iterations={ITERS}, "
+                        f"early exit as reference, SNR {args.snr_db} dB",
+            "frames_per_gpu_per_step": frames, "global_frames_per_step": frames * world, "iterations_max": ITERS,
+            "snr_db": args.snr_db, "l2": "inputs (17 KB/frame) exceed L2 at >= 8k frames; no flush needed",
+            "parallelism": f"frames sharded over {world} GPU(s), one NCCL all-reduce of the 24-word counter block per step"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU side
+def make_gpu_inputs(torch, cfg, frames, snr_db, dev, seed):
+    """Synthetic pool on the device: H ~ CN(0, 1/Nr) per frame, one active antenna with a 16-QAM symbol, AWGN."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    n, N = cfg.n, cfg.N
+    H = torch.empty(frames, n, N, dtype=torch.complex64, device=dev)
+    Hr = torch.view_as_real(H)
+    chunk = 1 << 16
+    for lo in range(0, frames, chunk):
+        hi = min(frames, lo + chunk)
+        Hr[lo:hi].normal_(0.0, float(np.sqrt(1 / NR / 2)), generator=gen)
+    ant = torch.randint(0, N, (frames,), device=dev, generator=gen)
+    k = torch.randint(0, cfg.K, (frames,), device=dev, generator=gen)
+    sym = torch.as_tensor(cfg.symbols).to(dev, torch.complex64)
+    gray = torch.as_tensor(np.asarray(cfg.gray)).to(dev, torch.int64)
+    x = torch.zeros(frames, N, dtype=torch.complex64, device=dev)
+    ar = torch.arange(frames, device=dev)
+    x[ar, ant] = sym[k]
+    sigma2 = (NA / NR) / 10 ** (snr_db / 10)
+    noise = torch.empty(frames, n, dtype=torch.complex64, device=dev)
+    torch.view_as_real(noise).normal_(0.0, float(np.sqrt(sigma2 / 2)), generator=gen)
+    y = H[ar, :, ant] * sym[k].unsqueeze(1) + noise
+    labels = gray[k].contiguous()
+    idx = (ar * N + ant).to(torch.int64).contiguous()
+    return H, y.contiguous(), x, labels, idx
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    cpu_base = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:       # before CUDA is touched in this process
+        cores = os.cpu_count() or 1
+        frames_cpu = args.cpu_frames or 4096 * cores
+        pool = CpuPool(cores)
+        rate, used, wall = pool.rate(frames_cpu, args.snr_db)
+        pool.close()
+        cpu_base = {"value": rate, "unit": "frame-iter/s", "cores": cores, "kind": "port",
+                    "sample": f"{used} frames of the same workload in {wall:.1f} s, numpy oracle port (oracle/amp_oracle.py), "
+                              f"{cores} processes"}
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    import amp_sparc_spatialmodulation_b200 as pkg
+    from amp_sparc_spatialmodulation_b200 import _cabi
+    from amp_sparc_spatialmodulation_b200.dist import allreduce_counters
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    frames = args.frames
+    cfg = pkg.Config(NT, NA, NR, LIN, LH, batch=frames, generator_mode='sparc', iterations=ITERS, alphabet=ALPHABET,
+                     channel_profile='uniform', device=str(dev))
+    H, y, x, labels, idx = make_gpu_inputs(torch, cfg, frames, args.snr_db, dev, 1234 + rank)
+    snr = 10 ** (args.snr_db / 10)
+    amp = pkg.BAMP(cfg, kernel=args.kernel, outputs=False)
+    amp_fixed = pkg.BAMP(cfg, kernel=args.kernel, outputs=False, early_exit=False)
+    frame_base = rank * frames
+
+    def step(module):
+        det = module.detect(H, y, snr, x, labels, idx - 0, frame_base=0)
+        return allreduce_counters(det.counters) if world > 1 else det.counters
+
+    def timed(module, steps, warmup):
+        for _ in range(warmup):
+            step(module)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.ampsm_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        totals = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        kernel_ms = []
+        with Clocks(local) as clk:
+            e0.record()
+            for _ in range(steps):
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                det = module.detect(H, y, snr, x, labels, idx, frame_base=0)
+                k1.record()
+                kernel_ms.append((k0, k1))
+                c = allreduce_counters(det.counters) if world > 1 else det.counters
+                totals += c
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = int(lib.ampsm_launch_count(0))
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        kms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ms]))
+        return ms, kms, _cabi.counters_to_dict(totals.cpu().numpy()), launches, clk.summary()
+
+    ms, kernel_ms, c, launches, clocks = timed(amp, args.steps, args.warmup)
+    # counters were all-reduced: c holds the global totals over all ranks and steps
+    frame_iters = c["iters"]
+    value = frame_iters / (ms * 1e-3)
+    frames_done = c["frames"]
+    mean_T = frame_iters / max(frames_done, 1)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bamp_c2_bytes_per_launch")
+    except OSError:
+        pass
+    per_gpu_frames_per_launch = frames
+    achieved_gbs = per_gpu_frames_per_launch * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "bamp (per-GPU launch)", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "kernel_ms": kernel_ms}
+
+    out = {
+        "metric": "BAMP frame-iterations/s", "value": value, "unit": "frame-iter/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex64 (f32 mat-vecs, f64 exponent differences, f32 exp)", "data": "synthetic",
+        "config": workload_config(args, frames, world), "mean_iterations_per_frame": mean_T,
+        "frames_per_s": frames_done / (ms * 1e-3), "fer": c["frame_err"] / max(frames_done, 1),
+        "ier": c["index_err"] / max(frames_done * NA * LIN, 1), "nan_frames": c["nan_frames"],
+        "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
+    }
+
+    if rank == 0 or world > 1:
+        pass
+    # fixed-T mode (exit disabled: exactly 20 iterations per frame) against the FP32 pipe
+    if not args.no_fixed_t:
+        ms2, kms2, c2, _, _ = timed(amp_fixed, max(2, args.steps // 2), 1)
+        tf = 0.0
+        if rank == 0:
+            import ctypes
+            t = ctypes.c_double(0.0)
+            lib.ampsm_probe_fp32_tflops(local, ctypes.byref(t))
+            tf = t.value
+        v2 = c2["iters"] / (ms2 * 1e-3)
+        ach = (frames * ITERS * FLOP_PER_FRAME_ITER) / (kms2 * 1e-3) / 1e12
+        out["fixed_T"] = {"value": v2, "unit": "frame-iter/s", "iterations": ITERS, "kernel_ms": kms2,
+                          "roofline_fp32": {"bound": "fp32", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
+                                            "frac": (ach / tf) if tf else None,
+                                            "peak_source": "FFMA probe kernel run in this process (ampsm_probe_fp32_tflops)",
+                                            "algorithmic_flop_per_frame_iter": FLOP_PER_FRAME_ITER}}
+
+    # end to end through the C-ABI host entry point: pinned host buffers, H2D/D2H inside the timed region
+    fe = min(args.e2e_frames, frames)
+    import ctypes
+    hH = H[:fe].cpu().pin_memory()
+    hy = y[:fe].cpu().pin_memory()
+    hx = x[:fe].cpu().pin_memory()
+    hl = labels[:fe].cpu().pin_memory()
+    hi = (idx[:fe] - 0).cpu().pin_memory()
+    prob = _cabi.make_problem(cfg, fe, kernel=args.kernel)
+    alpha = _cabi.make_alphabet(cfg)
+    hcount = np.zeros(_cabi.NUM_COUNTERS, dtype=np.int64)
+
+    def host_step():
+        rc = lib.ampsm_bamp_detect_host(prob, alpha, fe, hH.data_ptr(), cfg.n * cfg.N, hy.data_ptr(), float((NA / NR) / snr), None,
+                                        hx.data_ptr(), hl.data_ptr(), hi.data_ptr(), None, None, None, None, None,
+                                        hcount.ctypes.data, local)
+        _cabi.check(rc, "ampsm_bamp_detect_host")
+    for _ in range(max(1, args.warmup)):
+        host_step()
+    hcount[:] = 0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    t_e2e = time.perf_counter() - t0
+    ce = _cabi.counters_to_dict(hcount)
+    e2e_iters = torch.tensor([float(ce["iters"]), t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        it = e2e_iters[:1].clone()
+        tm = e2e_iters[1:].clone()
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_iters = torch.cat([it, tm])
+    h2d = fe * (BYTES_PER_FRAME + 16)
+    out["e2e"] = {"value": float(e2e_iters[0] / e2e_iters[1]), "unit": "frame-iter/s", "h2d_bytes_per_step": int(h2d),
+                  "d2h_bytes_per_step": _cabi.NUM_COUNTERS * 8, "frames_per_step": fe,
+                  "api": "ampsm_bamp_detect_host (C-ABI, pinned host buffers, chunked copies overlapped with the kernel)"}
+    if cpu_base:
+        out["cpu_baseline"] = cpu_base
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
