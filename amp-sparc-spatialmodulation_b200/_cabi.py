@@ -20,7 +20,8 @@ SQERR_NAMES = ['sqerr', 'sqerr_first', 'sqerr_mid', 'sqerr_last']
 # every symbol include/ampsm_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_host",
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
-           "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_probe_fp32_tflops", "ampsm_launch_count"]
+           "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops",
+           "ampsm_launch_count"]
 
 
 class Alphabet(C.Structure):
@@ -68,6 +69,7 @@ def lib():
     L.ampsm_scamp_workspace_bytes.restype = i64
     L.ampsm_loss_count.argtypes = [PP, AP, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_probe_fp32_tflops.argtypes = [i32, C.POINTER(dbl)]
+    L.ampsm_probe_fp32x2_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ampsm_launch_count.argtypes = [i32]
     L.ampsm_launch_count.restype = i64
     for name in EXPORTS:

@@ -18,6 +18,8 @@
 // Shapes are template parameters; launch_bamp_fast() dispatches the instantiated ones and returns AMPSM_ENOFIT
 // otherwise (the caller then uses the generic shared-memory kernel).
 #include "blockops.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ampsm {
@@ -36,9 +38,10 @@ struct FastShape {
     static constexpr int ebuf_bytes = 32 * CP * K_ * 4;
     static constexpr int xch_bytes_a = rowpart_bytes > colpart_bytes ? rowpart_bytes : colpart_bytes;
     static constexpr int xch_bytes = ((xch_bytes_a > ebuf_bytes ? xch_bytes_a : ebuf_bytes) + 127) & ~127;
-    static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 16 + 127) & ~127;
-    static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 16 + 127) & ~127;
-    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + 128;
+    static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // padded slots (see the kernel)
+    static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 20 + 127) & ~127;     // float4 per column + the variance array
+    static constexpr int wvec_bytes = ((n > 32 ? n : 32) * 8 + 127) & ~127;
+    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + 128;
 };
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -46,13 +49,163 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Packed fp32x2 arithmetic on 64-bit register pairs (FFMA2, sm_100).  The pairs are held in 64-bit containers so
+// that ptxas keeps the H tile PACKED across the whole frame; with float2 values it re-assembles every operand pair
+// with two MOVs per FFMA2 inside the iteration loop.
+typedef unsigned long long pair_t;
+__device__ __forceinline__ pair_t pack2(float lo, float hi) {
+    pair_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(pair_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pair_t ffma2(pair_t a, pair_t b, pair_t c) {
+    pair_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ pair_t fmul2(pair_t a, pair_t b) {
+    pair_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float fast_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
-template <int RT, int CTL, int M_, int K_>
+
+// Product-grid view of an alphabet: sym_k = (lr[a_k], li[b_k]) on an NGR x NGI grid, with `ncorr` grid points whose
+// multiplicity in the table differs from one (the reference's 16-QAM list has one point twice and one missing,
+// config.py:112).  exp(Re(q conj s)) then factorises into a real-part and an imaginary-part factor, so an antenna
+// needs NGR + NGI exponentials instead of K.
+
+static DevGrid make_grid(const DevAlphabet& al) {
+    DevGrid g{};
+    double lr[AMPSM_MAX_K], li[AMPSM_MAX_K];
+    int nr = 0, ni = 0;
+    auto add = [](double* v, int& n, double x) {
+        for (int i = 0; i < n; ++i)
+            if (v[i] == x) return;
+        v[n++] = x;
+    };
+    for (int k = 0; k < al.K; ++k) {
+        add(lr, nr, al.re[k]);
+        add(li, ni, al.im[k]);
+    }
+    if (nr > kGridMax || ni > kGridMax) return g;
+    auto sort = [](double* v, int n) {
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j)
+                if (v[j] < v[i]) { double t = v[i]; v[i] = v[j]; v[j] = t; }
+    };
+    sort(lr, nr);
+    sort(li, ni);
+    int cnt[kGridMax][kGridMax] = {};
+    for (int k = 0; k < al.K; ++k) {
+        int a = 0, b = 0;
+        while (lr[a] != al.re[k]) ++a;
+        while (li[b] != al.im[k]) ++b;
+        cnt[a][b]++;
+    }
+    int nc = 0;
+    for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < ni; ++b)
+            if (cnt[a][b] != 1) {
+                if (nc == kGridCorrMax) return g;
+                g.ca[nc] = a; g.cb[nc] = b; g.cw[nc] = (float)(cnt[a][b] - 1);
+                ++nc;
+            }
+    if (nr != kGridMax || ni != kGridMax) return g;          // only full 4 x 4 grids take the separable path for now
+    g.nr = nr; g.ni = ni; g.ncorr = nc;
+    const double log2e = 1.4426950408889634074;
+    for (int i = 0; i < kGridMax; ++i) {
+        g.lr2[i] = lr[i] * log2e; g.li2[i] = li[i] * log2e;
+        g.lr2f[i] = (float)g.lr2[i]; g.li2f[i] = (float)g.li2[i];
+        g.lrf[i] = (float)lr[i]; g.lif[i] = (float)li[i];
+    }
+    for (int c = 0; c < kGridCorrMax; ++c) {
+        if (c >= nc) { g.ca[c] = 0; g.cb[c] = 0; g.cw[c] = 0.f; }
+        g.scr[c] = g.lrf[g.ca[c]];
+        g.sci[c] = g.lif[g.cb[c]];
+    }
+    g.ok = 1;
+    return g;
+}
+
+// ---- section reductions over the column-owner layout (column = lane + 32 t) ---------------------------------------
+template <int M_, int CP>
+__device__ __forceinline__ void section_max(const float (&lmax)[CP], float (&smax)[CP]) {
+    if constexpr (M_ >= 32) {
+        constexpr int TPS = M_ / 32;
+#pragma unroll
+        for (int s0 = 0; s0 < CP; s0 += TPS) {
+            float m = lmax[s0];
+#pragma unroll
+            for (int q = 1; q < TPS; ++q) m = fmaxf(m, lmax[s0 + q]);
+            m = warp_max(m);
+#pragma unroll
+            for (int q = 0; q < TPS; ++q) smax[s0 + q] = m;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            float m = lmax[t];
+#pragma unroll
+            for (int o = M_ / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            smax[t] = m;
+        }
+    }
+}
+// Z = section sum of S0; others = Z - S0 WITHOUT cancellation: in a butterfly all-reduce, what a lane receives adds
+// up to everybody else's share.
+template <int M_, int CP>
+__device__ __forceinline__ void section_sum_excl(const float (&S0)[CP], float (&Z)[CP], float (&others)[CP]) {
+    if constexpr (M_ >= 32) {
+        constexpr int TPS = M_ / 32;
+#pragma unroll
+        for (int s0 = 0; s0 < CP; s0 += TPS) {
+            float mine = S0[s0];
+#pragma unroll
+            for (int q = 1; q < TPS; ++q) mine += S0[s0 + q];
+            float part = mine, recv = 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float r = __shfl_xor_sync(0xffffffffu, part, o);
+                recv += r;
+                part += r;
+            }
+#pragma unroll
+            for (int q = 0; q < TPS; ++q) {
+                Z[s0 + q] = part;
+                float sib = 0.f;                                     // the lane's other columns of this section
+#pragma unroll
+                for (int w = 0; w < TPS; ++w)
+                    if (w != q) sib += S0[s0 + w];
+                others[s0 + q] = recv + sib;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            float part = S0[t], recv = 0.f;
+#pragma unroll
+            for (int o = M_ / 2; o > 0; o >>= 1) {
+                const float r = __shfl_xor_sync(0xffffffffu, part, o);
+                recv += r;
+                part += r;
+            }
+            Z[t] = part;
+            others[t] = recv;
+        }
+    }
+}
+__device__ __forceinline__ float pick4(const float (&v)[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
+
+template <int RT, int CTL, int M_, int K_, bool GRID>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const __grid_constant__ BampArgs a) {
     using S = FastShape<RT, CTL, M_, K_>;
     constexpr int n = S::n, N = S::N, VW = S::VW, NV = S::NV, CP = S::CP;
@@ -69,7 +222,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     float* ebuf = reinterpret_cast<float*>(ws + S::stage_bytes);
     float4* rowvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes);
     float4* colvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes);
+    float2* wvec = reinterpret_cast<float2*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes + S::wvec_bytes);
 
     const Geom& g = a.g;
     const DevAlphabet& al = a.al;
@@ -97,27 +251,51 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     unsigned long long c_frames = 0, c_ferr = 0, c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0, c_iters = 0, c_nan = 0;
     double c_sq = 0.0;
 
-    float Hr[RT][CTL], Hi[RT][CTL], P[RT][CTL];
+    // H and |H|^2 tiles.  PAIR: every element stays the natural (re, im) register pair it is loaded as, and |H|^2 is
+    // paired over the lane's adjacent columns, so that all mat-vec FMAs are packed FFMA2 (fma.rn.f32x2, sm_100: half
+    // the issue slots for the same FMA-pipe work) with no register re-packing inside the iteration loop:
+    //   H x    : A += h (xx,xx), B += h (xy,xy)   ->  re = A.lo - B.hi, im = B.lo + A.hi
+    //   H^H g  : A += h (gx,gy), B += h (gy,-gx)  ->  re = A.lo + A.hi, im = B.lo + B.hi
+    constexpr bool PAIR = (VW == 2);
+    pair_t Hp[PAIR ? RT : 1][CTL], Pp[PAIR ? RT : 1][PAIR ? NV : 1];
+    float Hr[PAIR ? 1 : RT][CTL], Hi[PAIR ? 1 : RT][CTL], P[PAIR ? 1 : RT][CTL];
 
     for (; f < a.frames; f += warps_total) {
         mbar_wait(mbar, phase);
         phase ^= 1u;
         // ---- staging buffer -> registers: lane (a,b) takes rows a*RT+i, column vectors (t*8+b)*VW+e
+        if constexpr (PAIR) {
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
-            const float2* row = stH + (size_t)(la * RT + i) * N;
+            for (int i = 0; i < RT; ++i) {
+                const float2* row = stH + (size_t)(la * RT + i) * N;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) {
-                if constexpr (VW == 2) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + (t * 8 + lb) * 2);
-                    Hr[i][2 * t] = v.x; Hi[i][2 * t] = v.y; Hr[i][2 * t + 1] = v.z; Hi[i][2 * t + 1] = v.w;
-                } else {
-                    const float2 v = row[t * 8 + lb];
-                    Hr[i][t] = v.x; Hi[i][t] = v.y;
+                for (int t = 0; t < NV; ++t) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + (t * 8 + lb) * 2);
+                    Hp[i][2 * t] = v.x;
+                    Hp[i][2 * t + 1] = v.y;
+                    float a0, a1, b0, b1;
+                    unpack2(fmul2(v.x, v.x), a0, a1);
+                    unpack2(fmul2(v.y, v.y), b0, b1);
+                    Pp[i][t] = pack2(a0 + a1, b0 + b1);          // |H|^2 (bamp.py:18) of the two adjacent columns
                 }
             }
+        } else {
 #pragma unroll
-            for (int c = 0; c < CTL; ++c) P[i][c] = fmaf(Hr[i][c], Hr[i][c], Hi[i][c] * Hi[i][c]);   // |H|^2 (bamp.py:18)
+            for (int i = 0; i < RT; ++i) {
+                const float2* row = stH + (size_t)(la * RT + i) * N;
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    if constexpr (VW == 2) {
+                        const float4 v = *reinterpret_cast<const float4*>(row + (t * 8 + lb) * 2);
+                        Hr[i][2 * t] = v.x; Hi[i][2 * t] = v.y; Hr[i][2 * t + 1] = v.z; Hi[i][2 * t + 1] = v.w;
+                    } else {
+                        const float2 v = row[t * 8 + lb];
+                        Hr[i][t] = v.x; Hi[i][t] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CTL; ++c) P[i][c] = fmaf(Hr[i][c], Hr[i][c], Hi[i][c] * Hi[i][c]);
+            }
         }
         const float2 yv = lane < n ? stY[lane] : make_float2(0.f, 0.f);
         __syncwarp();
@@ -126,6 +304,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             if (nf < a.frames) prefetch(nf);
         }
         const float sigma2 = a.sigma2_pf ? a.sigma2_pf[f] : a.sigma2;
+
+        // column-vector exchange.  PAIR: per column one float4 {xx,xx,xy,xy} (the broadcast operand pairs of the row
+        // pass), placed so that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without
+        // conflicts, plus the variances as a plain float array (adjacent columns = one operand pair).
+        float* varvec = reinterpret_cast<float*>(colvec + N);
+        auto colslot = [&](int col) {
+            if constexpr (PAIR) {
+                const int t = col >> 4, b = (col >> 1) & 7, e = col & 1;
+                return (t * 2 + e) * 8 + (b ^ (e << 2));
+            } else {
+                return col ^ ((col >> 3) & 1);
+            }
+        };
+        auto publish = [&](int col, float xr, float xi, float v) {
+            if constexpr (PAIR) {
+                colvec[colslot(col)] = make_float4(xr, xr, xi, xi);
+                varvec[col] = v;
+            } else {
+                colvec[colslot(col)] = make_float4(xr, xi, v, 0.f);
+            }
+        };
 
         // state (bamp.py:20-25): row owner lane r keeps z_r, u_r; column owner lane keeps xhat, var of col lane+32t
         float2 z = yv;
@@ -138,33 +337,67 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             xmap[t] = make_float2(0.f, 0.f);
             var[t] = 1.0f;
             cov[t] = 0.f;
-            if (lane + 32 * t < N) colvec[lane + 32 * t] = make_float4(0.f, 0.f, 1.0f, 0.f);
+            if (lane + 32 * t < N) publish(lane + 32 * t, 0.f, 0.f, 1.0f);
         }
         __syncwarp();
 
         int t_done = 0;
         for (int it = 0; it < g.max_iters; ++it) {
             // ================= row pass: v = |H|^2 var, Hx = H xhat (bamp.py:59-60) =================
-            float av[RT], ar[RT], ai[RT];
+            if constexpr (PAIR) {
+                constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
 #pragma unroll
-            for (int i = 0; i < RT; ++i) av[i] = ar[i] = ai[i] = 0.f;
+                for (int i0 = 0; i0 < RT; i0 += RH) {
+                    pair_t A[RH], B[RH], V[RH];
 #pragma unroll
-            for (int c = 0; c < CTL; ++c) {
-                const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
-                const float4 xv = colvec[col];                       // {xhat.re, xhat.im, var, -}
+                    for (int i = 0; i < RH; ++i) A[i] = B[i] = V[i] = 0ull;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const int col = (t * 8 + lb) * 2;
+                        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {xx,xx | xy,xy}
+                        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
+                        const pair_t vp = *reinterpret_cast<const pair_t*>(&varvec[col]);                       // {var_c, var_c+1}
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) {
+                            A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
+                            B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
+                            A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
+                            B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
+                            V[i] = ffma2(Pp[i0 + i][t], vp, V[i]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        const int row = la * RT + i0 + i;
+                        float al_, ah_, bl_, bh_, vl_, vh_;
+                        unpack2(A[i], al_, ah_);
+                        unpack2(B[i], bl_, bh_);
+                        unpack2(V[i], vl_, vh_);
+                        xch[row * 8 + (lb ^ (row & 7))] = make_float4(vl_ + vh_, al_ - bh_, bl_ + ah_, 0.f);
+                    }
+                }
+            } else {
+                float av[RT], ar[RT], ai[RT];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) av[i] = ar[i] = ai[i] = 0.f;
+#pragma unroll
+                for (int c = 0; c < CTL; ++c) {
+                    const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
+                    const float4 xv = colvec[colslot(col)];           // {xhat.re, xhat.im, var, -}
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) {
+                        av[i] = fmaf(P[i][c], xv.z, av[i]);
+                        ar[i] = fmaf(Hr[i][c], xv.x, ar[i]);
+                        ar[i] = fmaf(-Hi[i][c], xv.y, ar[i]);
+                        ai[i] = fmaf(Hr[i][c], xv.y, ai[i]);
+                        ai[i] = fmaf(Hi[i][c], xv.x, ai[i]);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
-                    av[i] = fmaf(P[i][c], xv.z, av[i]);
-                    ar[i] = fmaf(Hr[i][c], xv.x, ar[i]);
-                    ar[i] = fmaf(-Hi[i][c], xv.y, ar[i]);
-                    ai[i] = fmaf(Hr[i][c], xv.y, ai[i]);
-                    ai[i] = fmaf(Hi[i][c], xv.x, ai[i]);
+                    const int row = la * RT + i;
+                    xch[row * 8 + (lb ^ (row & 7))] = make_float4(av[i], ar[i], ai[i], 0.f);
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                const int row = la * RT + i;
-                xch[row * 8 + (lb ^ (row & 7))] = make_float4(av[i], ar[i], ai[i], 0.f);
             }
             __syncwarp();
             if (lane < n) {
@@ -181,23 +414,65 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                 const float rn = fast_rcp(un);
                 z = zn;
                 u = un;
-                rowvec[lane] = make_float4((yv.x - zn.x) * rn, (yv.y - zn.y) * rn, rn, 0.f);
+                const float gx = (yv.x - zn.x) * rn, gy = (yv.y - zn.y) * rn;
+                if constexpr (PAIR) {
+                    rowvec[lane + (lane >> 3)] = make_float4(gx, gy, gy, -gx);     // operand pairs (gx,gy), (gy,-gx)
+                    wvec[lane] = make_float2(rn, rn);
+                } else {
+                    rowvec[lane + (lane >> 3)] = make_float4(gx, gy, rn, 0.f);
+                }
             }
             __syncwarp();
             // ================= column pass: cov = 1/(|H|^2^T 1/u), H^H((y-z)/u) (bamp.py:62-63) =================
             float cc[CTL], cr[CTL], ci[CTL];
+            if constexpr (PAIR) {
+                // columns in two halves: the accumulators would not fit next to the H tile otherwise
+                constexpr int CH = CTL > 4 ? CTL / 2 : CTL;
 #pragma unroll
-            for (int c = 0; c < CTL; ++c) cc[c] = cr[c] = ci[c] = 0.f;
+                for (int c0 = 0; c0 < CTL; c0 += CH) {
+                    pair_t A[CH], B[CH], C[CH / 2];
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                const float4 gv = rowvec[la * RT + i];               // {g.re, g.im, 1/u, -}
+                    for (int c = 0; c < CH; ++c) A[c] = B[c] = 0ull;
 #pragma unroll
-                for (int c = 0; c < CTL; ++c) {
-                    cc[c] = fmaf(P[i][c], gv.z, cc[c]);
-                    cr[c] = fmaf(Hr[i][c], gv.x, cr[c]);
-                    cr[c] = fmaf(Hi[i][c], gv.y, cr[c]);
-                    ci[c] = fmaf(Hr[i][c], gv.y, ci[c]);
-                    ci[c] = fmaf(-Hi[i][c], gv.x, ci[c]);
+                    for (int c = 0; c < CH / 2; ++c) C[c] = 0ull;
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) {
+                        const int row = la * RT + i;
+                        const ulonglong2 gq = *reinterpret_cast<const ulonglong2*>(&rowvec[row + (row >> 3)]);   // {gx,gy | gy,-gx}
+                        const pair_t wp = *reinterpret_cast<const pair_t*>(&wvec[row]);                          // {1/u, 1/u}
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            A[c] = ffma2(Hp[i][c0 + c], gq.x, A[c]);
+                            B[c] = ffma2(Hp[i][c0 + c], gq.y, B[c]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < CH / 2; ++c) C[c] = ffma2(Pp[i][c0 / 2 + c], wp, C[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        float lo, hi;
+                        unpack2(A[c], lo, hi);
+                        cr[c0 + c] = lo + hi;
+                        unpack2(B[c], lo, hi);
+                        ci[c0 + c] = lo + hi;
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH / 2; ++c) unpack2(C[c], cc[c0 + 2 * c], cc[c0 + 2 * c + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CTL; ++c) cc[c] = cr[c] = ci[c] = 0.f;
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    const float4 gv = rowvec[(la * RT + i) + ((la * RT + i) >> 3)];   // {g.re, g.im, 1/u, -}
+#pragma unroll
+                    for (int c = 0; c < CTL; ++c) {
+                        cc[c] = fmaf(P[i][c], gv.z, cc[c]);
+                        cr[c] = fmaf(Hr[i][c], gv.x, cr[c]);
+                        cr[c] = fmaf(Hi[i][c], gv.y, cr[c]);
+                        ci[c] = fmaf(Hr[i][c], gv.y, ci[c]);
+                        ci[c] = fmaf(-Hi[i][c], gv.x, ci[c]);
+                    }
                 }
             }
 #pragma unroll
@@ -223,126 +498,147 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             }
             __syncwarp();     // everyone is done with the column partials: the region becomes the exp buffer
             // ================= denoiser (bamp.py:66-77), tau = cov/2 =================
-            double qr[CP], qi[CP];
-            float lmax[CP];
-#pragma unroll
-            for (int t = 0; t < CP; ++t) {
-                const float rt = fast_rcp(cov[t] * 0.5f);
-                const float q_r = xmap[t].x * rt, q_i = xmap[t].y * rt;
-                qr[t] = (double)q_r;
-                qi[t] = (double)q_i;
-                float m = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < K_; ++k) m = fmaxf(m, fmaf(q_r, al.ref[k], q_i * al.imf[k]));
-                lmax[t] = (lane + 32 * t < N) ? m : -INFINITY;
-            }
-            // section maxima (only approximately the true maxima: they are a common shift, nothing else)
-            float smax[CP];
-            if constexpr (M_ >= 32) {
-                constexpr int TPS = M_ / 32;                         // owned columns per section
-#pragma unroll
-                for (int s0 = 0; s0 < CP; s0 += TPS) {
-                    float m = lmax[s0];
-#pragma unroll
-                    for (int q = 1; q < TPS; ++q) m = fmaxf(m, lmax[s0 + q]);
-                    m = warp_max(m);
-#pragma unroll
-                    for (int q = 0; q < TPS; ++q) smax[s0 + q] = m;
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {                       // sections are groups of M_ adjacent lanes
-                    float m = lmax[t];
-#pragma unroll
-                    for (int o = M_ / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    smax[t] = m;
-                }
-            }
-            // exp pass: e = 2^((x - shift) log2 e); per-antenna sums S0 = sum e, S1 = sum sym e
-            float S0[CP], S1r[CP], S1i[CP];
-#pragma unroll
-            for (int t = 0; t < CP; ++t) {
-                const double shift = (double)smax[t];
-                float s0 = 0.f, s1r = 0.f, s1i = 0.f;
-#pragma unroll
-                for (int k = 0; k < K_; ++k) {
-                    const double x = fma(qr[t], al.re[k], qi[t] * al.im[k]);
-                    const float e = fast_ex2((float)(x - shift) * 1.4426950408889634f);
-                    ebuf[(t * K_ + k) * 32 + lane] = e;
-                    s0 += e;
-                    s1r = fmaf(al.ref[k], e, s1r);
-                    s1i = fmaf(al.imf[k], e, s1i);
-                }
-                const bool live = lane + 32 * t < N;
-                S0[t] = live ? s0 : 0.f;
-                S1r[t] = s1r;
-                S1i[t] = s1i;
-            }
-            // section normaliser Z and the exclusive sum "others" = Z - S0 without cancellation: in a butterfly
-            // all-reduce, what a lane RECEIVES adds up to everybody else's share
-            float Z[CP], others[CP];
-            if constexpr (M_ >= 32) {
-                constexpr int TPS = M_ / 32;
-#pragma unroll
-                for (int s0 = 0; s0 < CP; s0 += TPS) {
-                    float mine = S0[s0];
-#pragma unroll
-                    for (int q = 1; q < TPS; ++q) mine += S0[s0 + q];
-                    float part = mine, recv = 0.f;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float r = __shfl_xor_sync(0xffffffffu, part, o);
-                        recv += r;
-                        part += r;
-                    }
-#pragma unroll
-                    for (int q = 0; q < TPS; ++q) {
-                        Z[s0 + q] = part;
-                        others[s0 + q] = recv + (mine - S0[s0 + q]);   // mine - S0 = the lane's other columns (exact: a sum of them)
-                    }
-                    if constexpr (TPS == 2) {   // avoid the subtraction above: name the sibling column directly
-                        others[s0] = recv + S0[s0 + 1];
-                        others[s0 + 1] = recv + S0[s0];
-                    }
-                }
-            } else {
+            float xr_[CP], xi_[CP], vn_[CP];
+            if constexpr (GRID) {
+                // separable path: e_k = Er[a_k] Ei[b_k], 8 exponentials per antenna; everything in the log2 domain
+                // (levels pre-multiplied by log2 e), one DFMA per exponent: 2^(q*level - shift) straight into ex2
+                const DevGrid& G = a.grid;
+                float q_r[CP], q_i[CP], lmax[CP], smax[CP];
 #pragma unroll
                 for (int t = 0; t < CP; ++t) {
-                    float part = S0[t], recv = 0.f;
+                    const float rt = fast_rcp(cov[t] * 0.5f);
+                    q_r[t] = xmap[t].x * rt;
+                    q_i[t] = xmap[t].y * rt;
+                    // levels are sorted: the largest product sits at one end (approximate: only a common shift)
+                    const float lm = fmaxf(q_r[t] * G.lr2f[0], q_r[t] * G.lr2f[3]) + fmaxf(q_i[t] * G.li2f[0], q_i[t] * G.li2f[3]);
+                    lmax[t] = (lane + 32 * t < N) ? lm : -INFINITY;
+                }
+                section_max<M_, CP>(lmax, smax);
+                float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], ec[CP][kGridCorrMax];
 #pragma unroll
-                    for (int o = M_ / 2; o > 0; o >>= 1) {
-                        const float r = __shfl_xor_sync(0xffffffffu, part, o);
-                        recv += r;
-                        part += r;
+                for (int t = 0; t < CP; ++t) {
+                    const double qrd = (double)q_r[t], qid = (double)q_i[t];
+                    const double sr = qrd * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]);      // exact max of the real-part products
+                    // x_k - smax = (ur - sr) + (ui - si) + (sr + si - smax): the imaginary factor carries sr - smax
+                    const double off_i = sr - (double)smax[t];
+                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        Er[t][l] = fast_ex2((float)fma(qrd, G.lr2[l], -sr));
+                        Ei[t][l] = fast_ex2((float)fma(qid, G.li2[l], off_i));
+                        a0 += Er[t][l];
+                        a1 = fmaf(G.lrf[l], Er[t][l], a1);
+                        b0 += Ei[t][l];
+                        b1 = fmaf(G.lif[l], Ei[t][l], b1);
                     }
-                    Z[t] = part;
-                    others[t] = recv;
+                    float s0 = a0 * b0;
+#pragma unroll
+                    for (int c = 0; c < kGridCorrMax; ++c) {      // multiplicity corrections (weight 0 when unused)
+                        ec[t][c] = G.cw[c] * pick4(Er[t], G.ca[c]) * pick4(Ei[t], G.cb[c]);
+                        s0 += ec[t][c];
+                    }
+                    S0[t] = (lane + 32 * t < N) ? s0 : 0.f;
+                    A0[t] = a0; A1[t] = a1; B0[t] = b0; B1[t] = b1;
+                }
+                float Z[CP], others[CP];
+                section_sum_excl<M_, CP>(S0, Z, others);
+#pragma unroll
+                for (int t = 0; t < CP; ++t) {
+                    const float rz = fast_rcp(Z[t]);
+                    float s1r = A1[t] * B0[t], s1i = A0[t] * B1[t];
+#pragma unroll
+                    for (int c = 0; c < kGridCorrMax; ++c) {
+                        s1r = fmaf(G.scr[c], ec[t][c], s1r);
+                        s1i = fmaf(G.sci[c], ec[t][c], s1i);
+                    }
+                    const float xr = s1r * rz, xi = s1i * rz;
+                    // two-term variance (bamp.py:74-76): sum_k |xhat - s_k|^2 e_k factorises the same way
+                    float dr = 0.f, di = 0.f;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const float er = xr - G.lrf[l], ei = xi - G.lif[l];
+                        dr = fmaf(er * er, Er[t][l], dr);
+                        di = fmaf(ei * ei, Ei[t][l], di);
+                    }
+                    float spread = fmaf(dr, B0[t], A0[t] * di);
+#pragma unroll
+                    for (int c = 0; c < kGridCorrMax; ++c) {
+                        const float er = xr - G.scr[c], ei = xi - G.sci[c];
+                        spread = fmaf(fmaf(er, er, ei * ei), ec[t][c], spread);
+                    }
+                    xr_[t] = xr;
+                    xi_[t] = xi;
+                    vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
+                }
+            } else {
+                double qr[CP], qi[CP];
+                float lmax[CP], smax[CP];
+#pragma unroll
+                for (int t = 0; t < CP; ++t) {
+                    const float rt = fast_rcp(cov[t] * 0.5f);
+                    const float q_r = xmap[t].x * rt, q_i = xmap[t].y * rt;
+                    qr[t] = (double)q_r;
+                    qi[t] = (double)q_i;
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < K_; ++k) m = fmaxf(m, fmaf(q_r, al.ref[k], q_i * al.imf[k]));
+                    lmax[t] = (lane + 32 * t < N) ? m : -INFINITY;
+                }
+                // section maxima (only approximately the true maxima: they are a common shift, nothing else)
+                section_max<M_, CP>(lmax, smax);
+                // exp pass: e = 2^((x - shift) log2 e); per-antenna sums S0 = sum e, S1 = sum sym e
+                float S0[CP], S1r[CP], S1i[CP];
+#pragma unroll
+                for (int t = 0; t < CP; ++t) {
+                    const double shift = (double)smax[t];
+                    float s0 = 0.f, s1r = 0.f, s1i = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K_; ++k) {
+                        const double x = fma(qr[t], al.re[k], qi[t] * al.im[k]);
+                        const float e = fast_ex2((float)(x - shift) * 1.4426950408889634f);
+                        ebuf[(t * K_ + k) * 32 + lane] = e;
+                        s0 += e;
+                        s1r = fmaf(al.ref[k], e, s1r);
+                        s1i = fmaf(al.imf[k], e, s1i);
+                    }
+                    S0[t] = (lane + 32 * t < N) ? s0 : 0.f;
+                    S1r[t] = s1r;
+                    S1i[t] = s1i;
+                }
+                float Z[CP], others[CP];
+                section_sum_excl<M_, CP>(S0, Z, others);
+                // mean and two-term variance (bamp.py:72-76)
+#pragma unroll
+                for (int t = 0; t < CP; ++t) {
+                    const float rz = fast_rcp(Z[t]);
+                    const float xr = S1r[t] * rz, xi = S1i[t] * rz;
+                    float spread = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K_; ++k) {
+                        const float e = ebuf[(t * K_ + k) * 32 + lane];
+                        const float dr = xr - al.ref[k], di = xi - al.imf[k];
+                        spread = fmaf(fmaf(dr, dr, di * di), e, spread);
+                    }
+                    xr_[t] = xr;
+                    xi_[t] = xi;
+                    vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
                 }
             }
-            // mean and two-term variance (bamp.py:72-76), exit test on var (bamp.py:140)
+            // exit test on var (bamp.py:140), publish the new estimate for the next row pass
             bool close = true;
             float s_tau = 0.f, s_var = 0.f, s_mse = 0.f;
 #pragma unroll
             for (int t = 0; t < CP; ++t) {
-                const float rz = fast_rcp(Z[t]);
-                const float xr = S1r[t] * rz, xi = S1i[t] * rz;
-                float spread = 0.f;
-#pragma unroll
-                for (int k = 0; k < K_; ++k) {
-                    const float e = ebuf[(t * K_ + k) * 32 + lane];
-                    const float dr = xr - al.ref[k], di = xi - al.imf[k];
-                    spread = fmaf(fmaf(dr, dr, di * di), e, spread);
-                }
-                const float vn = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
-                const bool live = lane + 32 * t < N;
-                if (live) {
+                const float xr = xr_[t], xi = xi_[t], vn = vn_[t];
+                const int col = lane + 32 * t;
+                if (col < N) {
                     close &= fabsf(vn - var[t]) <= __fadd_rn(kAtol, fabsf(__fmul_rn(kRtol, var[t])));
-                    colvec[lane + 32 * t] = make_float4(xr, xi, vn, 0.f);
+                    publish(col, xr, xi, vn);
                     if (a.traj) {
                         s_tau += cov[t];
                         s_var += vn;
                         if (a.io.x_true) {
-                            const float2 xt = a.io.x_true[f * N + lane + 32 * t];
+                            const float2 xt = a.io.x_true[f * N + col];
                             s_mse += (xr - xt.x) * (xr - xt.x) + (xi - xt.y) * (xi - xt.y);
                         }
                     }
@@ -509,13 +805,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     }
 }
 
-template <int RT, int CTL, int M_, int K_>
+template <int RT, int CTL, int M_, int K_, bool GRID>
 static int launch_shape(const BampArgs& a, cudaStream_t stream) {
     using S = FastShape<RT, CTL, M_, K_>;
     int dev = 0, sms = 0;
     if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = bamp_fast_kernel<RT, CTL, M_, K_>;
+    auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID>;
     const size_t smem = (size_t)S::warp_bytes * kWarpsPerCta;
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute(bamp_fast)"))
@@ -540,8 +836,12 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
         (a.H_stride != 0 && ((size_t)a.H_stride * 8) % 16))
         return AMPSM_ENOFIT;
     const int K = a.al.K;
+    BampArgs b = a;
+    b.grid = make_grid(a.al);
+    if (g.n == 32 && g.N == 64 && g.M == 64 && K == 16 && b.grid.ok && !getenv("AMPSM_NO_GRID"))
+        return launch_shape<8, 8, 64, 16, true>(b, stream);       // C2 with the separable 16-QAM denoiser
 #define AMPSM_SHAPE(RT, CTL, MM, KK) \
-    if (g.n == 4 * RT && g.N == 8 * CTL && g.M == MM && K == KK) return launch_shape<RT, CTL, MM, KK>(a, stream);
+    if (g.n == 4 * RT && g.N == 8 * CTL && g.M == MM && K == KK) return launch_shape<RT, CTL, MM, KK, false>(b, stream);
     AMPSM_SHAPE(8, 8, 64, 16)     // C2: 64 x 32, 16-QAM, one active antenna
     AMPSM_SHAPE(1, 1, 8, 4)       // C1:  8 x  4, QPSK
     AMPSM_SHAPE(8, 8, 64, 4)      // 64 x 32, QPSK

@@ -4,9 +4,23 @@
 
 namespace ampsm {
 
+constexpr int kGridMax = 4;
+constexpr int kGridCorrMax = 2;
+// Product-grid view of an alphabet (see bamp_fast.cu): sorted real / imaginary levels, in the log2 domain for the
+// exponents (x log2 e) and plain for the moments, plus the grid points whose multiplicity differs from one.
+struct DevGrid {
+    int ok, nr, ni, ncorr;
+    double lr2[kGridMax], li2[kGridMax];
+    float lr2f[kGridMax], li2f[kGridMax], lrf[kGridMax], lif[kGridMax];
+    int ca[kGridCorrMax], cb[kGridCorrMax];
+    float cw[kGridCorrMax];                  // multiplicity - 1 (0: unused slot)
+    float scr[kGridCorrMax], sci[kGridCorrMax];   // the corrected point itself
+};
+
 struct BampArgs {
     Geom g;
     DevAlphabet al;
+    DevGrid grid;
     const float2* H;
     long long H_stride;          // complex elements between frames, 0 = shared
     const float2* y;
@@ -80,5 +94,6 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
 int launch_loss(const LossArgs& a, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);
+int probe_fp32x2(int device, double* tflops);
 
 }  // namespace ampsm

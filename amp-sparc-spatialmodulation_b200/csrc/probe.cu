@@ -17,6 +17,55 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// same arithmetic issued as packed fp32x2 FMAs (FFMA2, sm_100): half the instructions for the same flops
+__global__ void __launch_bounds__(256) ffma2_probe_kernel(float* out, int iters, float a, float b) {
+    float2 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = make_float2(threadIdx.x * 1e-3f + u, threadIdx.x * 2e-3f + u);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) x[v] = __ffma2_rn(x[v], aa, bb);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u].x + x[u].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int probe_fp32x2(int device, double* tflops) {
+    if (!tflops) return AMPSM_EINVAL;
+    if (int e = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return e;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    if (int e = check_cuda(cudaMalloc(&out, (size_t)blocks * threads * 4), "cudaMalloc(probe)")) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        ffma2_probe_kernel<<<blocks, threads>>>(out, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 2 * 8 * 16 * (double)iters * blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return check_cuda(cudaGetLastError(), "ffma2 probe");
+}
+
 int probe_fp32(int device, double* tflops) {
     if (!tflops) return AMPSM_EINVAL;
     if (int e = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return e;

@@ -170,6 +170,7 @@ int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t fr
  * kernel launches this library has made since the last reset (bench.py's gpu_launches).
  */
 int ampsm_probe_fp32_tflops(int device, double* tflops);
+int ampsm_probe_fp32x2_tflops(int device, double* tflops);   /* same, issued as packed FFMA2 */
 int64_t ampsm_launch_count(int reset);
 
 #ifdef __cplusplus
