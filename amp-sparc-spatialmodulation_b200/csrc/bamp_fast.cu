@@ -41,7 +41,8 @@ struct FastShape {
     static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // padded slots (see the kernel)
     static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 20 + 127) & ~127;     // float4 per column + the variance array
     static constexpr int wvec_bytes = ((n > 32 ? n : 32) * 8 + 127) & ~127;
-    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + 128;
+    static constexpr int state_bytes = 32 * 16 + 32 * 8 + (N > 32 ? N : 32) * 8 + 128;   // z/u, y, xmap, counters
+    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + state_bytes + 128;
 };
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -127,12 +128,13 @@ static DevGrid make_grid(const DevAlphabet& al) {
         g.lr2f[i] = (float)g.lr2[i]; g.li2f[i] = (float)g.li2[i];
         g.lrf[i] = (float)lr[i]; g.lif[i] = (float)li[i];
     }
-    for (int c = 0; c < kGridCorrMax; ++c) {
-        if (c >= nc) { g.ca[c] = 0; g.cb[c] = 0; g.cw[c] = 0.f; }
-        g.scr[c] = g.lrf[g.ca[c]];
-        g.sci[c] = g.lif[g.cb[c]];
+    for (int i = 0; i < kGridMax; ++i) {
+        g.dpos_r[i] = (float)(g.lr2[i] - g.lr2[kGridMax - 1]); g.dneg_r[i] = (float)(g.lr2[i] - g.lr2[0]);
+        g.dpos_i[i] = (float)(g.li2[i] - g.li2[kGridMax - 1]); g.dneg_i[i] = (float)(g.li2[i] - g.li2[0]);
     }
-    g.ok = 1;
+    // the device code hard-wires the reference table's two irregular grid points (see the kernel)
+    const bool ref16 = nc == 2 && g.ca[0] == 1 && g.cb[0] == 3 && g.cw[0] == 1.f && g.ca[1] == 2 && g.cb[1] == 0 && g.cw[1] == -1.f;
+    g.ok = ref16 ? 1 : 0;
     return g;
 }
 
@@ -223,7 +225,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     float4* rowvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes);
     float4* colvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes);
     float2* wvec = reinterpret_cast<float2*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes + S::wvec_bytes);
+    // per-lane state that is only touched in one phase lives in shared memory, not in registers: the H tile needs them
+    unsigned char* st = ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes + S::wvec_bytes;
+    float4* rowstate = reinterpret_cast<float4*>(st);                       // {z.re, z.im, u, -} of row `lane`
+    float2* ystate = reinterpret_cast<float2*>(st + 32 * 16);               // y of row `lane`
+    float2* xmapvec = reinterpret_cast<float2*>(st + 32 * 16 + 32 * 8);     // xmap of every column (Loss input)
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(st + 32 * 16 + 32 * 8 + (N > 32 ? N : 32) * 8);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(st + S::state_bytes);
 
     const Geom& g = a.g;
     const DevAlphabet& al = a.al;
@@ -247,9 +255,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     if (f < a.frames) prefetch(f);
     uint32_t phase = 0;
 
-    // per-warp counters (lane 0 holds the totals that matter; sq sums are reduced at the flush)
-    unsigned long long c_frames = 0, c_ferr = 0, c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0, c_iters = 0, c_nan = 0;
-    double c_sq = 0.0;
+    // per-warp counters in shared memory (slots as the Counter enum, slot 12 = squared-error sum as double)
+    if (lane < 16) cnt[lane] = 0ull;
+    __syncwarp();
 
     // H and |H|^2 tiles.  PAIR: every element stays the natural (re, im) register pair it is loaded as, and |H|^2 is
     // paired over the lane's adjacent columns, so that all mat-vec FMAs are packed FFMA2 (fma.rn.f32x2, sm_100: half
@@ -327,19 +335,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
         };
 
         // state (bamp.py:20-25): row owner lane r keeps z_r, u_r; column owner lane keeps xhat, var of col lane+32t
-        float2 z = yv;
-        float u = sigma2;
-        float2 xh[CP], xmap[CP];
-        float var[CP], cov[CP];
-#pragma unroll
-        for (int t = 0; t < CP; ++t) {
-            xh[t] = make_float2(0.f, 0.f);
-            xmap[t] = make_float2(0.f, 0.f);
-            var[t] = 1.0f;
-            cov[t] = 0.f;
-            if (lane + 32 * t < N) publish(lane + 32 * t, 0.f, 0.f, 1.0f);
+        if (lane < n) {
+            rowstate[lane] = make_float4(yv.x, yv.y, sigma2, 0.f);   // z = y, u = sigma2
+            ystate[lane] = yv;
         }
+#pragma unroll
+        for (int t = 0; t < CP; ++t)
+            if (lane + 32 * t < N) publish(lane + 32 * t, 0.f, 0.f, 1.0f);   // xhat = 0, var = 1
         __syncwarp();
+        // read back the estimate a column owner published (xhat, var)
+        auto owned = [&](int col, float2& x, float& v) {
+            const float4 q = colvec[colslot(col)];
+            if constexpr (PAIR) {
+                x = make_float2(q.x, q.z);
+                v = varvec[col];
+            } else {
+                x = make_float2(q.x, q.y);
+                v = q.z;
+            }
+        };
 
         int t_done = 0;
         for (int it = 0; it < g.max_iters; ++it) {
@@ -401,19 +415,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             }
             __syncwarp();
             if (lane < n) {
-                float sv = 0.f, sr = 0.f, si = 0.f;
+                float4 p[8];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const float4 p = xch[lane * 8 + (b ^ (lane & 7))];
-                    sv += p.x; sr += p.y; si += p.z;
-                }
+                for (int b = 0; b < 8; ++b) p[b] = xch[lane * 8 + (b ^ (lane & 7))];
+                // tree, not a chain: this sits on the iteration's critical path
+                const float sv = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
+                const float sr = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
+                const float si = ((p[0].z + p[1].z) + (p[2].z + p[3].z)) + ((p[4].z + p[5].z) + (p[6].z + p[7].z));
                 // z = Hx - v (y - z)/u_old ; u = v + sigma2 ; operands of the column pass (bamp.py:60-63)
-                const float ru = fast_rcp(u);
+                const float4 rs = rowstate[lane];
+                const float2 z = make_float2(rs.x, rs.y), yv = ystate[lane];
+                const float ru = fast_rcp(rs.z);
                 const float2 zn = make_float2(sr - sv * (yv.x - z.x) * ru, si - sv * (yv.y - z.y) * ru);
                 const float un = sv + sigma2;
                 const float rn = fast_rcp(un);
-                z = zn;
-                u = un;
+                rowstate[lane] = make_float4(zn.x, zn.y, un, 0.f);
                 const float gx = (yv.x - zn.x) * rn, gy = (yv.y - zn.y) * rn;
                 if constexpr (PAIR) {
                     rowvec[lane + (lane >> 3)] = make_float4(gx, gy, gy, -gx);     // operand pairs (gx,gy), (gy,-gx)
@@ -482,61 +498,76 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                 xch[(col >> 1) * 8 + chunk] = make_float4(cc[c], cr[c], ci[c], 0.f);
             }
             __syncwarp();
+            float2 xh[CP], xmap[CP];
+            float var[CP], cov[CP];
 #pragma unroll
             for (int t = 0; t < CP; ++t) {
                 const int col = lane + 32 * t;
+                xh[t] = xmap[t] = make_float2(0.f, 0.f);
+                var[t] = cov[t] = 0.f;
                 if (col < N) {
-                    float sc = 0.f, sr = 0.f, si = 0.f;
+                    float4 p[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 p = xch[(col >> 1) * 8 + (((col & 1) * 4 + q) ^ ((col >> 1) & 7))];
-                        sc += p.x; sr += p.y; si += p.z;
-                    }
+                    for (int q = 0; q < 4; ++q) p[q] = xch[(col >> 1) * 8 + (((col & 1) * 4 + q) ^ ((col >> 1) & 7))];
+                    const float sc = (p[0].x + p[1].x) + (p[2].x + p[3].x);
+                    const float sr = (p[0].y + p[1].y) + (p[2].y + p[3].y);
+                    const float si = (p[0].z + p[1].z) + (p[2].z + p[3].z);
+                    owned(col, xh[t], var[t]);
                     cov[t] = fast_rcp(sc);
                     xmap[t] = make_float2(fmaf(cov[t], sr, xh[t].x), fmaf(cov[t], si, xh[t].y));
+                    xmapvec[col] = xmap[t];
                 }
             }
             __syncwarp();     // everyone is done with the column partials: the region becomes the exp buffer
             // ================= denoiser (bamp.py:66-77), tau = cov/2 =================
             float xr_[CP], xi_[CP], vn_[CP];
             if constexpr (GRID) {
-                // separable path: e_k = Er[a_k] Ei[b_k], 8 exponentials per antenna; everything in the log2 domain
-                // (levels pre-multiplied by log2 e), one DFMA per exponent: 2^(q*level - shift) straight into ex2
+                // Separable path for the reference's 16-QAM table: e_k = Er[a_k] Ei[b_k] on the 4 x 4 level grid, with the
+                // table's two irregular points hard-wired (config.py:112: (-1,+3) twice -> grid point (1,3) weight +1,
+                // (+1,-3) missing -> grid point (2,0) weight -1; launch_bamp_fast checks the table has this pattern).
+                // Exponents are formed relative to the antenna's own largest level product, i.e. as ONE float product
+                // q * (level - level_max) log2 e -- no cancellation, so float32 is exact enough; only the antenna's
+                // offset to the section maximum (a difference of two large numbers) is taken in float64.
                 const DevGrid& G = a.grid;
                 float q_r[CP], q_i[CP], lmax[CP], smax[CP];
+                double lmd[CP];
 #pragma unroll
                 for (int t = 0; t < CP; ++t) {
                     const float rt = fast_rcp(cov[t] * 0.5f);
                     q_r[t] = xmap[t].x * rt;
                     q_i[t] = xmap[t].y * rt;
-                    // levels are sorted: the largest product sits at one end (approximate: only a common shift)
-                    const float lm = fmaxf(q_r[t] * G.lr2f[0], q_r[t] * G.lr2f[3]) + fmaxf(q_i[t] * G.li2f[0], q_i[t] * G.li2f[3]);
-                    lmax[t] = (lane + 32 * t < N) ? lm : -INFINITY;
+                    lmd[t] = (double)q_r[t] * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]) + (double)q_i[t] * (q_i[t] >= 0.f ? G.li2[3] : G.li2[0]);
+                    lmax[t] = (lane + 32 * t < N) ? (float)lmd[t] : -INFINITY;
                 }
-                section_max<M_, CP>(lmax, smax);
-                float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], ec[CP][kGridCorrMax];
+                if constexpr (L_ == 1) {           // the section is the whole warp: one CREDUX instead of a shuffle tree
+                    float m = lmax[0];
+#pragma unroll
+                    for (int t = 1; t < CP; ++t) m = fmaxf(m, lmax[t]);
+                    float r;
+                    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(m));
+#pragma unroll
+                    for (int t = 0; t < CP; ++t) smax[t] = r;
+                } else {
+                    section_max<M_, CP>(lmax, smax);
+                }
+                float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], e13[CP], e20[CP];
 #pragma unroll
                 for (int t = 0; t < CP; ++t) {
-                    const double qrd = (double)q_r[t], qid = (double)q_i[t];
-                    const double sr = qrd * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]);      // exact max of the real-part products
-                    // x_k - smax = (ur - sr) + (ui - si) + (sr + si - smax): the imaginary factor carries sr - smax
-                    const double off_i = sr - (double)smax[t];
+                    const float off = (float)(lmd[t] - (double)smax[t]);       // <= 0 up to rounding
+                    const bool rp = q_r[t] >= 0.f, ip = q_i[t] >= 0.f;
                     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
-                        Er[t][l] = fast_ex2((float)fma(qrd, G.lr2[l], -sr));
-                        Ei[t][l] = fast_ex2((float)fma(qid, G.li2[l], off_i));
+                        Er[t][l] = fast_ex2(q_r[t] * (rp ? G.dpos_r[l] : G.dneg_r[l]));
+                        Ei[t][l] = fast_ex2(fmaf(q_i[t], ip ? G.dpos_i[l] : G.dneg_i[l], off));
                         a0 += Er[t][l];
                         a1 = fmaf(G.lrf[l], Er[t][l], a1);
                         b0 += Ei[t][l];
                         b1 = fmaf(G.lif[l], Ei[t][l], b1);
                     }
-                    float s0 = a0 * b0;
-#pragma unroll
-                    for (int c = 0; c < kGridCorrMax; ++c) {      // multiplicity corrections (weight 0 when unused)
-                        ec[t][c] = G.cw[c] * pick4(Er[t], G.ca[c]) * pick4(Ei[t], G.cb[c]);
-                        s0 += ec[t][c];
-                    }
+                    e13[t] = Er[t][1] * Ei[t][3];
+                    e20[t] = Er[t][2] * Ei[t][0];
+                    const float s0 = fmaf(a0, b0, e13[t] - e20[t]);
                     S0[t] = (lane + 32 * t < N) ? s0 : 0.f;
                     A0[t] = a0; A1[t] = a1; B0[t] = b0; B1[t] = b1;
                 }
@@ -545,27 +576,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
 #pragma unroll
                 for (int t = 0; t < CP; ++t) {
                     const float rz = fast_rcp(Z[t]);
-                    float s1r = A1[t] * B0[t], s1i = A0[t] * B1[t];
-#pragma unroll
-                    for (int c = 0; c < kGridCorrMax; ++c) {
-                        s1r = fmaf(G.scr[c], ec[t][c], s1r);
-                        s1i = fmaf(G.sci[c], ec[t][c], s1i);
-                    }
+                    const float s1r = fmaf(A1[t], B0[t], fmaf(G.lrf[1], e13[t], -G.lrf[2] * e20[t]));
+                    const float s1i = fmaf(A0[t], B1[t], fmaf(G.lif[3], e13[t], -G.lif[0] * e20[t]));
                     const float xr = s1r * rz, xi = s1i * rz;
                     // two-term variance (bamp.py:74-76): sum_k |xhat - s_k|^2 e_k factorises the same way
-                    float dr = 0.f, di = 0.f;
+                    float dr = 0.f, di = 0.f, er2[4], ei2[4];
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
                         const float er = xr - G.lrf[l], ei = xi - G.lif[l];
-                        dr = fmaf(er * er, Er[t][l], dr);
-                        di = fmaf(ei * ei, Ei[t][l], di);
+                        er2[l] = er * er;
+                        ei2[l] = ei * ei;
+                        dr = fmaf(er2[l], Er[t][l], dr);
+                        di = fmaf(ei2[l], Ei[t][l], di);
                     }
                     float spread = fmaf(dr, B0[t], A0[t] * di);
-#pragma unroll
-                    for (int c = 0; c < kGridCorrMax; ++c) {
-                        const float er = xr - G.scr[c], ei = xi - G.sci[c];
-                        spread = fmaf(fmaf(er, er, ei * ei), ec[t][c], spread);
-                    }
+                    spread = fmaf(er2[1] + ei2[3], e13[t], spread);
+                    spread = fmaf(-(er2[2] + ei2[0]), e20[t], spread);
                     xr_[t] = xr;
                     xi_[t] = xi;
                     vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
@@ -643,8 +669,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                         }
                     }
                 }
-                xh[t] = make_float2(xr, xi);
-                var[t] = vn;
             }
             const bool all_close = __all_sync(0xffffffffu, close);
             __syncwarp();     // colvec is published, the exp buffer is free: the next row pass may start
@@ -664,10 +688,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
         }
 
         // ================= outputs =================
+        float2 xh[CP], xmap[CP];
+        float var[CP];
 #pragma unroll
         for (int t = 0; t < CP; ++t) {
             const int col = lane + 32 * t;
+            xh[t] = xmap[t] = make_float2(0.f, 0.f);
+            var[t] = 0.f;
             if (col < N) {
+                owned(col, xh[t], var[t]);
+                xmap[t] = xmapvec[col];
                 if (a.xmap) a.xmap[f * N + col] = xmap[t];
                 if (a.xmmse) a.xmmse[f * N + col] = xh[t];
                 if (a.var) a.var[f * N + col] = var[t];
@@ -680,8 +710,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                     a.traj[(f * g.max_iters + it) * 3 + q] = a.traj[(f * g.max_iters + t_done - 1) * 3 + q];
         }
         if (lane == 0 && a.iters) a.iters[f] = t_done;
-        c_frames += 1;
-        c_iters += t_done;
+        unsigned long long c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0;
+        if (lane == 0) {
+            cnt[C_FRAMES] += 1;
+            cnt[C_ITERS] += t_done;
+        }
 
         // ================= Loss: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1 shapes only ========
         if (a.io.x_true) {
@@ -759,49 +792,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                     }
                 }
             }
-            c_sq += sq;
-            if (__any_sync(0xffffffffu, wrong)) c_ferr += 1;        // Lin = 1: one time slot per frame
-            if (__any_sync(0xffffffffu, nan_seen)) c_nan += 1;
+            // once per frame: fold the lanes' label counters and book everything in the warp's shared counters
+            auto wsum = [](unsigned long long v) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                return v;
+            };
+            const unsigned long long packed = wsum(c_idx | (c_sym << 12) | (c_ibit << 24) | (c_sbit << 44));   // <= 64 sections, 64 bits each
+            sq = warp_sum(sq);
+            const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
+            if (lane == 0) {
+                cnt[C_INDEX_ERR] += packed & 0xfffull;
+                cnt[C_SYMBOL_ERR] += (packed >> 12) & 0xfffull;
+                cnt[C_INDEX_BIT] += (packed >> 24) & 0xfffffull;
+                cnt[C_SYMBOL_BIT] += packed >> 44;
+                cnt[C_FRAME_ERR] += any_wrong;                       // Lin = 1: one time slot per frame
+                cnt[C_NAN_FRAMES] += any_nan;
+                reinterpret_cast<double*>(cnt)[12] += sq;
+            }
         }
         __syncwarp();
     }
 
-    // ---- flush the warp's counters (label counters are spread over lanes: reduce them first)
-    if (a.io.counters) {
-        auto wsum = [](unsigned long long v) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            return v;
-        };
-        c_idx = wsum(c_idx);
-        c_sym = wsum(c_sym);
-        c_ibit = wsum(c_ibit);
-        c_sbit = wsum(c_sbit);
-        c_sq = warp_sum(c_sq);
-        if (lane == 0) {
-            unsigned long long* out = a.io.counters;
-            if (c_frames) atomicAdd(out + C_FRAMES, c_frames);
-            if (c_ferr) {
-                atomicAdd(out + C_FRAME_ERR, c_ferr);
-                atomicAdd(out + C_SLOT_ERR, c_ferr);
-                atomicAdd(out + C_SLOT_FIRST, c_ferr);
-                atomicAdd(out + C_SLOT_MID, c_ferr);
-                atomicAdd(out + C_SLOT_LAST, c_ferr);
-            }
-            if (c_idx) atomicAdd(out + C_INDEX_ERR, c_idx);
-            if (c_sym) atomicAdd(out + C_SYMBOL_ERR, c_sym);
-            if (c_ibit) atomicAdd(out + C_INDEX_BIT, c_ibit);
-            if (c_sbit) atomicAdd(out + C_SYMBOL_BIT, c_sbit);
-            if (c_iters) atomicAdd(out + C_ITERS, c_iters);
-            if (c_nan) atomicAdd(out + C_NAN_FRAMES, c_nan);
-            if (c_sq != 0.0) {
-                double* sq = reinterpret_cast<double*>(out) + C_SQERR;
-                atomicAdd(sq + 0, c_sq);      // Lin = 1: slot 0 = middle slot = last slot
-                atomicAdd(sq + 1, c_sq);
-                atomicAdd(sq + 2, c_sq);
-                atomicAdd(sq + 3, c_sq);
-            }
+    // ---- flush the warp's counters
+    __syncwarp();
+    if (a.io.counters && lane == 0) {
+        unsigned long long* out = a.io.counters;
+        const int plain[] = {C_FRAMES, C_INDEX_ERR, C_SYMBOL_ERR, C_INDEX_BIT, C_SYMBOL_BIT, C_ITERS, C_NAN_FRAMES};
+        for (int k : plain)
+            if (cnt[k]) atomicAdd(out + k, cnt[k]);
+        if (cnt[C_FRAME_ERR]) {          // Lin = 1: the frame is its only, first, middle and last time slot
+            const int slots[] = {C_FRAME_ERR, C_SLOT_ERR, C_SLOT_FIRST, C_SLOT_MID, C_SLOT_LAST};
+            for (int k : slots) atomicAdd(out + k, cnt[C_FRAME_ERR]);
         }
+        const double sq = reinterpret_cast<double*>(cnt)[12];
+        if (sq != 0.0)
+            for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
     }
 }
 

@@ -14,7 +14,7 @@ struct DevGrid {
     float lr2f[kGridMax], li2f[kGridMax], lrf[kGridMax], lif[kGridMax];
     int ca[kGridCorrMax], cb[kGridCorrMax];
     float cw[kGridCorrMax];                  // multiplicity - 1 (0: unused slot)
-    float scr[kGridCorrMax], sci[kGridCorrMax];   // the corrected point itself
+    float dpos_r[kGridMax], dneg_r[kGridMax], dpos_i[kGridMax], dneg_i[kGridMax];   // (level - top/bottom level) log2 e
 };
 
 struct BampArgs {
