@@ -312,6 +312,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             if (nf < a.frames) prefetch(nf);
         }
         const float sigma2 = a.sigma2_pf ? a.sigma2_pf[f] : a.sigma2;
+        if (a.io.x_true) {   // the Loss epilogue reads these once, right after the last iteration: start the fetch now
+            if (lane * 16 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.x_true + f * N + lane * 16));
+            if (lane == 31) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.idx_true + f * L_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.sym_true + f * L_));
+            }
+        }
 
         // column-vector exchange.  PAIR: per column one float4 {xx,xx,xy,xy} (the broadcast operand pairs of the row
         // pass), placed so that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without
@@ -727,11 +734,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                 best[t] = Pick{-INFINITY, 0x7fffffff};
                 if (col < N) {
                     const int m = col % M_;
+                    // in-order scan (flat index increases with k): the first maximum wins, so replace only on
+                    // "strictly greater"; a NaN wins once and then sticks (np.argmax).  Predicated selects, no branches.
+                    const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
+                    double bv = __dadd_rn(__dmul_rn(xr, al.re[0]), __dmul_rn(xi, al.im[0]));
+                    int bk = 0;
 #pragma unroll
-                    for (int k = 0; k < K_; ++k) {
-                        Pick c{__dadd_rn(__dmul_rn((double)xmap[t].x, al.re[k]), __dmul_rn((double)xmap[t].y, al.im[k])), m * K_ + k};
-                        if (pick_better(c, best[t])) best[t] = c;
+                    for (int k = 1; k < K_; ++k) {
+                        const double v = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
+                        const bool upd = (bv == bv) & ((v > bv) | (v != v));
+                        bv = upd ? v : bv;
+                        bk = upd ? k : bk;
                     }
+                    best[t] = Pick{bv, m * K_ + bk};
                     nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
                 }
             }

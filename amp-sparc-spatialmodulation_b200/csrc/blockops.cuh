@@ -171,10 +171,10 @@ struct Pick {
     int idx;
 };
 // np.argmax order: NaN beats everything, then larger value, then smaller flat index (loss.py:296)
+// (written with bitwise predicate logic so that it compiles to SETP/SEL, not branches)
 __device__ __forceinline__ bool pick_better(const Pick& a, const Pick& b) {
-    const bool an = a.v != a.v, bn = b.v != b.v;
-    if (an || bn) return an && (!bn || a.idx < b.idx);
-    return a.v > b.v || (a.v == b.v && a.idx < b.idx);
+    const bool an = a.v != a.v, bn = b.v != b.v, first = a.idx < b.idx;
+    return (an & (!bn | first)) | (!an & !bn & ((a.v > b.v) | ((a.v == b.v) & first)));
 }
 
 // Decide one section with one warp.  Returns (antenna, symbol index) in every lane; symbol index < 0 when the

@@ -62,7 +62,9 @@ def test_bamp_matches_reference_goldens(name, mode):
     assert per_frame.max() < 1e-2 and np.median(per_frame) < 1e-4
     check_trajectory(name + ".tau", out["traj"][:, :, 0], g["tau"])
     check_trajectory(name + ".var", out["traj"][:, :, 1], g["varm"])
-    check_trajectory(name + ".mse", out["traj"][:, :, 2], g["mse"], loose=0.2)
+    # float32 exp: the tiny estimates of the inactive antennas are differences of nearly equal exponentials, good to
+    # ~2^-22/|q| only; an MSE below 1e-7 of the unit symbol power (-70 dB) is therefore compared in float64 mode only
+    check_trajectory(name + ".mse", out["traj"][:, :, 2], g["mse"], loose=0.2, floor=1e-9 if mode["exp"] == "f64" else 1e-7)
     # hard decisions and every error count identical to the reference's own Loss on its own estimates
     assert decision_mismatch_frames(cfg, out["xmap"], g["xmap"]).size == 0
     for snr_db, have, want, _ in out["counters"]:
