@@ -298,7 +298,8 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bamp_c2_bytes_per_launch")
+        per_frame = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bamp_c2_bytes_per_frame")
+        traffic = per_frame * frames if per_frame else None       # ncu dram bytes per frame x frames of this launch
     except OSError:
         pass
     per_gpu_frames_per_launch = frames
