@@ -117,7 +117,7 @@ def make_problem(config, frames, *, R=0, early_exit=True, shift='section', exp='
     p.decision = 0 if config.mode == 'sparc' else 1
     count = config.Lin * max(int(frames), 1) * config.Na
     p.index_bits_kept = int(math.ceil(math.log2(count))) if count > 0 else 0
-    p.kernel = {'auto': 0, 'generic': 1, 'fast': 2}[kernel]
+    p.kernel = {'auto': 0, 'generic': 1, 'fast': 2, 'pair': 3}[kernel]
     p.frame_base = int(frame_base)
     return p
 

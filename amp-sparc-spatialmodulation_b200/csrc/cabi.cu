@@ -1,5 +1,6 @@
 // C-ABI entry points of libampsm_b200.so (declared in include/ampsm_b200.h): argument checking, kernel selection,
 // and the host-buffer variants that overlap chunked host<->device copies with the kernels on two streams.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -237,11 +238,15 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0) {
+        if (p->kernel != 2 && !(p->kernel == 0 && getenv("AMPSM_NO_PAIR"))) {
+            const int rc = launch_bamp_pair(k, st);
+            if (rc != AMPSM_ENOFIT || p->kernel == 3) return rc;
+        }
         const int rc = launch_bamp_fast(k, st);
         if (rc != AMPSM_ENOFIT) return rc;
         if (p->kernel == 2) return rc;
-    } else if (p->kernel == 2) {
-        set_error("BAMP fast kernel supports exp_f64=0, shift_mode=0 only");
+    } else if (p->kernel == 2 || p->kernel == 3) {
+        set_error("BAMP register-resident kernels support exp_f64=0, shift_mode=0 only");
         return AMPSM_ENOFIT;
     }
     return launch_bamp_generic(k, p->exp_f64 != 0, st);

@@ -89,6 +89,7 @@ struct LossArgs {
 
 int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
+int launch_bamp_pair(const BampArgs& a, cudaStream_t stream);       // two warps per frame (64 x 32 shapes), else AMPSM_ENOFIT
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);

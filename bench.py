@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--snr-db", type=float, default=15.0)
     ap.add_argument("--e2e-frames", type=int, default=1 << 17)
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast", "pair"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed-t", action="store_true")
     return ap.parse_args()

@@ -57,7 +57,8 @@ typedef struct {
     int32_t exp_f64;         /* 1: denoiser exponents/exp in float64 as the reference; 0: float32 exp      */
     int32_t decision;        /* 0: MAP decision (loss.py:282-302, mode 'sparc'); 1: segmented (223-250)    */
     int32_t index_bits_kept; /* low bits of the index XOR that Loss.de2bi keeps (loss.py:20,168)           */
-    int32_t kernel;          /* 0: auto, 1: generic shared-memory kernel, 2: register-resident fast kernel */
+    int32_t kernel;          /* 0: auto, 1: generic shared-memory kernel, 2: register-resident kernel, one warp
+                                per frame, 3: register-resident kernel, two warps per frame (64 x 32 shapes)   */
     int32_t reserved0;
     int64_t frame_base;      /* global index of the first frame of this call (flat indices, loss.py:300)   */
 } ampsm_problem;

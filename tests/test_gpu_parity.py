@@ -51,8 +51,11 @@ def run_bamp_golden(name, per_snr=True, **kw):
 @pytest.mark.parametrize("name", ["bamp_c1", "bamp_c2", "bamp_isi", "bamp_seg"])
 @pytest.mark.parametrize("mode", [dict(kernel="generic", exp="f64", shift="reference"),
                                   dict(kernel="generic", exp="f32", shift="section"),
-                                  dict(kernel="auto", exp="f32", shift="section")])
+                                  dict(kernel="auto", exp="f32", shift="section"),
+                                  dict(kernel="fast", exp="f32", shift="section")])
 def test_bamp_matches_reference_goldens(name, mode):
+    if mode["kernel"] == "fast" and name != "bamp_c2":
+        pytest.skip("'auto' already takes the one-warp kernel for this shape (or none fits)")
     g, out = run_bamp_golden(name, **mode)
     cfg = config_from_meta(g["meta"])
     assert np.abs(out["iters"] - g["iters"]).max() <= 1, (out["iters"], g["iters"])

@@ -43,14 +43,15 @@ def ints(c):
     return {k: c[k] for k in INT_KEYS}
 
 
-def test_fast_and_generic_kernels_agree_on_every_count_c2():
+@pytest.mark.parametrize("fast", ["pair", "fast"])
+def test_fast_and_generic_kernels_agree_on_every_count_c2(fast):
     """Two independent kernels (register-resident FFMA2 + separable denoiser vs shared-memory float64-exponent one)
     must take identical hard decisions on 40k frames per SNR point."""
     F = 40000
     cfg = c2(F)
     for snr_db in (5.0, 15.0):
         H, y, x, lab, idx = make_frames(cfg, F, snr_db, seed=11)
-        a = pkg.BAMP(cfg, kernel='fast', outputs=True).detect(H, y, 10 ** (snr_db / 10), x, lab, idx)
+        a = pkg.BAMP(cfg, kernel=fast, outputs=True).detect(H, y, 10 ** (snr_db / 10), x, lab, idx)
         b = pkg.BAMP(cfg, kernel='generic', exp='f64', outputs=True).detect(H, y, 10 ** (snr_db / 10), x, lab, idx)
         ca, cb = a.counters_dict(), b.counters_dict()
         ia, ib = a.iters.cpu().numpy(), b.iters.cpu().numpy()
@@ -101,17 +102,18 @@ def test_high_snr_qpsk_decodes_every_frame():
     F = 20000
     cfg = c2(F, alphabet='QPSK')
     H, y, x, lab, idx = make_frames(cfg, F, 30.0, seed=3)
-    for kernel in ('fast', 'generic'):
+    for kernel in ('pair', 'fast', 'generic'):
         c = pkg.BAMP(cfg, kernel=kernel, outputs=False).detect(H, y, 10 ** 3.0, x, lab, idx).counters_dict()
         assert c["frame_err"] == 0 and c["index_bit_err"] == 0 and c["symbol_bit_err"] == 0 and c["nan_frames"] == 0
 
 
-def test_multi_section_fast_shape_matches_generic():
-    """64 x 32, QPSK, Na = 4 (sections of 16 antennas: sub-warp section reductions in the fast kernel)."""
+@pytest.mark.parametrize("fast,Na", [("pair", 4), ("fast", 4), ("pair", 2)])
+def test_multi_section_fast_shape_matches_generic(fast, Na):
+    """64 x 32, QPSK, Na = 4 / 2 (sections of 16 / 32 antennas: sub-warp and whole-warp section reductions)."""
     F = 20000
-    cfg = c2(F, alphabet='QPSK', Na=4)
+    cfg = c2(F, alphabet='QPSK', Na=Na)
     H, y, x, lab, idx = make_frames(cfg, F, 6.0, seed=8)
-    a = pkg.BAMP(cfg, kernel='fast').detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
+    a = pkg.BAMP(cfg, kernel=fast).detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
     b = pkg.BAMP(cfg, kernel='generic', exp='f64').detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
     diff = {k: (a[k], b[k]) for k in INT_KEYS if a[k] != b[k]}
     assert all(abs(u - v) <= 2 for u, v in diff.values()), diff
@@ -120,7 +122,7 @@ def test_multi_section_fast_shape_matches_generic():
 def test_shared_matrix_and_edge_frame_counts():
     cfg = c2(7)
     H, y, x, lab, idx = make_frames(cfg, 7, 12.0, seed=2, shared_H=True)
-    for kernel in ('fast', 'generic'):
+    for kernel in ('pair', 'fast', 'generic'):
         d = pkg.BAMP(pkg.Config(64, 1, 32, 1, 1, batch=7, generator_mode='sparc', alphabet='16QAM', channel_profile='uniform',
                                 device=DEV), kernel=kernel).detect(H, y, 10 ** 1.2, x, lab, idx)
         assert d.counters_dict()["frames"] == 7
