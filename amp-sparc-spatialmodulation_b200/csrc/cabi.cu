@@ -238,7 +238,7 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0) {
-        if (p->kernel != 2 && !(p->kernel == 0 && getenv("AMPSM_NO_PAIR"))) {
+        if (p->kernel == 3 || (p->kernel == 0 && getenv("AMPSM_PAIR"))) {   // measured slower than the one-warp kernel: opt-in
             const int rc = launch_bamp_pair(k, st);
             if (rc != AMPSM_ENOFIT || p->kernel == 3) return rc;
         }
@@ -302,6 +302,13 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
     k.io.counters = (unsigned long long*)counters;
     k.xmap = xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
+    if (p->kernel != 1 && !is_double && !p->exp_f64 && p->shift_mode == 0) {
+        const int rc = launch_vamp_fast(k, (cudaStream_t)stream);
+        if (rc != AMPSM_ENOFIT || p->kernel == 2) return rc;
+    } else if (p->kernel == 2) {
+        set_error("VAMP register-resident kernel supports complex64, exp_f64=0, shift_mode=0 only");
+        return AMPSM_ENOFIT;
+    }
     return launch_vamp_generic(k, is_double != 0, p->exp_f64 != 0, (cudaStream_t)stream);
 }
 

@@ -168,4 +168,247 @@ __device__ __forceinline__ void section_sum_excl(const float (&S0)[CP], float (&
 }
 __device__ __forceinline__ float pick4(const float (&v)[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
 
+// ---- section denoiser on the column-owner layout (column = lane + 32 t), one warp per frame ---------------------------
+// Input: q = s / tau (complex64) of the lane's CP columns; output: posterior mean and variance (bamp.py:66-77,
+// vamp.py:96-119).  GRID: the separable path for the reference's 16-QAM table (see bamp_fast.cu); otherwise float64
+// exponent products and differences, float32 ex2, the exponentials parked in `ebuf` (shared, 32 * CP * K_ floats)
+// between the two passes.  "1 - p" comes from the butterfly's exclusive sum (no cancellation), the variance is the
+// reference's two-term form.
+template <int N_, int M_, int K_, bool GRID, int CP>
+__device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float (&q_i)[CP], const DevAlphabet& al, const DevGrid& G,
+                                             float* ebuf, int lane, float (&xr_)[CP], float (&xi_)[CP], float (&vn_)[CP]) {
+    constexpr int L_ = N_ / M_;
+    if constexpr (GRID) {
+        float lmax[CP], smax[CP];
+        double lmd[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            lmd[t] = (double)q_r[t] * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]) + (double)q_i[t] * (q_i[t] >= 0.f ? G.li2[3] : G.li2[0]);
+            lmax[t] = (lane + 32 * t < N_) ? (float)lmd[t] : -INFINITY;
+        }
+        if constexpr (L_ == 1) {           // the section is the whole warp: one CREDUX instead of a shuffle tree
+            float m = lmax[0];
+#pragma unroll
+            for (int t = 1; t < CP; ++t) m = fmaxf(m, lmax[t]);
+            float r;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(m));
+#pragma unroll
+            for (int t = 0; t < CP; ++t) smax[t] = r;
+        } else {
+            section_max<M_, CP>(lmax, smax);
+        }
+        float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], e13[CP], e20[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const float off = (float)(lmd[t] - (double)smax[t]);       // <= 0 up to rounding
+            const bool rp = q_r[t] >= 0.f, ip = q_i[t] >= 0.f;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                Er[t][l] = fast_ex2(q_r[t] * (rp ? G.dpos_r[l] : G.dneg_r[l]));
+                Ei[t][l] = fast_ex2(fmaf(q_i[t], ip ? G.dpos_i[l] : G.dneg_i[l], off));
+                a0 += Er[t][l];
+                a1 = fmaf(G.lrf[l], Er[t][l], a1);
+                b0 += Ei[t][l];
+                b1 = fmaf(G.lif[l], Ei[t][l], b1);
+            }
+            e13[t] = Er[t][1] * Ei[t][3];
+            e20[t] = Er[t][2] * Ei[t][0];
+            const float s0 = fmaf(a0, b0, e13[t] - e20[t]);
+            S0[t] = (lane + 32 * t < N_) ? s0 : 0.f;
+            A0[t] = a0; A1[t] = a1; B0[t] = b0; B1[t] = b1;
+        }
+        float Z[CP], others[CP];
+        section_sum_excl<M_, CP>(S0, Z, others);
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const float rz = fast_rcp(Z[t]);
+            const float s1r = fmaf(A1[t], B0[t], fmaf(G.lrf[1], e13[t], -G.lrf[2] * e20[t]));
+            const float s1i = fmaf(A0[t], B1[t], fmaf(G.lif[3], e13[t], -G.lif[0] * e20[t]));
+            const float xr = s1r * rz, xi = s1i * rz;
+            float dr = 0.f, di = 0.f, er2[4], ei2[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float er = xr - G.lrf[l], ei = xi - G.lif[l];
+                er2[l] = er * er;
+                ei2[l] = ei * ei;
+                dr = fmaf(er2[l], Er[t][l], dr);
+                di = fmaf(ei2[l], Ei[t][l], di);
+            }
+            float spread = fmaf(dr, B0[t], A0[t] * di);
+            spread = fmaf(er2[1] + ei2[3], e13[t], spread);
+            spread = fmaf(-(er2[2] + ei2[0]), e20[t], spread);
+            xr_[t] = xr;
+            xi_[t] = xi;
+            vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
+        }
+    } else {
+        double qr[CP], qi[CP];
+        float lmax[CP], smax[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            qr[t] = (double)q_r[t];
+            qi[t] = (double)q_i[t];
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < K_; ++k) m = fmaxf(m, fmaf(q_r[t], al.ref[k], q_i[t] * al.imf[k]));
+            lmax[t] = (lane + 32 * t < N_) ? m : -INFINITY;
+        }
+        section_max<M_, CP>(lmax, smax);      // only approximately the true maxima: a common shift, nothing else
+        float S0[CP], S1r[CP], S1i[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const double shift = (double)smax[t];
+            float s0 = 0.f, s1r = 0.f, s1i = 0.f;
+#pragma unroll
+            for (int k = 0; k < K_; ++k) {
+                const double x = fma(qr[t], al.re[k], qi[t] * al.im[k]);
+                const float e = fast_ex2((float)(x - shift) * 1.4426950408889634f);
+                ebuf[(t * K_ + k) * 32 + lane] = e;
+                s0 += e;
+                s1r = fmaf(al.ref[k], e, s1r);
+                s1i = fmaf(al.imf[k], e, s1i);
+            }
+            S0[t] = (lane + 32 * t < N_) ? s0 : 0.f;
+            S1r[t] = s1r;
+            S1i[t] = s1i;
+        }
+        float Z[CP], others[CP];
+        section_sum_excl<M_, CP>(S0, Z, others);
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const float rz = fast_rcp(Z[t]);
+            const float xr = S1r[t] * rz, xi = S1i[t] * rz;
+            float spread = 0.f;
+#pragma unroll
+            for (int k = 0; k < K_; ++k) {
+                const float e = ebuf[(t * K_ + k) * 32 + lane];
+                const float dr = xr - al.ref[k], di = xi - al.imf[k];
+                spread = fmaf(fmaf(dr, dr, di * di), e, spread);
+            }
+            xr_[t] = xr;
+            xi_[t] = xi;
+            vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
+        }
+    }
+}
+
+// ---- Loss on the column-owner layout: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1, one warp per frame ----
+// xmap / xh: the lane's CP columns of the decision input and of the MMSE estimate.  Books into the warp's shared
+// counter block `cnt` (slots as the Counter enum, slot 12 = squared-error sum as double); lane 0 writes.
+template <int N_, int M_, int K_, int CP>
+__device__ __forceinline__ void fast_loss(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const Geom& g,
+                                          const LossIO& io, long long f, int lane, unsigned long long* cnt) {
+    constexpr int L_ = N_ / M_;
+    bool wrong = false, nan_seen = false;
+    double sq = 0.0;
+    Pick best[CP];
+#pragma unroll
+    for (int t = 0; t < CP; ++t) {
+        const int col = lane + 32 * t;
+        best[t] = Pick{-INFINITY, 0x7fffffff};
+        if (col < N_) {
+            const int m = col % M_;
+            // in-order scan (flat index increases with k): the first maximum wins, so replace only on "strictly
+            // greater"; a NaN wins once and then sticks (np.argmax).  Predicated selects, no branches.
+            const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
+            double bv = __dadd_rn(__dmul_rn(xr, al.re[0]), __dmul_rn(xi, al.im[0]));
+            int bk = 0;
+#pragma unroll
+            for (int k = 1; k < K_; ++k) {
+                const double v = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
+                const bool upd = (bv == bv) & ((v > bv) | (v != v));
+                bv = upd ? v : bv;
+                bk = upd ? k : bk;
+            }
+            best[t] = Pick{bv, m * K_ + bk};
+            nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
+        }
+    }
+    int dec_ant[CP], dec_k[CP];
+    if constexpr (M_ >= 32) {
+        constexpr int TPS = M_ / 32;
+#pragma unroll
+        for (int s0 = 0; s0 < CP; s0 += TPS) {
+            Pick b = best[s0];
+#pragma unroll
+            for (int q = 1; q < TPS; ++q)
+                if (pick_better(best[s0 + q], b)) b = best[s0 + q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
+                if (pick_better(other, b)) b = other;
+            }
+#pragma unroll
+            for (int q = 0; q < TPS; ++q) {
+                dec_ant[s0 + q] = b.idx / K_;
+                dec_k[s0 + q] = b.idx % K_;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            Pick b = best[t];
+#pragma unroll
+            for (int o = M_ / 2; o > 0; o >>= 1) {
+                Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
+                if (pick_better(other, b)) b = other;
+            }
+            dec_ant[t] = b.idx / K_;
+            dec_k[t] = b.idx % K_;
+        }
+    }
+    unsigned long long c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0;
+#pragma unroll
+    for (int t = 0; t < CP; ++t) {
+        const int col = lane + 32 * t;
+        if (col < N_) {
+            const int sec = col / M_, m = col % M_;
+            const float2 xt = io.x_true[f * N_ + col];
+            const int k = dec_k[t];
+            const float2 h = (m == dec_ant[t]) ? make_float2((float)al.re[k], (float)al.im[k]) : make_float2(0.f, 0.f);
+            wrong |= (h.x != xt.x) || (h.y != xt.y);
+            const float dr = xh[t].x - xt.x, di = xh[t].y - xt.y;
+            sq += (double)dr * dr + (double)di * di;
+            if (m == 0) {   // one lane per section books the label counters
+                const long long ih = (g.frame_base + f) * (long long)N_ + sec * M_ + dec_ant[t];
+                const long long itrue = io.idx_true[f * L_ + sec];
+                const long long sh = al.gray[k], st = io.sym_true[f * L_ + sec];
+                const unsigned long long imask = g.index_bits_kept >= 64 ? ~0ull : ((1ull << g.index_bits_kept) - 1ull);
+                c_idx += (ih != itrue);
+                c_sym += (sh != st);
+                c_ibit += __popcll((unsigned long long)(ih ^ itrue) & imask);
+                c_sbit += __popcll((unsigned long long)(sh ^ st) & ((1ull << al.sbits) - 1ull));
+            }
+        }
+    }
+    unsigned long long packed = c_idx | (c_sym << 12) | (c_ibit << 24) | (c_sbit << 44);   // <= 64 sections, 64 bits each
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+    sq = warp_sum(sq);
+    const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
+    if (lane == 0) {
+        cnt[C_INDEX_ERR] += packed & 0xfffull;
+        cnt[C_SYMBOL_ERR] += (packed >> 12) & 0xfffull;
+        cnt[C_INDEX_BIT] += (packed >> 24) & 0xfffffull;
+        cnt[C_SYMBOL_BIT] += packed >> 44;
+        cnt[C_FRAME_ERR] += any_wrong;                       // Lin = 1: one time slot per frame
+        cnt[C_NAN_FRAMES] += any_nan;
+        reinterpret_cast<double*>(cnt)[12] += sq;
+    }
+}
+// flush a warp's shared counter block into the global one (Lin = 1: the frame is its only, first, middle and last slot)
+__device__ __forceinline__ void fast_flush_counters(const unsigned long long* cnt, unsigned long long* out) {
+    const int plain[] = {C_FRAMES, C_INDEX_ERR, C_SYMBOL_ERR, C_INDEX_BIT, C_SYMBOL_BIT, C_ITERS, C_NAN_FRAMES};
+    for (int k : plain)
+        if (cnt[k]) atomicAdd(out + k, cnt[k]);
+    if (cnt[C_FRAME_ERR]) {
+        const int slots[] = {C_FRAME_ERR, C_SLOT_ERR, C_SLOT_FIRST, C_SLOT_MID, C_SLOT_LAST};
+        for (int k : slots) atomicAdd(out + k, cnt[C_FRAME_ERR]);
+    }
+    const double sq = reinterpret_cast<const double*>(cnt)[12];
+    if (sq != 0.0)
+        for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
+}
+
 }  // namespace ampsm

@@ -39,6 +39,7 @@ struct BampArgs {
 struct VampArgs {
     Geom g;
     DevAlphabet al;
+    DevGrid grid;
     const void* U;               // [n][R] complex64 / complex128
     long long U_stride;
     const void* s;               // [R] float / double
@@ -91,6 +92,7 @@ int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
 int launch_bamp_pair(const BampArgs& a, cudaStream_t stream);       // two warps per frame (64 x 32 shapes), else AMPSM_ENOFIT
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
+int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64 32 x 64 factors, else AMPSM_ENOFIT
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
 int launch_loss(const LossArgs& a, cudaStream_t stream);

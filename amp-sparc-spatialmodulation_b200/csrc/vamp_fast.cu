@@ -1,0 +1,410 @@
+// Register-resident VAMP kernel: ONE WARP PER FRAME, Vh lives in registers for all iterations (complex64 path).
+//
+// VAMP in the caller's SVD basis (vamp.py:66-94) touches the frame's matrix twice per iteration -- q = Vh r~ and
+// x~ = V(..) -- which are the same two complex mat-vecs as BAMP's H xhat and H^H g, without the |H|^2 products.  So:
+//   * lanes form a 4 x 8 grid; lane (a,b) keeps an RT x CTL tile of Vh as the natural (re,im) register pairs (R = 4 RT
+//     singular values, N = 8 CTL columns: 128 registers for 32 x 64) and runs both passes with packed FFMA2 exactly
+//     as bamp_fast.cu does (operand pairs {x,x},{y,y} for the plain product, {dx,dy},{dy,-dx} for the adjoint one);
+//   * no staging buffer -- the lanes load their tiles straight from global memory as full 128-byte lines, issued right
+//     after the last iteration so that they fly under the Loss epilogue of the previous frame; the next frame's
+//     Vh / U / y / x_true are L2-prefetched (cp.async.bulk.prefetch.L2) one frame ahead.  Two warps per SM
+//     sub-partition (8 frames per SM, 220-255 registers); a three-warp build (168 registers, 12 frames per SM) is kept
+//     for A/B runs -- it measured ~20 % slower because it spills;
+//   * partial sums cross lanes as float2 planes in shared memory (conflict-free stores and loads, half the wavefronts
+//     of the float4 exchange of the BAMP kernel);
+//   * y~ = diag(s) U^H y (vamp.py:22) is formed once per frame, lane k owning singular value k, with U read
+//     column-wise (coalesced over k) from L2;
+//   * the scalar bookkeeping (alpha, sigma^2, dxdr, sigma~^2 with the reference's clips, vamp.py:73-94) is evaluated
+//     redundantly by every lane from two warp sums; scalar divisions are IEEE (they are not on the hot path);
+//   * the un-halved scalar-variance section denoiser (vamp.py:96-119), the allclose exit on var (vamp.py:185) and Loss
+//     on (r, xmmse) (vamp.py:187) are shared with the BAMP kernels (fastops.cuh).
+// launch_vamp_fast() returns AMPSM_ENOFIT for anything else (complex128, other shapes): the generic kernel takes it.
+#include <cstdlib>
+
+#include "fastops.cuh"
+
+namespace ampsm {
+
+namespace {
+
+
+template <int RT, int CTL, int M_, int K_, bool GRID>
+struct VFastShape {
+    static constexpr int R = 4 * RT, N = 8 * CTL, NV = CTL / 2, CP = N / 32;
+    static_assert(CTL % 2 == 0 && N % 32 == 0 && R == 32, "one singular value per lane, whole columns per lane");
+    static constexpr int kMaxRows = 64;                                   // n of U / y
+    static constexpr int rowp = 0;                                        // float2 [8][R + 1]   row-pass partials
+    static constexpr int colp = rowp + ((8 * (R + 1) * 8 + 15) & ~15);    // float2 [4][N + 1]   column-pass partials
+    static constexpr int ebuf = colp + ((4 * (N + 1) * 8 + 15) & ~15);    // float  [CP * K_][32] (table-driven denoiser)
+    static constexpr int colvec = ebuf + (GRID ? 0 : 32 * CP * K_ * 4);   // float4 [N] {x,x,y,y} of r~
+    static constexpr int varvec = colvec + N * 16;                        // float  [N]
+    static constexpr int rowvec = varvec + N * 4;                         // float4 [R + R/8] {dx,dy,dy,-dx}
+    static constexpr int rowstate = rowvec + (R + R / 8) * 16;            // float4 [R] {y~.re, y~.im, s^2, -}
+    static constexpr int ystage = rowstate + R * 16;                      // float2 [kMaxRows]
+    static constexpr int xmapvec = ystage + kMaxRows * 8;                 // float2 [N]  r (the Loss input)
+    static constexpr int cnt = xmapvec + N * 8;                           // u64 [16]
+    static constexpr int total = cnt + 128;
+};
+
+__device__ __forceinline__ float clampF(float v, float lo, float hi) {
+    // torch.max / torch.min propagate NaN (vamp.py:76-77)
+    if (v != v) return v;
+    return fminf(fmaxf(v, lo), hi);
+}
+
+// WPS = warps (frames) per SM: 12 = three per sub-partition at 168 registers, 8 = two at 255 registers (A/B switch)
+template <int RT, int CTL, int M_, int K_, bool GRID, int WPS>
+__global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constant__ VampArgs a) {
+    using S = VFastShape<RT, CTL, M_, K_, GRID>;
+    constexpr int R = S::R, N = S::N, NV = S::NV, CP = S::CP, L_ = N / M_;
+    static_assert(N % M_ == 0, "section size must divide N");
+    static_assert(M_ >= 32 ? (M_ % 32 == 0) : (32 % M_ == 0), "sections must tile the warp");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int la = lane >> 3, lb = lane & 7;
+    float2* rowp = reinterpret_cast<float2*>(smem + S::rowp);
+    float2* colp = reinterpret_cast<float2*>(smem + S::colp);
+    float* ebuf = reinterpret_cast<float*>(smem + S::ebuf);
+    float4* colvec = reinterpret_cast<float4*>(smem + S::colvec);
+    float* varvec = reinterpret_cast<float*>(smem + S::varvec);
+    float4* rowvec = reinterpret_cast<float4*>(smem + S::rowvec);
+    float4* rowstate = reinterpret_cast<float4*>(smem + S::rowstate);
+    float2* ystage = reinterpret_cast<float2*>(smem + S::ystage);
+    float2* xmapvec = reinterpret_cast<float2*>(smem + S::xmapvec);
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(smem + S::cnt);
+
+    const Geom& g = a.g;
+    const DevAlphabet& al = a.al;
+    const int n = g.n;
+    const float2* Vall = reinterpret_cast<const float2*>(a.Vh);
+    const float2* Uall = reinterpret_cast<const float2*>(a.U);
+    const float* sall = reinterpret_cast<const float*>(a.s);
+    const float2* yall = reinterpret_cast<const float2*>(a.y);
+    const float ratio_min = 1.0e-5f, ratio_max = 1.0f - 1.0e-5f;          // float32 tensors (vamp.py:51-52)
+    const float var_min = 1.0e-9f, var_max = 1.0e5f;                      // vamp.py:53-54
+    const double eta_d = (double)R / (double)N;                           // vamp.py:28
+    const float eta = (float)eta_d, one_m_eta = (float)(1.0 - eta_d);
+    const double sp = a.sparsity;
+    const double s2t0_d = sp * sp * (1.0 - sp) + (1.0 - sp) * (1.0 - sp) * sp;   // python float (vamp.py:26)
+
+    if (lane < 16) cnt[lane] = 0ull;
+    __syncwarp();
+
+    // column-vector exchange: per column one float4 {x,x,y,y} (the broadcast operand pairs of the row pass), placed so
+    // that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without conflicts
+    auto colslot = [&](int col) {
+        const int t = col >> 4, b = (col >> 1) & 7, e = col & 1;
+        return (t * 2 + e) * 8 + (b ^ (e << 2));
+    };
+
+    pair_t Hp[RT][CTL];
+    // global memory -> registers: per (i, t) the warp reads 4 rows x one full 128-byte line
+    auto load_tile = [&](long long ff) {
+        const float2* Vf = Vall + ff * a.Vh_stride;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(Vf + (size_t)(la * RT + i) * N + (t * 8 + lb) * 2));
+                Hp[i][2 * t] = v.x;
+                Hp[i][2 * t + 1] = v.y;
+            }
+        }
+    };
+    auto l2_prefetch = [&](long long ff) {    // one frame ahead, so that the tile loads and the y~ loop hit in L2
+        if (lane == 0) {
+            if (a.Vh_stride) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Vall + ff * a.Vh_stride), "r"(R * N * 8) : "memory");
+            if (a.U_stride) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Uall + ff * a.U_stride), "r"(n * R * 8) : "memory");
+        } else if (lane == 1) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(yall + ff * n));
+            if (n > 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(yall + ff * n + 16));
+            if (a.s_stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(sall + ff * a.s_stride));
+        } else if (a.io.x_true) {
+            if (lane >= 2 && (lane - 2) * 16 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.x_true + ff * N + (lane - 2) * 16));
+            if (lane == 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.idx_true + ff * L_));
+            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.sym_true + ff * L_));
+        }
+    };
+    long long f = blockIdx.x;
+    if (f < a.frames) load_tile(f);
+
+    for (; f < a.frames; f += gridDim.x) {
+        {
+            const long long nf = f + gridDim.x;
+            if (nf < a.frames) l2_prefetch(nf);
+        }
+        // ---- y~ = (s U^H) y (vamp.py:22): lane k owns singular value k; U column-wise, coalesced over k
+        for (int i = lane; i < n; i += 32) ystage[i] = __ldg(yall + f * n + i);
+        __syncwarp();
+        {
+            const float2* Uf = Uall + f * a.U_stride;
+            const float sk = __ldg(sall + f * a.s_stride + lane);
+            float ar = 0.f, ai = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) {
+                const float2 u = __ldg(Uf + (size_t)i * R + lane);
+                const float2 yv = ystage[i];
+                const float wr = sk * u.x, wi = -(sk * u.y);            // s * conj(U)
+                ar += wr * yv.x - wi * yv.y;
+                ai += wr * yv.y + wi * yv.x;
+            }
+            rowstate[lane] = make_float4(ar, ai, sk * sk, 0.f);         // vamp.py:17
+        }
+        const double noise_var_d = a.sigma2_pf ? (double)a.sigma2_pf[f] : a.sigma2_d;
+        const float nv = (float)noise_var_d;
+        float s2t = (float)s2t0_d;
+        // state (vamp.py:23-26): r~ = sparsity, var = 1; the column owner (column = lane + 32 t) publishes them
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const int col = lane + 32 * t;
+            colvec[colslot(col)] = make_float4((float)sp, (float)sp, 0.f, 0.f);
+            varvec[col] = 1.0f;
+            xmapvec[col] = make_float2(0.f, 0.f);
+        }
+        float2 xh[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) xh[t] = make_float2(0.f, 0.f);
+        __syncwarp();
+
+        int t_done = 0;
+        for (int it = 0; it < g.max_iters; ++it) {
+            // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66)
+            const float ratio = (it == 0) ? (float)(noise_var_d / s2t0_d) : nv / s2t;
+            // ================= row pass: q = Vh r~ (vamp.py:67) =================
+            {
+                constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
+#pragma unroll
+                for (int i0 = 0; i0 < RT; i0 += RH) {
+                    pair_t A[RH], B[RH];
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const int col = (t * 8 + lb) * 2;
+                        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {x,x | y,y}
+                        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
+                        if (t == 0) {
+#pragma unroll
+                            for (int i = 0; i < RH; ++i) A[i] = fmul2(Hp[i0 + i][0], x0.x);
+#pragma unroll
+                            for (int i = 0; i < RH; ++i) B[i] = fmul2(Hp[i0 + i][0], x0.y);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
+#pragma unroll
+                            for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        float al_, ah_, bl_, bh_;
+                        unpack2(A[i], al_, ah_);
+                        unpack2(B[i], bl_, bh_);
+                        rowp[lb * (R + 1) + la * RT + i0 + i] = make_float2(al_ - bh_, bl_ + ah_);
+                    }
+                }
+            }
+            __syncwarp();
+            // ================= LMMSE in the SVD basis: d = scale (y~ + ratio q) - q (vamp.py:68-72) =================
+            float scale;
+            {
+                float2 p[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) p[b] = rowp[b * (R + 1) + lane];
+                const float qx = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
+                const float qy = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
+                const float4 rs = rowstate[lane];
+                scale = __frcp_rn(rs.z + ratio);
+                const float dx = scale * (rs.x + ratio * qx) - qx, dy = scale * (rs.y + ratio * qy) - qy;
+                rowvec[lane + (lane >> 3)] = make_float4(dx, dy, dy, -dx);      // operand pairs (dx,dy), (dy,-dx)
+            }
+            __syncwarp();
+            // ================= column pass: V d (vamp.py:72) =================
+            {
+                constexpr int CH = CTL > 4 ? CTL / 2 : CTL;
+#pragma unroll
+                for (int c0 = 0; c0 < CTL; c0 += CH) {
+                    pair_t A[CH], B[CH];
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) {
+                        const int row = la * RT + i;
+                        const ulonglong2 gq = *reinterpret_cast<const ulonglong2*>(&rowvec[row + (row >> 3)]);   // {dx,dy | dy,-dx}
+                        if (i == 0) {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) A[c] = fmul2(Hp[0][c0 + c], gq.x);
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) B[c] = fmul2(Hp[0][c0 + c], gq.y);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) A[c] = ffma2(Hp[i][c0 + c], gq.x, A[c]);
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) B[c] = ffma2(Hp[i][c0 + c], gq.y, B[c]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int col = (((c0 + c) >> 1) * 8 + lb) * 2 + (c & 1);
+                        float lo, hi, lo2, hi2;
+                        unpack2(A[c], lo, hi);
+                        unpack2(B[c], lo2, hi2);
+                        colp[la * (N + 1) + col] = make_float2(lo + hi, lo2 + hi2);
+                    }
+                }
+            }
+            // scalars (vamp.py:71-82), the same in every lane
+            const float scale_tot = warp_sum(scale);
+            const float var_lmmse = (scale_tot / (float)R) * nv;               // scale.mean() * noise_var
+            const float xt_var = eta * var_lmmse + one_m_eta * s2t;
+            const float alpha = clampF(xt_var / s2t, ratio_min, ratio_max);
+            const float inv_1ma = __frcp_rn(1.0f - alpha);
+            const float sig2 = clampF(alpha / (1.0f - alpha) * s2t, var_min, var_max);
+            const float rsig = __frcp_rn(sig2);
+            __syncwarp();
+            // ================= r = (x~ - alpha r~)/(1 - alpha), denoiser with the scalar variance (vamp.py:79-84) ==========
+            float2 r[CP];
+            float q_r[CP], q_i[CP], var_old[CP];
+#pragma unroll
+            for (int t = 0; t < CP; ++t) {
+                const int col = lane + 32 * t;
+                float2 p[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) p[q] = colp[q * (N + 1) + col];
+                const float sx = (p[0].x + p[1].x) + (p[2].x + p[3].x);
+                const float sy = (p[0].y + p[1].y) + (p[2].y + p[3].y);
+                const float4 cv = colvec[colslot(col)];                        // r~ of this column
+                const float xtx = sx + cv.x, xty = sy + cv.z;
+                r[t] = make_float2((xtx - alpha * cv.x) * inv_1ma, (xty - alpha * cv.z) * inv_1ma);
+                xmapvec[col] = r[t];
+                q_r[t] = __fmul_rn(r[t].x, rsig);                              // s / tau in complex64 (vamp.py:111)
+                q_i[t] = __fmul_rn(r[t].y, rsig);
+                var_old[t] = varvec[col];
+            }
+            __syncwarp();     // everyone has read r~ and the partials
+            float xr_[CP], xi_[CP], vn_[CP];
+            fast_denoise<N, M_, K_, GRID, CP>(q_r, q_i, al, a.grid, ebuf, lane, xr_, xi_, vn_);
+            // ================= Onsager bookkeeping (vamp.py:85-94), exit test on var (vamp.py:185) =================
+            float vs = 0.f;
+            bool close = true;
+#pragma unroll
+            for (int t = 0; t < CP; ++t) {
+                vs += vn_[t];
+                close &= fabsf(vn_[t] - var_old[t]) <= __fadd_rn(kAtol, fabsf(__fmul_rn(kRtol, var_old[t])));
+            }
+            const float vtot = warp_sum(vs);
+            const float vmean = vtot / (float)N;
+            const float dxdr = clampF(vmean / sig2, ratio_min, ratio_max);
+            const float norm = __frcp_rn(1.0f - dxdr);
+            float s_mse = 0.f;
+#pragma unroll
+            for (int t = 0; t < CP; ++t) {
+                const int col = lane + 32 * t;
+                xh[t] = make_float2(xr_[t], xi_[t]);
+                const float rx = (xr_[t] - dxdr * r[t].x) * norm, ry = (xi_[t] - dxdr * r[t].y) * norm;
+                colvec[colslot(col)] = make_float4(rx, rx, ry, ry);
+                varvec[col] = vn_[t];
+                if (a.traj && a.io.x_true) {
+                    const float2 xt = a.io.x_true[f * N + col];
+                    s_mse += (xr_[t] - xt.x) * (xr_[t] - xt.x) + (xi_[t] - xt.y) * (xi_[t] - xt.y);
+                }
+            }
+            s2t = clampF(sig2 * dxdr * norm, var_min, var_max);
+            const bool all_close = __all_sync(0xffffffffu, close);
+            __syncwarp();     // r~ is published: the next row pass may start
+            if (a.traj) {
+                s_mse = warp_sum(s_mse);
+                if (lane == 0) {
+                    float* tr = a.traj + (f * g.max_iters + it) * 3;
+                    tr[0] = s2t;
+                    tr[1] = vmean;
+                    tr[2] = s_mse / N;
+                }
+            }
+            t_done = it + 1;
+            if (g.early_exit && all_close) break;
+        }
+        {   // the tile registers are free: fetch the next frame's tile under the Loss epilogue
+            const long long nf = f + gridDim.x;
+            if (nf < a.frames) load_tile(nf);
+        }
+        // ================= outputs =================
+        float2 xmap[CP];
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const int col = lane + 32 * t;
+            xmap[t] = xmapvec[col];
+            if (a.xmap) reinterpret_cast<float2*>(a.xmap)[f * N + col] = xmap[t];
+            if (a.xmmse) a.xmmse[f * N + col] = xh[t];
+            if (a.var) a.var[f * N + col] = varvec[col];
+        }
+        if (a.traj) {
+            __syncwarp();
+            for (int it = t_done + lane; it < g.max_iters; it += 32)
+                for (int q = 0; q < 3; ++q)
+                    a.traj[(f * g.max_iters + it) * 3 + q] = a.traj[(f * g.max_iters + t_done - 1) * 3 + q];
+        }
+        if (lane == 0) {
+            if (a.iters) a.iters[f] = t_done;
+            cnt[C_FRAMES] += 1;
+            cnt[C_ITERS] += t_done;
+        }
+        if (a.io.x_true) fast_loss<N, M_, K_, CP>(xmap, xh, al, g, a.io, f, lane, cnt);   // Loss is fed T.r as xmap (vamp.py:187)
+        __syncwarp();
+    }
+    __syncwarp();
+    if (a.io.counters && lane == 0) fast_flush_counters(cnt, a.io.counters);
+}
+
+template <int RT, int CTL, int M_, int K_, bool GRID, int WPS>
+int launch_vshape_w(const VampArgs& a, cudaStream_t stream) {
+    using S = VFastShape<RT, CTL, M_, K_, GRID>;
+    int dev = 0, sms = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = vamp_fast_kernel<RT, CTL, M_, K_, GRID, WPS>;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total),
+                           "cudaFuncSetAttribute(vamp_fast)"))
+        return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, S::total);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.frames) grid = a.frames;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 32, S::total, stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "vamp_fast_kernel launch");
+}
+
+template <int RT, int CTL, int M_, int K_, bool GRID>
+int launch_vshape(const VampArgs& a, cudaStream_t stream) {
+    // measured on B200 (1M-frame pools): 8 frames per SM at 220-255 registers beat 12 frames per SM at 168 registers by
+    // ~20 % (the 168-register build spills ~30 values per iteration); the 12-warp build stays selectable for A/B runs
+    static const bool three = getenv("AMPSM_VAMP_WPS12") != nullptr;
+    return three ? launch_vshape_w<RT, CTL, M_, K_, GRID, 12>(a, stream) : launch_vshape_w<RT, CTL, M_, K_, GRID, 8>(a, stream);
+}
+
+}  // namespace
+
+int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
+    const Geom& g = a.g;
+    // complex64, one time slot per frame, MAP decision, per-section shift; 16-byte aligned rows for the tile loads
+    if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0 || g.R != 32 || g.N != 64 || g.n > 64 || g.n < 1) return AMPSM_ENOFIT;
+    if ((reinterpret_cast<uintptr_t>(a.Vh) % 16) || (a.Vh_stride != 0 && ((size_t)a.Vh_stride * 8) % 16) ||
+        (reinterpret_cast<uintptr_t>(a.U) % 8) || (reinterpret_cast<uintptr_t>(a.y) % 8))
+        return AMPSM_ENOFIT;
+    const int K = a.al.K;
+    VampArgs b = a;
+    b.grid = make_grid(a.al);
+    if (g.M == 64 && K == 16 && b.grid.ok && !getenv("AMPSM_NO_GRID")) return launch_vshape<8, 8, 64, 16, true>(b, stream);
+#define AMPSM_VSHAPE(MM, KK) \
+    if (g.M == MM && K == KK) return launch_vshape<8, 8, MM, KK, false>(b, stream);
+    AMPSM_VSHAPE(64, 16)    // 64 x 32, 16-QAM, table-driven denoiser
+    AMPSM_VSHAPE(64, 4)     // 64 x 32, QPSK
+    AMPSM_VSHAPE(16, 4)     // 64 x 32, QPSK, Na = 4
+#undef AMPSM_VSHAPE
+    return AMPSM_ENOFIT;
+}
+
+}  // namespace ampsm

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--e2e-frames", type=int, default=1 << 17)
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast", "pair"])
+    ap.add_argument("--vamp-frames", type=int, default=1 << 18, help="frames per GPU of the VAMP leg (0 = skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed-t", action="store_true")
     return ap.parse_args()
@@ -376,6 +377,69 @@ def main():
     out["e2e"] = {"value": float(e2e_iters[0] / e2e_iters[1]), "unit": "frame-iter/s", "h2d_bytes_per_step": int(h2d),
                   "d2h_bytes_per_step": _cabi.NUM_COUNTERS * 8, "frames_per_step": fe,
                   "api": "ampsm_bamp_detect_host (C-ABI, pinned host buffers, chunked copies overlapped with the kernel)"}
+    # ---- VAMP leg: the same 64 x 32 16-QAM frames through VAMP (vamp.py:159-191) with per-frame SVD factors resident
+    # in HBM (the reference's caller computes them once per channel draw, vamp_model.py:58)
+    if args.vamp_frames > 0:
+        fv = min(args.vamp_frames, frames)
+        del hH, hy, hx, hl, hi
+        Us, ss, Vs = [], [], []
+        for H1 in H[:fv].split(16384):                      # thin SVD through the Hermitian eigenproblem of H H^H (float64)
+            Hd = H1.to(torch.complex128)
+            w, V = torch.linalg.eigh(Hd @ Hd.mH)
+            w, V = w.flip(-1), V.flip(-1)
+            sv = w.clamp_min(0).sqrt()
+            Us.append(V.to(torch.complex64)), ss.append(sv.to(torch.float32))
+            Vs.append(((V.mH @ Hd) / sv.unsqueeze(-1)).to(torch.complex64))
+            del Hd, w, V, sv
+        U, sv, Vh = torch.cat(Us).contiguous(), torch.cat(ss).contiguous(), torch.cat(Vs).contiguous()
+        del Us, ss, Vs
+        yv, xv, lv, iv = y[:fv].contiguous(), x[:fv].contiguous(), labels[:fv].contiguous(), idx[:fv].contiguous()
+        cfgv = pkg.Config(NT, NA, NR, LIN, LH, batch=fv, generator_mode='sparc', iterations=ITERS, alphabet=ALPHABET,
+                          channel_profile='uniform', device=str(dev))
+        vout = {}
+        for tag, ee in (("exit", True), ("fixed_T", False)):
+            vamp = pkg.VAMP(cfgv, kernel=args.kernel if args.kernel in ("auto", "generic", "fast") else "auto", outputs=False,
+                            early_exit=ee)
+            for _ in range(max(1, args.warmup)):
+                vamp.detect(U, sv, Vh, yv, snr, xv, lv, iv)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+            e0.record()
+            for _ in range(args.steps):
+                det = vamp.detect(U, sv, Vh, yv, snr, xv, lv, iv)
+                tot += allreduce_counters(det.counters) if world > 1 else det.counters
+            e1.record()
+            torch.cuda.synchronize()
+            msv = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([msv], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                msv = float(tt.item())
+            cv = _cabi.counters_to_dict(tot.cpu().numpy())
+            vout[tag] = (cv, msv)
+        cv, msv = vout["exit"]
+        cf, msf = vout["fixed_T"]
+        vbytes = 8 * NR * NT + 8 * NR * NR + 4 * NR + 8 * NR + 8 * NT            # Vh, U, s, y, x_true: 25 472 B
+        vflop = 16 * NR * NT + 18 * NT * 16 + 40 * NT + 10 * NR                  # 54 080 flop per frame-iteration
+        gbs = (cv["frames"] / world) * vbytes / (msv * 1e-3) / 1e9
+        tfl = (cf["iters"] / world) * vflop / (msf * 1e-3) / 1e12
+        tf32 = out.get("fixed_T", {}).get("roofline_fp32", {}).get("peak") or 0.0
+        out["vamp"] = {
+            "metric": "VAMP frame-iterations/s", "value": cv["iters"] / (msv * 1e-3), "unit": "frame-iter/s",
+            "frames_per_gpu_per_step": fv, "frames_per_s": cv["frames"] / (msv * 1e-3),
+            "mean_iterations_per_frame": cv["iters"] / max(cv["frames"], 1), "ier": cv["index_err"] / max(cv["frames"], 1),
+            "nan_frames": cv["nan_frames"],
+            "config": {"workload": f"VAMP Nt={NT} Nr={NR} Na={NA} 16-QAM SM, per-frame thin SVD factors (U, s, Vh) resident in HBM, "
+                                   f"iterations={ITERS}, early exit as reference, SNR {args.snr_db} dB"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_frame": vbytes, "traffic": None},
+            "fixed_T": {"value": cf["iters"] / (msf * 1e-3), "unit": "frame-iter/s", "iterations": ITERS,
+                        "roofline_fp32": {"bound": "fp32", "achieved": tfl, "peak": tf32, "unit": "TFLOP/s",
+                                          "frac": (tfl / tf32) if tf32 else None, "algorithmic_flop_per_frame_iter": vflop}},
+        }
     if cpu_base:
         out["cpu_baseline"] = cpu_base
     if rank == 0:

@@ -1,6 +1,6 @@
 """Generate the golden fixtures in this directory by running the REFERENCE itself (build container only).
 
-    python tests/golden/make_golden.py            # needs /root/reference (read-only) and CPU torch/numpy
+    python tests/golden/make_golden.py [name ...]   # needs /root/reference (read-only) and CPU torch/numpy
 
 The reference ships no tests, seeds or golden vectors, so the pins are manufactured here:
 fixed-seed inputs drawn by the reference's own ``Channel`` / ``Data`` (numpy + torch global RNGs), detectors run
@@ -214,20 +214,40 @@ def save(name, out, batch_loss_vec, gidx, meta):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])          # optional: fixture names to (re)generate; default all
+
+    def want(name):
+        return not only or name in only
+
     # C1: BAMP 8x4 QPSK, one active antenna (L=1)
-    run_bamp('bamp_c1', (8, 1, 4, 1, 1, 'QPSK'), {}, [0, 10, 20], 48, seed=0)
+    if want('bamp_c1'):
+        run_bamp('bamp_c1', (8, 1, 4, 1, 1, 'QPSK'), {}, [0, 10, 20], 48, seed=0)
     # C2: BAMP 64x32 16-QAM (L=1) -- the headline config
-    run_bamp('bamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 12, seed=0)
+    if want('bamp_c2'):
+        run_bamp('bamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 12, seed=0)
     # multi-section ISI frame, matrix drawn as in bamp_model.py:56 (generate_as_sparc)
-    run_bamp('bamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [2, 8], 12, seed=1, matrix='sparc')
+    if want('bamp_isi'):
+        run_bamp('bamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [2, 8], 12, seed=1, matrix='sparc')
     # 'segmented' decision rule (B=1 only in the reference)
-    run_bamp('bamp_seg', (16, 2, 8, 3, 2, '8PSK'), dict(trunc='tail', mode='segmented'), [4, 10], 8, seed=2, matrix='sparc')
+    if want('bamp_seg'):
+        run_bamp('bamp_seg', (16, 2, 8, 3, 2, '8PSK'), dict(trunc='tail', mode='segmented'), [4, 10], 8, seed=2, matrix='sparc')
     # C3: VAMP 128x64, Na=4, QPSK; complex64 and the complex128-input variant
-    run_vamp('vamp_c3', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 3, seed=3)
-    run_vamp('vamp_c3_c128', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 2, seed=3, double=True)
-    run_vamp('vamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [4, 10], 8, seed=4)
+    if want('vamp_c3'):
+        run_vamp('vamp_c3', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 3, seed=3)
+    if want('vamp_c3_c128'):
+        run_vamp('vamp_c3_c128', (128, 4, 64, 1, 1, 'QPSK'), {}, [0, 4], 2, seed=3, double=True)
+    if want('vamp_isi'):
+        run_vamp('vamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [4, 10], 8, seed=4)
+    # VAMP at the headline 64x32 shapes (the register-resident kernel): 16-QAM one active antenna; QPSK, 4 sections of 16
+    if want('vamp_c2'):
+        run_vamp('vamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 4, seed=8)
+    if want('vamp_c2_na4'):
+        run_vamp('vamp_c2_na4', (64, 4, 32, 1, 1, 'QPSK'), {}, [2, 8], 4, seed=9)
     # SCAMP: small coupled instance, design matrix shared by groups of 4 frames (res=4)
-    run_scamp('scamp_small', (32, 2, 8, 8, 3, 'QPSK'), dict(trunc='tail'), [4, 8], 8, seed=5, res=4)
+    if want('scamp_small'):
+        run_scamp('scamp_small', (32, 2, 8, 8, 3, 'QPSK'), dict(trunc='tail'), [4, 8], 8, seed=5, res=4)
     # Loss alone at B>1
-    run_loss_only('loss_qpsk', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), 24, seed=6)
-    run_loss_only('loss_16qam', (64, 1, 32, 1, 1, '16QAM'), {}, 64, seed=7)
+    if want('loss_qpsk'):
+        run_loss_only('loss_qpsk', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), 24, seed=6)
+    if want('loss_16qam'):
+        run_loss_only('loss_16qam', (64, 1, 32, 1, 1, '16QAM'), {}, 64, seed=7)

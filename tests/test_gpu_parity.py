@@ -93,9 +93,17 @@ def test_bamp_loss_dict_matches_reference_batch_loss():
     assert L.loss['T'] == pytest.approx(g["iters"][sel].mean(), abs=0.1)
 
 
-@pytest.mark.parametrize("name,double", [("vamp_c3", False), ("vamp_isi", False), ("vamp_c3_c128", True)])
-@pytest.mark.parametrize("exp", ["f64", "f32"])
+@pytest.mark.parametrize("name,double", [("vamp_c3", False), ("vamp_isi", False), ("vamp_c2", False), ("vamp_c2_na4", False),
+                                         ("vamp_c3_c128", True)])
+@pytest.mark.parametrize("exp", ["f64", "f32", "f32-generic"])
 def test_vamp_matches_reference_goldens(name, double, exp):
+    """exp = 'f32' lets the library choose: the register-resident kernel for the 64 x 32 fixtures (vamp_c2*), the
+    generic one elsewhere; 'f32-generic' pins the generic kernel on the same fixtures."""
+    kernel = "auto"
+    if exp == "f32-generic":
+        if not name.startswith("vamp_c2"):
+            pytest.skip("'f32' already runs the generic kernel for this shape")
+        exp, kernel = "f32", "generic"
     if double and exp == "f32":
         pytest.skip("complex128 path always uses float64 exponents")
     g = load_golden(name)
@@ -108,7 +116,7 @@ def test_vamp_matches_reference_goldens(name, double, exp):
     iters = np.zeros(F, np.int32)
     for f in range(F):          # per-frame factors with their own sigma2: one call per frame
         cfg = config_from_meta(g["meta"], batch=1, device=DEV)
-        amp = pkg.VAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section")
+        amp = pkg.VAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section", kernel=kernel)
         snr = (cfg.Na / cfg.Nr) / float(g["sigma2"][f])
         amp(t(g["U"][f]).to(ct), t(g["s"][f]).to(torch.float64 if double else torch.float32), t(g["Vh"][f]).to(ct),
             t(g["y"][f]).to(ct).reshape(1, -1, 1), snr, t(g["x"][f]).reshape(1, -1, 1), g["sym"][f], g["idx"][f])
@@ -121,7 +129,8 @@ def test_vamp_matches_reference_goldens(name, double, exp):
         want = counters_for(cfg, g["xmap"][f:f + 1], g["xmmse"][f:f + 1], g["x"][f:f + 1], g["sym"][f], g["idx"][f])
         assert_counts_equal(f"{name}[{f}]", d.counters_dict(), want)
     tight = 5e-7 if double else 1e-4     # see tests/test_oracle_golden.py for why not 1e-10
-    for it in range(2):
+    # (vamp_c2: sigma2_tilde is tail mass from iteration 2 on -- see tests/test_oracle_golden.py)
+    for it in range(1 if name == "vamp_c2" else 2):
         assert np.abs(s2t[:, it] - g["sigma2t"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["sigma2t"][:, it]).max()
         assert np.abs(varm[:, it] - g["varm"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["varm"][:, it]).max()
     if double:
@@ -136,7 +145,10 @@ def test_vamp_matches_reference_goldens(name, double, exp):
         d_oracle = np.abs(r["traj"]["sigma2"].T - g["sigma2t"]) / g["sigma2t"]
         d_kernel = np.abs(s2t - g["sigma2t"]) / g["sigma2t"]
         assert np.median(d_kernel) <= max(5e-2, 3 * np.median(d_oracle))
-        assert np.abs(xmmse - g["xmmse"]).max() < 2e-3
+        conv = g["iters"] < cfg.N_Layers                      # frames the reference itself brought to the exit test
+        assert (iters[g["iters"] <= 4] == g["iters"][g["iters"] <= 4]).all()
+        per_frame = np.abs(xmmse - g["xmmse"]).max(axis=1)
+        assert per_frame[conv].max(initial=0.0) < 2e-3 and per_frame.max() < 5e-2
     cfg = config_from_meta(g["meta"])
     assert decision_mismatch_frames(cfg, xmap, g["xmap"]).size == 0
 

@@ -116,7 +116,8 @@ def test_multi_section_fast_shape_matches_generic(fast, Na):
     a = pkg.BAMP(cfg, kernel=fast).detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
     b = pkg.BAMP(cfg, kernel='generic', exp='f64').detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
     diff = {k: (a[k], b[k]) for k in INT_KEYS if a[k] != b[k]}
-    assert all(abs(u - v) <= 2 for u, v in diff.values()), diff
+    # at most two frames may decide differently (near-ties in float32); a frame carries up to 4 sections of bit errors
+    assert all(abs(u - v) <= (8 if k.endswith("bit_err") else 2) for k, (u, v) in diff.items()), diff
 
 
 def test_shared_matrix_and_edge_frame_counts():
@@ -233,3 +234,51 @@ def test_scamp_zero_tile_skipping_is_exact():
     assert torch.allclose(band.xmmse, full.xmmse, atol=1e-6) and torch.equal(band.iters, full.iters)
     cb, cf = band.counters_dict(), full.counters_dict()
     assert all(cb[k] == cf[k] for k in INT_KEYS + ["iters", "nan_frames"])
+
+
+def svd_factors(H):
+    """Thin SVD factors of a batch of wide matrices through the Hermitian eigenproblem of H H^H (float64), as the
+    batched in-kernel Jacobi route does: H = U diag(s) Vh with s descending."""
+    Us, ss, Vs = [], [], []
+    for H1 in H.split(16384):                                # cuSOLVER's batched eigh rejects very large batches
+        Hd = H1.to(torch.complex128)
+        w, V = torch.linalg.eigh(Hd @ Hd.mH)                # ascending
+        w, V = w.flip(-1), V.flip(-1)
+        s = w.clamp_min(0).sqrt()
+        Vh = (V.mH @ Hd) / s.unsqueeze(-1)
+        Us.append(V.to(torch.complex64)), ss.append(s.to(torch.float32)), Vs.append(Vh.to(torch.complex64))
+    return torch.cat(Us).contiguous(), torch.cat(ss).contiguous(), torch.cat(Vs).contiguous()
+
+
+@pytest.mark.parametrize("alphabet,Na,snr_db", [("16QAM", 1, 12.0), ("QPSK", 1, 8.0), ("QPSK", 4, 6.0)])
+def test_vamp_fast_and_generic_kernels_agree(alphabet, Na, snr_db):
+    """Register-resident VAMP kernel (one warp per frame, FFMA2, separable / table denoiser) against the generic
+    shared-memory kernel with float64 exponents on 20k frames with per-frame SVD factors."""
+    F = 20000
+    cfg = c2(F, alphabet=alphabet, Na=Na)
+    H, y, x, lab, idx = make_frames(cfg, F, snr_db, seed=21)
+    U, s, Vh = svd_factors(H)
+    snr = 10 ** (snr_db / 10)
+    a = pkg.VAMP(cfg, kernel='fast', outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    b = pkg.VAMP(cfg, kernel='generic', exp='f64', outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    c = pkg.VAMP(cfg, kernel='generic', exp='f32', outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    ca, cb, cc = a.counters_dict(), b.counters_dict(), c.counters_dict()
+    assert ca["frames"] == cb["frames"] == F and ca["nan_frames"] == cb["nan_frames"] == 0
+    ia, ib, ic = a.iters.cpu().numpy(), b.iters.cpu().numpy(), c.iters.cpu().numpy()
+    # VAMP's sigma2_tilde is posterior tail mass: exit iterations of slowly converging frames are not comparable between
+    # two float32 evaluation orders (SURVEY.md section 7).  Two-sided acceptance: the register-resident kernel must be as
+    # close to the float64-exponent kernel as the generic kernel's own float32-exp mode is.
+    assert (ia == ib).mean() >= (ic == ib).mean() - 0.03, ((ia == ib).mean(), (ic == ib).mean())
+    assert (np.abs(ia - ib) <= 1).mean() >= (np.abs(ic - ib) <= 1).mean() - 0.03
+    assert abs(ia.mean() - ib.mean()) < 0.02 * ib.mean()
+    for k in INT_KEYS:
+        slack = max(4, 1e-3 * F) * (4 if k.endswith("bit_err") else 1)
+        assert abs(ca[k] - cb[k]) <= abs(cc[k] - cb[k]) + slack, (k, ca[k], cb[k], cc[k])
+    d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
+    d32 = (c.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
+    assert float(d.median()) < 1e-5 and float(torch.quantile(d, 0.9)) <= max(1e-5, 10 * float(torch.quantile(d32, 0.9)))
+    # deterministic, and the early-exit-disabled mode runs exactly T iterations
+    a2 = pkg.VAMP(cfg, kernel='fast', outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    assert torch.equal(a.xmmse, a2.xmmse) and ints(a2.counters_dict()) == ints(ca)
+    fixed = pkg.VAMP(cfg, kernel='fast', outputs=False, early_exit=False).detect(U, s, Vh, y, snr, x, lab, idx).counters_dict()
+    assert fixed["iters"] == 20 * F
