@@ -11,7 +11,7 @@ from .data import Data
 from .loss import Loss
 from .bamp import BAMP
 from .scamp import SCAMP
-from .vamp import VAMP
+from .vamp import VAMP, svd_batched
 from .shrink import Shrink
 
-__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink"]
+__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink", "svd_batched"]

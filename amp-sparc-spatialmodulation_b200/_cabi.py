@@ -19,7 +19,8 @@ SQERR_NAMES = ['sqerr', 'sqerr_first', 'sqerr_mid', 'sqerr_last']
 
 # every symbol include/ampsm_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_host",
-           "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
+           "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
+           "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops",
            "ampsm_launch_count"]
 
@@ -62,6 +63,10 @@ def lib():
     vamp = [PP, AP, i64, i32, vp, i64, vp, i64, vp, i64, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_vamp_detect.argtypes = vamp + [vp]
     L.ampsm_vamp_detect_host.argtypes = vamp + [i32]
+    L.ampsm_svd_batched.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ampsm_vamp_from_h_workspace_bytes.argtypes = [PP, i64]
+    L.ampsm_vamp_from_h_workspace_bytes.restype = i64
+    L.ampsm_vamp_detect_from_h.argtypes = [PP, AP, i64, vp, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     scamp = [PP, AP, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_scamp_detect.argtypes = scamp + [vp, vp]
     L.ampsm_scamp_detect_host.argtypes = scamp + [i32]

@@ -354,6 +354,40 @@ int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int6
                     });
 }
 
+// ---------------------------------------------------------------- batched SVD, VAMP from the channel matrices
+int ampsm_svd_batched(int64_t frames, int32_t n, int32_t N, const void* H, void* U, float* s, void* Vh, int32_t* sweeps,
+                      void* stream) {
+    if (frames < 0 || (frames > 0 && (!H || !U || !s || !Vh))) { set_error("SVD: NULL pointer or frames < 0"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    return launch_svd_jacobi((const float2*)H, frames, n, N, (float2*)U, s, (float2*)Vh, sweeps, (cudaStream_t)stream);
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+int64_t ampsm_vamp_from_h_workspace_bytes(const ampsm_problem* p, int64_t frames) {
+    if (!p || frames < 0) return -1;
+    const size_t n = p->n, N = p->N;
+    return (int64_t)(align256((size_t)frames * n * n * 8) + align256((size_t)frames * n * 4) + align256((size_t)frames * n * N * 8));
+}
+
+int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H, const void* y,
+                             double sigma2, const float* sigma2_per_frame, double sparsity, const void* x_true,
+                             const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* var,
+                             int32_t* iters, float* traj, uint64_t* counters, void* workspace, void* stream) {
+    if (!p || !a) { set_error("problem / alphabet pointer is NULL"); return AMPSM_EINVAL; }
+    if (frames < 0 || (frames > 0 && (!H || !y || !workspace))) { set_error("VAMP from H: H / y / workspace is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (p->R != p->n || p->n > p->N) { set_error("VAMP from H: needs R = n <= N (got n=%d N=%d R=%d)", p->n, p->N, p->R); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    const size_t n = p->n, N = p->N;
+    unsigned char* w = (unsigned char*)workspace;
+    void* U = w;
+    float* s = (float*)(w + align256((size_t)frames * n * n * 8));
+    void* Vh = w + align256((size_t)frames * n * n * 8) + align256((size_t)frames * n * 4);
+    if (int e = ampsm_svd_batched(frames, p->n, p->N, H, U, s, Vh, nullptr, stream)) return e;
+    return ampsm_vamp_detect(p, a, frames, 0, U, (int64_t)(n * n), s, (int64_t)n, Vh, (int64_t)(n * N), y, sigma2, sigma2_per_frame,
+                             sparsity, x_true, sym_true, idx_true, xmap, xmmse, var, iters, traj, counters, stream);
+}
+
 // ---------------------------------------------------------------- SCAMP
 int64_t ampsm_scamp_workspace_bytes(const ampsm_problem* p, int64_t frames) {
     Geom g{};

@@ -96,6 +96,8 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
 int launch_loss(const LossArgs& a, cudaStream_t stream);
+// batched thin SVD H = U diag(s) Vh of dense [frames][n][N] complex64 matrices, n <= 32 (svd_jacobi.cu); sweeps optional
+int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);
 int probe_fp32x2(int device, double* tflops);
 

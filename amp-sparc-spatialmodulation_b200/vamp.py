@@ -54,3 +54,51 @@ class VAMP(Detector):
 
     def forward(self, U, s, Vh, y, SNR, x, symbols, indices):
         return self._wrap(self.detect(U, s, Vh, y, SNR, x, symbols, indices))
+
+    def detect_from_channel(self, H, y, SNR, x=None, symbols=None, indices=None, frame_base=0) -> Detection:
+        """vamp_model.py:56-61 for a batch of frames with their own channel matrices: batched Jacobi SVD on the device
+        (csrc/svd_jacobi.cu) followed by the VAMP iterations, one C-ABI call (``ampsm_vamp_detect_from_h``)."""
+        dev = self._cuda_device(y, H)
+        cfg = self.config
+        n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
+        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        F = y.shape[0]
+        H = H.to(dev, torch.complex64).contiguous()
+        if tuple(H.shape) != (F, n, N):
+            raise RuntimeError(f"H{tuple(H.shape)} is not ({F}, {n}, {N})")
+        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
+        counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        iters = torch.empty(F, dtype=torch.int32, device=dev)
+        xmap = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        xmmse = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        var = torch.empty(F, N, 1, dtype=torch.float32, device=dev) if self.outputs else None
+        traj = torch.empty(F, cfg.N_Layers, 3, dtype=torch.float32, device=dev) if self.trajectory else None
+        prob = self._problem(F, R=min(n, N), frame_base=frame_base)
+        ws = torch.empty(int(_cabi.lib().ampsm_vamp_from_h_workspace_bytes(prob, F)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().ampsm_vamp_detect_from_h(
+                prob, self._alphabet, F, H.data_ptr(), y.data_ptr(), float(self.E / SNR), None, float(self.sparsity),
+                ptr(xt), ptr(sym), ptr(idx), ptr(xmap), ptr(xmmse), ptr(var), iters.data_ptr(), ptr(traj),
+                counters.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ampsm_vamp_detect_from_h")
+        return Detection(F, counters, iters, xmap, xmmse, var, traj)
+
+
+def svd_batched(H, return_sweeps=False):
+    """Thin SVD of a batch of wide complex64 matrices on the device, ``H (F, n, N) -> U (F, n, n), s (F, n), Vh (F, n, N)``
+    with ``s`` descending -- the device-side stand-in for ``torch.linalg.svd(A, full_matrices=False)`` at
+    vamp_model.py:58 (one-sided Jacobi, one warp per matrix; singular-vector phases differ from LAPACK's)."""
+    if not H.is_cuda:
+        raise _cabi.AmpsmError("svd_batched runs on the GPU only (no CPU fallback)")
+    H = H.to(torch.complex64).contiguous()
+    F, n, N = H.shape
+    U = torch.empty(F, n, n, dtype=torch.complex64, device=H.device)
+    s = torch.empty(F, n, dtype=torch.float32, device=H.device)
+    Vh = torch.empty(F, n, N, dtype=torch.complex64, device=H.device)
+    sw = torch.empty(F, dtype=torch.int32, device=H.device) if return_sweeps else None
+    with torch.cuda.device(H.device):
+        rc = _cabi.lib().ampsm_svd_batched(F, n, N, H.data_ptr(), U.data_ptr(), s.data_ptr(), Vh.data_ptr(), ptr(sw),
+                                           torch.cuda.current_stream(H.device).cuda_stream)
+    _cabi.check(rc, "ampsm_svd_batched")
+    return (U, s, Vh, sw) if return_sweeps else (U, s, Vh)

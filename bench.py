@@ -420,6 +420,19 @@ def main():
                 msv = float(tt.item())
             cv = _cabi.counters_to_dict(tot.cpu().numpy())
             vout[tag] = (cv, msv)
+        # from the channel matrices: batched Jacobi SVD on the device + iterations in ONE call (vamp_model.py:56-61)
+        vfh = pkg.VAMP(cfgv, outputs=False)
+        Hv = H[:fv]
+        for _ in range(2):
+            vfh.detect_from_channel(Hv, yv, snr, xv, lv, iv)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        det = vfh.detect_from_channel(Hv, yv, snr, xv, lv, iv)
+        e1.record()
+        torch.cuda.synchronize()
+        ch = det.counters_dict()
+        ms_fh = e0.elapsed_time(e1)
         cv, msv = vout["exit"]
         cf, msf = vout["fixed_T"]
         vbytes = 8 * NR * NT + 8 * NR * NR + 4 * NR + 8 * NR + 8 * NT            # Vh, U, s, y, x_true: 25 472 B
@@ -439,6 +452,10 @@ def main():
             "fixed_T": {"value": cf["iters"] / (msf * 1e-3), "unit": "frame-iter/s", "iterations": ITERS,
                         "roofline_fp32": {"bound": "fp32", "achieved": tfl, "peak": tf32, "unit": "TFLOP/s",
                                           "frac": (tfl / tf32) if tf32 else None, "algorithmic_flop_per_frame_iter": vflop}},
+            "from_channel": {"frames_per_s": world * ch["frames"] / (ms_fh * 1e-3), "value": world * ch["iters"] / (ms_fh * 1e-3),
+                             "unit": "frame-iter/s", "ms": ms_fh,
+                             "what": "ampsm_vamp_detect_from_h: one-sided Jacobi SVD of every frame's H (one warp per matrix) "
+                                     "+ the iterations; per-rank time, not reduced over ranks"},
         }
     if cpu_base:
         out["cpu_baseline"] = cpu_base

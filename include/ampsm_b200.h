@@ -134,6 +134,31 @@ int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int6
                            uint64_t* counters, int device);
 
 /*
+ * Batched thin SVD -- replaces the caller-side `U, s, Vh = torch.linalg.svd(A, full_matrices=False)` of the reference's
+ * VAMP driver (vamp_model.py:56-58) for per-frame channel matrices, by one-sided Jacobi on the device (one warp per
+ * matrix, csrc/svd_jacobi.cu).
+ *   H  : complex64 [frames][n][N] dense, 1 <= n <= 32, n <= N, N in {8, 16, 32, 64}
+ *   U  : complex64 [frames][n][n];  s : float [frames][n] descending;  Vh : complex64 [frames][n][N];  H = U diag(s) Vh
+ *   sweeps : int32 [frames] executed Jacobi sweeps (optional, may be NULL)
+ * The phases of the singular-vector pairs are not LAPACK's (VAMP is invariant to them: vamp.py:22,67,72).
+ */
+int ampsm_svd_batched(int64_t frames, int32_t n, int32_t N, const void* H, void* U, float* s, void* Vh,
+                      int32_t* sweeps, void* stream);
+
+/*
+ * VAMP straight from per-frame channel matrices: ampsm_svd_batched into `workspace`, then ampsm_vamp_detect with
+ * per-frame factors -- the whole of vamp_model.py:56-61 for one batch of frames.  complex64 only.
+ *   H : complex64 [frames][n][N];  workspace : device scratch of ampsm_vamp_from_h_workspace_bytes(p, frames) bytes.
+ *   Every other argument as ampsm_vamp_detect.  p->R must be min(n, N) = n.
+ */
+int64_t ampsm_vamp_from_h_workspace_bytes(const ampsm_problem* p, int64_t frames);
+int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H, const void* y,
+                             double sigma2, const float* sigma2_per_frame, double sparsity,
+                             const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                             void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                             uint64_t* counters, void* workspace, void* stream);
+
+/*
  * SCAMP -- replaces scamp.SCAMP.forward (scamp.py:77-108): Tracker (8-25), SCAMPLayer iterations (43-59) with
  * the mean-only denoiser (61-68), exit on psi (105), Loss on (xmap, xmmse) (107).
  *   W : float [Lout][Lin] base matrix; A : complex64 [n][N] design matrix shared by all frames of the call

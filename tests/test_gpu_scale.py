@@ -282,3 +282,49 @@ def test_vamp_fast_and_generic_kernels_agree(alphabet, Na, snr_db):
     assert torch.equal(a.xmmse, a2.xmmse) and ints(a2.counters_dict()) == ints(ca)
     fixed = pkg.VAMP(cfg, kernel='fast', outputs=False, early_exit=False).detect(U, s, Vh, y, snr, x, lab, idx).counters_dict()
     assert fixed["iters"] == 20 * F
+
+
+@pytest.mark.parametrize("n,N", [(32, 64), (24, 64), (8, 16), (4, 8), (32, 32)])
+def test_batched_jacobi_svd_reconstructs_and_matches_lapack(n, N):
+    """ampsm_svd_batched: H = U diag(s) Vh to float32 accuracy, orthonormal factors, singular values equal to LAPACK's
+    (torch.linalg.svdvals in float64), descending order; an ill-conditioned (Kronecker-correlated) batch included."""
+    F = 3000
+    g = torch.Generator(device=DEV).manual_seed(4)
+    H = torch.view_as_complex(torch.randn(F, n, N, 2, device=DEV, generator=g) * float(np.sqrt(0.5 / n)))
+    # second half: exponential correlation on both sides (rho = 0.9): condition numbers of 1e2 .. 1e3
+    def corr_root(m, rho):
+        R = rho ** (torch.arange(m, device=DEV)[:, None] - torch.arange(m, device=DEV)[None, :]).abs().double()
+        w, V = torch.linalg.eigh(R)
+        return (V * w.clamp_min(0).sqrt()) @ V.T
+    Hc = (corr_root(n, 0.9).to(torch.complex128) @ H[F // 2:].to(torch.complex128) @ corr_root(N, 0.9).to(torch.complex128))
+    H = torch.cat([H[:F // 2], Hc.to(torch.complex64)]).contiguous()
+    U, s, Vh, sw = pkg.svd_batched(H, return_sweeps=True)
+    rec = (U * s.unsqueeze(-2).to(torch.complex64)) @ Vh
+    scale = H.abs().amax(dim=(1, 2))
+    assert float(((rec - H).abs().amax(dim=(1, 2)) / scale).max()) < 2e-5
+    eye_n = torch.eye(n, dtype=torch.complex64, device=DEV)
+    assert float((U.mH @ U - eye_n).abs().max()) < 2e-5 and float((Vh @ Vh.mH - eye_n).abs().max()) < 2e-5
+    ref = torch.linalg.svdvals(H.to(torch.complex128))
+    assert float(((s.double() - ref).abs() / ref[:, :1]).max()) < 3e-5      # float32 through ~200 rotations per row
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+    assert 2 <= int(sw.min()) and int(sw.max()) <= 14
+
+
+def test_vamp_from_channel_equals_factor_entry_point():
+    """detect_from_channel (device Jacobi SVD + iterations in one call) against factors from float64 eigh of H H^H fed
+    to the factor entry point: same decisions on all but near-tie frames."""
+    F = 20000
+    cfg = c2(F)
+    H, y, x, lab, idx = make_frames(cfg, F, 12.0, seed=31)
+    snr = 10 ** 1.2
+    U, s, Vh = svd_factors(H)
+    a = pkg.VAMP(cfg, outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    b = pkg.VAMP(cfg, outputs=True).detect_from_channel(H, y, snr, x, lab, idx)
+    ca, cb = a.counters_dict(), b.counters_dict()
+    assert cb["frames"] == F and cb["nan_frames"] == 0
+    ia, ib = a.iters.cpu().numpy(), b.iters.cpu().numpy()
+    assert (ia == ib).mean() > 0.97
+    for k in INT_KEYS:
+        assert abs(ca[k] - cb[k]) <= max(4, 2e-3 * F) * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
+    d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
+    assert float(d.median()) < 1e-5
