@@ -15,7 +15,7 @@
 //   * y~ = diag(s) U^H y (vamp.py:22) is formed once per frame, lane k owning singular value k, with U read
 //     column-wise (coalesced over k) from L2;
 //   * the scalar bookkeeping (alpha, sigma^2, dxdr, sigma~^2 with the reference's clips, vamp.py:73-94) is evaluated
-//     redundantly by every lane from two warp sums; scalar divisions are IEEE (they are not on the hot path);
+//     redundantly by every lane from two warp sums, with MUFU reciprocals (the generic kernel keeps IEEE divisions);
 //   * the un-halved scalar-variance section denoiser (vamp.py:96-119), the allclose exit on var (vamp.py:185) and Loss
 //     on (r, xmmse) (vamp.py:187) are shared with the BAMP kernels (fastops.cuh).
 // launch_vamp_fast() returns AMPSM_ENOFIT for anything else (complex128, other shapes): the generic kernel takes it.
@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
 
         int t_done = 0;
         for (int it = 0; it < g.max_iters; ++it) {
-            // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66)
-            const float ratio = (it == 0) ? (float)(noise_var_d / s2t0_d) : nv / s2t;
+            // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66).  The scalar
+            // divisions of the bookkeeping are MUFU reciprocals (2^-23 relative): an IEEE division is a ~15-instruction
+            // dependent sequence, eight of them per iteration sat on the critical path of the first version.
+            const float rs2t = fast_rcp(s2t);
+            const float ratio = (it == 0) ? (float)(noise_var_d / s2t0_d) : nv * rs2t;
             // ================= row pass: q = Vh r~ (vamp.py:67) =================
             {
                 constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 const float qx = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
                 const float qy = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
                 const float4 rs = rowstate[lane];
-                scale = __frcp_rn(rs.z + ratio);
+                scale = fast_rcp(rs.z + ratio);
                 const float dx = scale * (rs.x + ratio * qx) - qx, dy = scale * (rs.y + ratio * qy) - qy;
                 rowvec[lane + (lane >> 3)] = make_float4(dx, dy, dy, -dx);      // operand pairs (dx,dy), (dy,-dx)
             }
@@ -255,12 +258,12 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             }
             // scalars (vamp.py:71-82), the same in every lane
             const float scale_tot = warp_sum(scale);
-            const float var_lmmse = (scale_tot / (float)R) * nv;               // scale.mean() * noise_var
+            const float var_lmmse = (scale_tot * (1.0f / (float)R)) * nv;      // scale.mean() * noise_var
             const float xt_var = eta * var_lmmse + one_m_eta * s2t;
-            const float alpha = clampF(xt_var / s2t, ratio_min, ratio_max);
-            const float inv_1ma = __frcp_rn(1.0f - alpha);
-            const float sig2 = clampF(alpha / (1.0f - alpha) * s2t, var_min, var_max);
-            const float rsig = __frcp_rn(sig2);
+            const float alpha = clampF(xt_var * rs2t, ratio_min, ratio_max);
+            const float inv_1ma = fast_rcp(1.0f - alpha);
+            const float sig2 = clampF(alpha * inv_1ma * s2t, var_min, var_max);
+            const float rsig = __frcp_rn(sig2);                                // the one accurate reciprocal: it scales every exponent
             __syncwarp();
             // ================= r = (x~ - alpha r~)/(1 - alpha), denoiser with the scalar variance (vamp.py:79-84) ==========
             float2 r[CP];
@@ -293,9 +296,9 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 close &= fabsf(vn_[t] - var_old[t]) <= __fadd_rn(kAtol, fabsf(__fmul_rn(kRtol, var_old[t])));
             }
             const float vtot = warp_sum(vs);
-            const float vmean = vtot / (float)N;
-            const float dxdr = clampF(vmean / sig2, ratio_min, ratio_max);
-            const float norm = __frcp_rn(1.0f - dxdr);
+            const float vmean = vtot * (1.0f / (float)N);
+            const float dxdr = clampF(vmean * rsig, ratio_min, ratio_max);
+            const float norm = fast_rcp(1.0f - dxdr);
             float s_mse = 0.f;
 #pragma unroll
             for (int t = 0; t < CP; ++t) {
