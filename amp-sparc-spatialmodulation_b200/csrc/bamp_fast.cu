@@ -23,15 +23,19 @@
 
 namespace ampsm {
 
-constexpr int kWarpsPerCta = 4;
-
-template <int RT, int CTL, int M_, int K_>
+// DIRECT = false: the frame's H lands in a per-warp staging buffer (bulk TMA) and |H|^2 lives in registers next to H.
+// DIRECT = true : no staging buffer -- the lanes load their tiles straight from global memory (full 128-byte lines,
+//                 issued right after the last iteration so that they fly under the Loss epilogue of the previous
+//                 frame, L2-prefetched one frame ahead).  Spares the shared-memory pipe the 16 KiB TMA write and the
+//                 64 LDS.128 per frame; |H|^2 stays in registers.  (A variant with |H|^2 in SHARED memory, 168
+//                 registers and 12 frames per SM measured 20 % slower: it is bound by the shared-memory pipe.)
+template <int RT, int CTL, int M_, int K_, bool DIRECT>
 struct FastShape {
     static constexpr int n = 4 * RT, N = 8 * CTL;
     static constexpr int VW = CTL >= 2 ? 2 : 1;            // columns per vector load
     static constexpr int NV = CTL / VW;
     static constexpr int CP = (N + 31) / 32;               // owned columns per lane in the denoiser
-    static constexpr int stage_bytes = (n * N * 8 + n * 8 + 127) & ~127;
+    static constexpr int stage_bytes = DIRECT ? 0 : ((n * N * 8 + n * 8 + 127) & ~127);   // H, y
     static constexpr int rowpart_bytes = n * 8 * 16;
     static constexpr int colpart_bytes = N * 4 * 16;
     static constexpr int ebuf_bytes = 32 * CP * K_ * 4;
@@ -42,12 +46,16 @@ struct FastShape {
     static constexpr int wvec_bytes = ((n > 32 ? n : 32) * 8 + 127) & ~127;
     static constexpr int state_bytes = 32 * 16 + 32 * 8 + (N > 32 ? N : 32) * 8 + 128;   // z/u, y, xmap, counters
     static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + state_bytes + 128;
+    static constexpr int warps_per_cta = DIRECT ? 1 : 4;
+    static constexpr int ctas_per_sm = DIRECT ? 8 : 2;    // two warps per SM sub-partition either way: 255 registers
 };
 
-
-template <int RT, int CTL, int M_, int K_, bool GRID>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const __grid_constant__ BampArgs a) {
-    using S = FastShape<RT, CTL, M_, K_>;
+template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
+__global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_cta * 32, FastShape<RT, CTL, M_, K_, DIRECT>::ctas_per_sm)
+    bamp_fast_kernel(const __grid_constant__ BampArgs a) {
+    using S = FastShape<RT, CTL, M_, K_, DIRECT>;
+    constexpr int kWarpsPerCta = S::warps_per_cta;
+    static_assert(!DIRECT || CTL % 2 == 0, "DIRECT serves the packed shapes");
     constexpr int n = S::n, N = S::N, VW = S::VW, NV = S::NV, CP = S::CP;
     constexpr int L_ = N / M_;
     static_assert(N % M_ == 0, "section size must divide N");
@@ -77,11 +85,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     const long long warp_global = (long long)blockIdx.x * kWarpsPerCta + wic;
     constexpr uint32_t kHBytes = n * N * 8, kYBytes = n * 8;
 
-    if (lane == 0) {
-        mbar_init(mbar, 1);
-        fence_mbar_init();
+    if constexpr (!DIRECT) {
+        if (lane == 0) {
+            mbar_init(mbar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
     }
-    __syncwarp();
     auto prefetch = [&](long long f) {
         if (lane == 0) {
             mbar_expect_tx(mbar, kHBytes + kYBytes);
@@ -90,7 +100,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
         }
     };
     long long f = warp_global;
-    if (f < a.frames) prefetch(f);
+    if constexpr (!DIRECT)
+        if (f < a.frames) prefetch(f);
     uint32_t phase = 0;
 
     // per-warp counters in shared memory (slots as the Counter enum, slot 12 = squared-error sum as double)
@@ -103,10 +114,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     //   H x    : A += h (xx,xx), B += h (xy,xy)   ->  re = A.lo - B.hi, im = B.lo + A.hi
     //   H^H g  : A += h (gx,gy), B += h (gy,-gx)  ->  re = A.lo + A.hi, im = B.lo + B.hi
     constexpr bool PAIR = (VW == 2);
+    static_assert(!DIRECT || PAIR, "DIRECT needs the packed tile");
     pair_t Hp[PAIR ? RT : 1][CTL], Pp[PAIR ? RT : 1][PAIR ? NV : 1];
     float Hr[PAIR ? 1 : RT][CTL], Hi[PAIR ? 1 : RT][CTL], P[PAIR ? 1 : RT][CTL];
+    float2 ynext = make_float2(0.f, 0.f);
+    // global memory -> registers: per (i, t) the warp reads 4 rows x one full 128-byte line
+    auto load_tile = [&](long long ff) {
+        const float2* Hf = a.H + ff * a.H_stride;
+#pragma unroll
+        for (int i = 0; i < (PAIR ? RT : 0); ++i) {
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(Hf + (size_t)(la * RT + i) * N + (t * 8 + lb) * 2));
+                Hp[i][2 * t] = v.x;
+                Hp[i][2 * t + 1] = v.y;
+            }
+        }
+        ynext = lane < n ? __ldg(a.y + ff * n + lane) : make_float2(0.f, 0.f);
+    };
+    if constexpr (DIRECT)
+        if (f < a.frames) load_tile(f);
 
     for (; f < a.frames; f += warps_total) {
+        if constexpr (DIRECT) {
+            // |H|^2 (bamp.py:18) of the tile that load_tile() brought into registers, paired over adjacent columns
+#pragma unroll
+            for (int i = 0; i < (PAIR ? RT : 0); ++i) {
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    float a0, a1, b0, b1;
+                    unpack2(fmul2(Hp[i][2 * t], Hp[i][2 * t]), a0, a1);
+                    unpack2(fmul2(Hp[i][2 * t + 1], Hp[i][2 * t + 1]), b0, b1);
+                    Pp[i][t] = pack2(a0 + a1, b0 + b1);
+                }
+            }
+            const long long nf = f + warps_total;
+            if (nf < a.frames && lane == 0) {   // one frame ahead: H and y into L2, so that load_tile() hits there
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.H + nf * a.H_stride), "r"(kHBytes) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.y + nf * n), "r"(kYBytes) : "memory");
+            }
+        } else {
         mbar_wait(mbar, phase);
         phase ^= 1u;
         // ---- staging buffer -> registers: lane (a,b) takes rows a*RT+i, column vectors (t*8+b)*VW+e
@@ -143,9 +190,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
                 for (int c = 0; c < CTL; ++c) P[i][c] = fmaf(Hr[i][c], Hr[i][c], Hi[i][c] * Hi[i][c]);
             }
         }
-        const float2 yv = lane < n ? stY[lane] : make_float2(0.f, 0.f);
+        }
+        float2 yv = ynext;
+        if constexpr (!DIRECT) yv = lane < n ? stY[lane] : make_float2(0.f, 0.f);
         __syncwarp();
-        {   // the staging buffer is free again: bring in the next frame while this one iterates
+        if constexpr (!DIRECT) {   // the staging buffer is free again: bring in the next frame while this one iterates
             const long long nf = f + warps_total;
             if (nf < a.frames) prefetch(nf);
         }
@@ -532,6 +581,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
             if (g.early_exit && all_close) break;
         }
 
+        if constexpr (DIRECT) {   // the H registers are free: fetch the next frame's tile under the Loss epilogue
+            const long long nf = f + warps_total;
+            if (nf < a.frames) load_tile(nf);
+        }
         // ================= outputs =================
         float2 xh[CP], xmap[CP];
         float var[CP];
@@ -684,13 +737,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bamp_fast_kernel(const _
     }
 }
 
-template <int RT, int CTL, int M_, int K_, bool GRID>
+template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
 static int launch_shape(const BampArgs& a, cudaStream_t stream) {
-    using S = FastShape<RT, CTL, M_, K_>;
+    using S = FastShape<RT, CTL, M_, K_, DIRECT>;
+    constexpr int kWarpsPerCta = S::warps_per_cta;
     int dev = 0, sms = 0;
     if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID>;
+    auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID, DIRECT>;
     const size_t smem = (size_t)S::warp_bytes * kWarpsPerCta;
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute(bamp_fast)"))
@@ -709,7 +763,7 @@ static int launch_shape(const BampArgs& a, cudaStream_t stream) {
 
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
     const Geom& g = a.g;
-    // the fused Loss epilogue assumes one time slot per frame; the staging path needs 16-byte aligned frames
+    // the fused Loss epilogue assumes one time slot per frame; the tile loads need 16-byte aligned frames
     if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0) return AMPSM_ENOFIT;
     if ((reinterpret_cast<uintptr_t>(a.H) % 16) || (reinterpret_cast<uintptr_t>(a.y) % 16) || (((size_t)g.n * 8) % 16) ||
         (a.H_stride != 0 && ((size_t)a.H_stride * 8) % 16))
@@ -717,15 +771,23 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
     const int K = a.al.K;
     BampArgs b = a;
     b.grid = make_grid(a.al);
-    if (g.n == 32 && g.N == 64 && g.M == 64 && K == 16 && b.grid.ok && !getenv("AMPSM_NO_GRID"))
-        return launch_shape<8, 8, 64, 16, true>(b, stream);       // C2 with the separable 16-QAM denoiser
-#define AMPSM_SHAPE(RT, CTL, MM, KK) \
-    if (g.n == 4 * RT && g.N == 8 * CTL && g.M == MM && K == KK) return launch_shape<RT, CTL, MM, KK, false>(b, stream);
-    AMPSM_SHAPE(8, 8, 64, 16)     // C2: 64 x 32, 16-QAM, one active antenna
-    AMPSM_SHAPE(1, 1, 8, 4)       // C1:  8 x  4, QPSK
-    AMPSM_SHAPE(8, 8, 64, 4)      // 64 x 32, QPSK
-    AMPSM_SHAPE(8, 8, 16, 4)      // 64 x 32, QPSK, Na = 4
-    AMPSM_SHAPE(4, 4, 32, 4)      // 32 x 16, QPSK
+    const bool staged = getenv("AMPSM_STAGED") != nullptr;     // A/B switch: the TMA-staged variant of the 64-column shapes
+    if (g.n == 32 && g.N == 64 && g.M == 64 && K == 16 && b.grid.ok && !getenv("AMPSM_NO_GRID")) {   // C2, separable 16-QAM denoiser
+        if (staged) return launch_shape<8, 8, 64, 16, true, false>(b, stream);
+        return launch_shape<8, 8, 64, 16, true, true>(b, stream);
+    }
+#define AMPSM_SHAPE(RT, CTL, MM, KK, DIRECT) \
+    if (g.n == 4 * RT && g.N == 8 * CTL && g.M == MM && K == KK) return launch_shape<RT, CTL, MM, KK, false, DIRECT>(b, stream);
+    if (!staged) {
+        AMPSM_SHAPE(8, 8, 64, 16, true)     // C2 with the table-driven denoiser
+        AMPSM_SHAPE(8, 8, 64, 4, true)      // 64 x 32, QPSK
+        AMPSM_SHAPE(8, 8, 16, 4, true)      // 64 x 32, QPSK, Na = 4
+    }
+    AMPSM_SHAPE(8, 8, 64, 16, false)
+    AMPSM_SHAPE(1, 1, 8, 4, false)       // C1:  8 x  4, QPSK
+    AMPSM_SHAPE(8, 8, 64, 4, false)
+    AMPSM_SHAPE(8, 8, 16, 4, false)
+    AMPSM_SHAPE(4, 4, 32, 4, false)      // 32 x 16, QPSK
 #undef AMPSM_SHAPE
     return AMPSM_ENOFIT;
 }

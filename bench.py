@@ -215,7 +215,7 @@ def main():
     cpu_base = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:       # before CUDA is touched in this process
         cores = os.cpu_count() or 1
-        frames_cpu = args.cpu_frames or 4096 * cores
+        frames_cpu = args.cpu_frames or 32768 * cores      # ~10-15 s of host work
         pool = CpuPool(cores)
         rate, used, wall = pool.rate(frames_cpu, args.snr_db)
         pool.close()
