@@ -13,5 +13,6 @@ from .bamp import BAMP
 from .scamp import SCAMP
 from .vamp import VAMP, svd_batched
 from .shrink import Shrink
+from .simulate import MonteCarlo, device_frames, run_scamp
 
-__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink", "svd_batched"]
+__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink", "svd_batched", "MonteCarlo", "device_frames", "run_scamp"]

@@ -328,3 +328,26 @@ def test_vamp_from_channel_equals_factor_entry_point():
         assert abs(ca[k] - cb[k]) <= max(4, 2e-3 * F) * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
     d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
     assert float(d.median()) < 1e-5
+
+
+def test_monte_carlo_sweep_exports_reference_schema(tmp_path):
+    """simulate.MonteCarlo (the GPU counterpart of Model.simulate, bamp_model.py:44-67): device-generated frames, one JSON
+    per Eb/N0 point with the reference's keys, error rates falling with SNR, VAMP on Kronecker-correlated channels."""
+    import json
+    cfg = pkg.Config(64, 1, 32, 1, 1, batch=8192, generator_mode='sparc', iterations=20, alphabet='QPSK',
+                     channel_profile='uniform', device=str(DEV))
+    mc = pkg.MonteCarlo(cfg, 'bamp', frames_per_point=20000, chunk=8192, path=str(tmp_path), device=DEV)
+    pts = mc.simulate(start=-6.0, final=2.0, step=4.0, stop_fer=0.0)
+    assert [p["EbN0dB"] for p in pts] == [-6.0, -2.0, 2.0] and all(p["frames"] == 20000 for p in pts)
+    assert pts[0]["fer"] > pts[1]["fer"] > pts[2]["fer"] and pts[0]["fer"] > 0.1
+    d = json.load(open(tmp_path / "-2.0.json"))
+    for k in pkg.Loss.keys + ['T', 'EbN0dB', 'SNRdB', 'rate', 'C', 'ShannonLimitdB']:
+        assert k in d, k
+    assert d["fer"] == pytest.approx(pts[1]["fer"]) and d["T"] == pytest.approx(pts[1]["T"])
+    # same seed, same counters; another chunking of the same pool changes the draws but not the statistics
+    again = pkg.MonteCarlo(cfg, 'bamp', frames_per_point=20000, chunk=8192, device=DEV).run_point(-2.0, 1)
+    assert again["frame_err"] == round(pts[1]["fer"] * 20000)
+    vm = pkg.MonteCarlo(cfg, 'vamp', frames_per_point=12000, chunk=4096, channel='kronecker', rho_t=0.5, rho_r=0.5, device=DEV)
+    c0, c1 = vm.run_point(-2.0, 0), vm.run_point(6.0, 1)
+    assert c0["frames"] == c1["frames"] == 12000 and c0["nan_frames"] == 0
+    assert c1["frame_err"] < c0["frame_err"]

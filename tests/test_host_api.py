@@ -135,3 +135,34 @@ def test_cabi_struct_layout_matches_header():
     import ctypes
     assert ctypes.sizeof(_cabi.Alphabet) == 4 + 4 * 16 + 4 + 8 * 16 * 2 or ctypes.sizeof(_cabi.Alphabet) == 328
     assert ctypes.sizeof(_cabi.Problem) == 16 * 4 + 8
+
+
+def test_device_frames_generator_is_consistent_on_cpu():
+    """simulate.device_frames (the on-device input generator of the Monte-Carlo driver) with a CPU generator: labels and
+    flat indices describe x as Data.generate_message does (data.py:88-90), y - H x is noise of variance Na/Nr/SNR, and
+    the Kronecker option imposes the exponential correlation."""
+    import torch
+    from amp_sparc_spatialmodulation_b200.simulate import device_frames, exp_corr_root
+    cfg = pkg.Config(64, 4, 32, 1, 1, batch=4096, generator_mode='sparc', iterations=20, alphabet='QPSK',
+                     channel_profile='uniform', device='cpu')
+    gen = torch.Generator(device='cpu').manual_seed(5)
+    snr = 10.0
+    H, y, x, lab, idx = device_frames(cfg, 4096, snr, gen)
+    F, N, L, M = 4096, cfg.N, cfg.L, cfg.M
+    nz = x.reshape(-1).nonzero().reshape(-1)
+    assert torch.equal(nz, idx) and idx.numel() == F * L                      # sorted flat positions, one per section
+    assert bool(((idx % N) // M == torch.arange(L).repeat(F)).all())
+    sym = torch.as_tensor(np.asarray(cfg.symbols)).to(torch.complex64)
+    gray = np.asarray(cfg.gray)
+    k = (x.reshape(-1)[idx][:, None] - sym[None, :]).abs().argmin(dim=1)
+    assert np.array_equal(gray[k.numpy()], lab.numpy())
+    noise = y - (H @ x.unsqueeze(-1)).squeeze(-1)
+    sigma2 = (cfg.Na / cfg.Nr) / snr
+    assert abs(float(noise.abs().pow(2).mean()) / sigma2 - 1) < 0.02
+    assert abs(float(H.abs().pow(2).mean()) * cfg.Nr - 1) < 0.02
+    Hk, *_ = device_frames(cfg, 4096, snr, gen, channel='kronecker', rho_t=0.7, rho_r=0.5)
+    Rt = (Hk.mH @ Hk).mean(dim=0) / (Hk.abs().pow(2).sum(dim=1).mean())         # column correlation, unit diagonal
+    assert abs(float(Rt[0, 1].real) - 0.7) < 0.05 and abs(float(Rt[0, 2].real) - 0.49) < 0.05
+    root = exp_corr_root(8, 0.9, 'cpu').to(torch.complex128)
+    i = torch.arange(8, dtype=torch.float64)
+    assert float(((root @ root).real - 0.9 ** (i[:, None] - i[None, :]).abs()).abs().max()) < 1e-6
