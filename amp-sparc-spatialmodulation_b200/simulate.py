@@ -186,9 +186,9 @@ def main(argv=None):
     ap.add_argument("--channel", default="iid", choices=["iid", "kronecker"])
     ap.add_argument("--rho-t", type=float, default=0.0)
     ap.add_argument("--rho-r", type=float, default=0.0)
-    ap.add_argument("--start", type=float, default=None)
-    ap.add_argument("--final", type=float, default=None)
-    ap.add_argument("--step", type=float, default=1.0)
+    ap.add_argument("--ebn0-start", dest="start", type=float, default=None, help="first Eb/N0 in dB (default: ceil of the Shannon limit)")
+    ap.add_argument("--ebn0-final", dest="final", type=float, default=None, help="last Eb/N0 in dB (default: first + 20)")
+    ap.add_argument("--ebn0-step", dest="step", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--path", default=None, help="directory for the per-point JSON files (reference schema)")
     a = ap.parse_args(argv)
