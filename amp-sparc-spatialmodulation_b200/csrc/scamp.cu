@@ -5,33 +5,21 @@
 // A is streamed tile by tile; tiles of A that are entirely zero (the band structure of a coupled design matrix,
 // channel.py:89-91) are skipped through a tile map computed once per call from A itself.  Frames that met the
 // exit test are frozen: their tiles are skipped and their state is never rewritten.
+#include <cstdlib>
+
 #include "blockops.cuh"
 #include "kernels.h"
+#include "scamp_ws.cuh"
 
 namespace ampsm {
 
 constexpr int BM = 64;   // frames per tile
 constexpr int BN = 32;   // output columns per tile (rows of A in `residual`, columns of A in `estimate`)
 constexpr int BK = 32;   // reduction chunk
-constexpr int TILE = 32; // granularity of the zero-tile map of A
-
-struct ScampWs {
-    float2* Xh;      // [F][N]
-    float2* Z;       // [F][n]
-    float2* Zs;      // [F][n]   Z / phi
-    float2* Xmap;    // [F][N]
-    float* psi;      // [F][Lc]
-    float* phi;      // [F][Lr]
-    float* tau;      // [F][Lc]
-    float* b;        // [F][Lr]
-    int* active;     // [F]
-    int* iters;      // [F]
-    void* scr;       // [F][3N] exponent-typed scratch of the denoiser
-    unsigned char* nz;  // [ceil(n/TILE)][ceil(N/TILE)]
-    int nzc;         // columns of nz
-};
 
 __host__ __device__ inline size_t up256(size_t v) { return (v + 255) & ~size_t(255); }
+
+static bool scamp_use_tc(long long F) { return F >= 128 && !getenv("AMPSM_SCAMP_SIMT"); }
 
 static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, ScampWs* ws, unsigned char* base) {
     size_t o = 0;
@@ -54,6 +42,7 @@ static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, S
     w.scr = take((size_t)F * g.N * 3 * (exp64 ? 8 : 4));
     w.nzc = (g.N + TILE - 1) / TILE;
     w.nz = take((size_t)((g.n + TILE - 1) / TILE) * w.nzc);
+    w.At = (float2*)take(scamp_use_tc(F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
     if (ws) *ws = w;
     return o;
 }
@@ -318,10 +307,19 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
     count_launch();
     const dim3 grid_res((g.n + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
     const dim3 grid_est((g.N + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
+    // batches of >= 128 frames: both GEMMs on the tensor cores (tcgen05, 3xTF32, scamp_tc.cu); smaller ones on the SIMT tiles
+    const bool use_tc = scamp_use_tc(F);
+    if (use_tc)
+        if (int e = scamp_tc_prepare(a.A, w.At, g.n, g.N, stream)) return e;
     for (int t = 0; t < g.max_iters; ++t) {
         scamp_scalars_kernel<<<(unsigned)F, 64, 0, stream>>>(w, g, a.W, a.sigma2, a.sigma2_pf, F);
-        scamp_gemm_kernel<0><<<grid_res, 256, 0, stream>>>(w, g, a.A, a.y, F);
-        scamp_gemm_kernel<1><<<grid_est, 256, 0, stream>>>(w, g, a.A, a.y, F);
+        if (use_tc) {
+            if (int e = scamp_tc_gemm(0, w, g, a.A, a.y, F, stream)) return e;
+            if (int e = scamp_tc_gemm(1, w, g, w.At, a.y, F, stream)) return e;
+        } else {
+            scamp_gemm_kernel<0><<<grid_res, 256, 0, stream>>>(w, g, a.A, a.y, F);
+            scamp_gemm_kernel<1><<<grid_est, 256, 0, stream>>>(w, g, a.A, a.y, F);
+        }
         if (exp64)
             scamp_denoise_kernel<true><<<(unsigned)F, 256, 0, stream>>>(w, g, a.al, a.io.x_true, a.traj, t, F);
         else

@@ -1,0 +1,335 @@
+// SCAMP's two batched complex GEMMs (scamp.py:48,56) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the
+// 3xTF32 split (hi*hi + hi*lo + lo*hi, float32 accumulation in TMEM), operands staged in shared memory in the canonical
+// K-major no-swizzle UMMA layout, accumulators read back with tcgen05.ld for the fused epilogues of scamp.cu.
+//
+//   MODE 0 (residual) : S[f][i] = sum_j Xh[f][j] A[i][j]         B-source = A   [n][N]
+//   MODE 1 (estimate) : S[f][j] = sum_i Zs[f][i] conj(A[i][j])   B-source = A^T [N][n]  (transposed once per call)
+//
+// One CTA = one 128-frame x 64-output tile.  Complex arithmetic on split planes: the frame tile (MMA operand A, M = 128)
+// and the design-matrix tile (MMA operand B, N = 64) are each split into {re,im} x {hi,lo} float32 planes while they are
+// staged (hi = value with the low 13 mantissa bits cleared -- what kind::tf32 reads anyway --, lo = value - hi, exact);
+// per K = 8 step twelve MMAs feed two accumulators
+//   D_re += Xr Br -/+ Xi Bi        D_im += Xr Bi +/- ... Xi Br      (signs by MODE; the minus is the descriptor's negate-A bit)
+// 32 x 32 tiles of the design matrix that are entirely zero (band structure, channel.py:89-91) are skipped through the
+// tile map of scamp.cu; tiles whose 128 frames all met the exit test are skipped altogether.
+// Shared memory is single-buffered (96 KiB per CTA): two CTAs per SM overlap one's staging with the other's MMAs.
+#include "blockops.cuh"
+#include "kernels.h"
+#include "scamp_ws.cuh"
+
+namespace ampsm {
+
+namespace {
+
+constexpr int TM = 128;          // frames per tile (UMMA M)
+constexpr int TN = 64;           // outputs per tile (UMMA N)
+constexpr int TK = 32;           // reduction elements per staged block (4 MMA K-steps of 8)
+constexpr int kTcThreads = 256;
+constexpr int kTmemCols = 128;   // D_re | D_im, 64 float32 columns each
+
+constexpr int kXPlane = TM * TK * 4;         // bytes of one frame-tile plane (16 KiB)
+constexpr int kBPlane = TN * TK * 4;         // bytes of one design-tile plane (8 KiB)
+constexpr int kSmemX = 0;                    // planes: Xr_hi, Xr_lo, Xi_hi, Xi_lo
+constexpr int kSmemB = 4 * kXPlane;          // planes: Br_hi, Br_lo, Bi_hi, Bi_lo
+constexpr int kSmemBar = kSmemB + 4 * kBPlane;
+constexpr int kSmemTotal = kSmemBar + 64;
+
+// K-major, no swizzle: 8 rows x 16 bytes core matrices; a plane is [K chunk of 4][row group of 8][8 rows][16 B]
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);             // start address            bits [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;       // leading byte offset      bits [16,30)  (next K chunk)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;       // stride byte offset       bits [32,46)  (next 8-row group)
+    d |= (uint64_t)1 << 46;                                  // descriptor version 1 (Blackwell)
+    return d;                                                // base offset 0, layout type SWIZZLE_NONE
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 64, optional negate-A
+__device__ __forceinline__ uint32_t umma_idesc(bool neg_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// split four values into the hi / lo planes: 16 bytes each at (chunk, row) of the canonical layout
+__device__ __forceinline__ void split_store(unsigned char* hi_plane, unsigned char* lo_plane, uint32_t off, float a, float b, float c,
+                                            float d) {
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u), bh = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+    const float ch = __uint_as_float(__float_as_uint(c) & 0xffffe000u), dh = __uint_as_float(__float_as_uint(d) & 0xffffe000u);
+    *reinterpret_cast<float4*>(hi_plane + off) = make_float4(ah, bh, ch, dh);
+    *reinterpret_cast<float4*>(lo_plane + off) = make_float4(a - ah, b - bh, c - ch, d - dh);
+}
+
+// Bm: the B-source matrix [Odim][Kdim] complex64 row-major (A for MODE 0, A^T for MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w, Geom g, const float2* __restrict__ Bm,
+                                                                      const float2* __restrict__ y, long long F) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int act_s[TM];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long f0 = (long long)blockIdx.y * TM;
+    const int o0 = blockIdx.x * TN;                       // first output of this tile
+    const int Kdim = MODE == 0 ? g.N : g.n;               // reduction length
+    const int Odim = MODE == 0 ? g.n : g.N;               // output width
+    const float2* __restrict__ Xin = MODE == 0 ? w.Xh : w.Zs;
+
+    int any_active = 0;
+    if (tid < TM) {
+        const long long f = f0 + tid;
+        const int a = (f < F) ? w.active[f] : 0;
+        act_s[tid] = a;
+        any_active = a;
+    }
+    if (!__syncthreads_or(any_active)) return;            // before any TMEM allocation
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    unsigned char* Xp[4] = {smem + kSmemX, smem + kSmemX + kXPlane, smem + kSmemX + 2 * kXPlane, smem + kSmemX + 3 * kXPlane};
+    unsigned char* Bp[4] = {smem + kSmemB, smem + kSmemB + kBPlane, smem + kSmemB + 2 * kBPlane, smem + kSmemB + 3 * kBPlane};
+    constexpr uint32_t kXLbo = TM * 16, kBLbo = TN * 16, kSbo = 128;
+
+    constexpr int kXItems = TM * (TK / 4) / kTcThreads;    // (row, K chunk) items of the frame tile per thread   (4)
+    constexpr int kBItems = TN * (TK / 4) / kTcThreads;    // ... of the design tile                              (2)
+    static_assert(TM * (TK / 4) % kTcThreads == 0 && TN * (TK / 4) % kTcThreads == 0, "items must divide over the threads");
+    const bool vec_ok = (Kdim & 1) == 0;                   // 16-byte aligned rows
+    auto nonzero_block = [&](int k0) {
+        // zero-tile map of A (32 x 32 granularity): both 32-output halves of this tile against this K block
+        bool nz = false;
+#pragma unroll
+        for (int hh = 0; hh < TN / TILE; ++hh) {
+            const int ot = (o0 + hh * TILE) / TILE, kt = k0 / TILE;
+            if (o0 + hh * TILE < Odim) nz |= (MODE == 0 ? w.nz[ot * w.nzc + kt] : w.nz[kt * w.nzc + ot]) != 0;
+        }
+        return nz;
+    };
+    auto next_block = [&](int k0) {                        // first non-zero K block at or after k0 (Kdim if none)
+        while (k0 < Kdim && !nonzero_block(k0)) k0 += TK;
+        return k0;
+    };
+    // global memory -> registers (issued BEFORE waiting for the previous block's MMAs: the loads fly under them)
+    float4 xv[kXItems][2];
+    float2 bv[kBItems][4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < kXItems; ++u) {
+            const int it = tid + u * kTcThreads;
+            const int r = it % TM, c = it / TM;
+            const long long f = f0 + r;
+            const int k = k0 + c * 4;
+            xv[u][0] = xv[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < F && k + 3 < Kdim && vec_ok) {
+                const float4* src = reinterpret_cast<const float4*>(Xin + f * Kdim + k);
+                xv[u][0] = src[0];
+                xv[u][1] = src[1];
+            } else if (f < F) {
+                float2 e[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[q] = (k + q < Kdim) ? Xin[f * Kdim + k + q] : make_float2(0.f, 0.f);
+                xv[u][0] = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
+                xv[u][1] = make_float4(e[2].x, e[2].y, e[3].x, e[3].y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBItems; ++u) {
+            const int it = tid + u * kTcThreads;
+            const int r = it % TN, c = it / TN;
+            const int o = o0 + r;
+            const int k = k0 + c * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bv[u][q] = (o < Odim && k + q < Kdim) ? __ldg(Bm + (size_t)o * Kdim + k + q) : make_float2(0.f, 0.f);
+        }
+    };
+    // registers -> the eight hi / lo planes in the canonical layout
+    auto stage = [&]() {
+#pragma unroll
+        for (int u = 0; u < kXItems; ++u) {
+            const int it = tid + u * kTcThreads;
+            const int r = it % TM, c = it / TM;
+            const uint32_t off = (uint32_t)c * kXLbo + (uint32_t)(r >> 3) * kSbo + (uint32_t)(r & 7) * 16;
+            split_store(Xp[0], Xp[1], off, xv[u][0].x, xv[u][0].z, xv[u][1].x, xv[u][1].z);      // real parts of the 4 elements
+            split_store(Xp[2], Xp[3], off, xv[u][0].y, xv[u][0].w, xv[u][1].y, xv[u][1].w);      // imaginary parts
+        }
+#pragma unroll
+        for (int u = 0; u < kBItems; ++u) {
+            const int it = tid + u * kTcThreads;
+            const int r = it % TN, c = it / TN;
+            const uint32_t off = (uint32_t)c * kBLbo + (uint32_t)(r >> 3) * kSbo + (uint32_t)(r & 7) * 16;
+            split_store(Bp[0], Bp[1], off, bv[u][0].x, bv[u][1].x, bv[u][2].x, bv[u][3].x);
+            split_store(Bp[2], Bp[3], off, bv[u][0].y, bv[u][1].y, bv[u][2].y, bv[u][3].y);
+        }
+    };
+
+    uint32_t phase = 0;
+    int blocks_done = 0;
+    int k0 = next_block(0);
+    if (k0 < Kdim) fetch(k0);
+    while (k0 < Kdim) {
+        if (blocks_done > 0) {                             // the previous block's MMAs still read the planes
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        stage();
+        fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_re = tmem_base, d_im = tmem_base + TN;
+            const uint32_t id_pos = umma_idesc(false), id_neg = umma_idesc(true);
+            const uint32_t xa[4] = {smem_u32(Xp[0]), smem_u32(Xp[1]), smem_u32(Xp[2]), smem_u32(Xp[3])};   // Xr_hi, Xr_lo, Xi_hi, Xi_lo
+            const uint32_t ba[4] = {smem_u32(Bp[0]), smem_u32(Bp[1]), smem_u32(Bp[2]), smem_u32(Bp[3])};   // Br_hi, Br_lo, Bi_hi, Bi_lo
+#pragma unroll
+            for (int j = 0; j < TK / 8; ++j) {
+                const uint32_t xo = (uint32_t)(2 * j) * kXLbo, bo = (uint32_t)(2 * j) * kBLbo;
+                uint32_t acc = (blocks_done > 0 || j > 0) ? 1u : 0u;
+                // (x plane pair, b plane pair, accumulator, negate) for the four real products of the complex product
+                //   MODE 0: re = XrBr - XiBi, im = XrBi + XiBr;   MODE 1 (conj): re = XrBr + XiBi, im = XiBr - XrBi
+                const int xs[4] = {0, 2, 0, 2}, bs[4] = {0, 2, 2, 0};
+                const bool ng[4] = {false, MODE == 0, MODE == 1, false};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t dst = (q < 2) ? d_re : d_im;
+                    const uint32_t accq = (q == 0 || q == 2) ? acc : 1u;
+                    const uint32_t id = ng[q] ? id_neg : id_pos;
+                    // 3xTF32: hi*hi + hi*lo + lo*hi
+                    umma_tf32(dst, umma_desc(xa[xs[q]] + xo, kXLbo, kSbo), umma_desc(ba[bs[q]] + bo, kBLbo, kSbo), id, accq);
+                    umma_tf32(dst, umma_desc(xa[xs[q]] + xo, kXLbo, kSbo), umma_desc(ba[bs[q] + 1] + bo, kBLbo, kSbo), id, 1u);
+                    umma_tf32(dst, umma_desc(xa[xs[q] + 1] + xo, kXLbo, kSbo), umma_desc(ba[bs[q]] + bo, kBLbo, kSbo), id, 1u);
+                }
+            }
+            umma_commit(bar);                              // arrives when every MMA issued so far has completed
+        }
+        ++blocks_done;
+        k0 = next_block(k0 + TK);
+        if (k0 < Kdim) fetch(k0);                          // next block's loads fly under this block's MMAs
+    }
+    if (blocks_done > 0) {
+        mbar_wait(bar, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    // ---- epilogue.  TMEM -> registers (thread = one frame = one TMEM lane; warps 0-3 take outputs 0-31, warps 4-7 outputs
+    // 32-63) -> shared memory (the operand planes are free now), then the fused update with consecutive threads on
+    // consecutive outputs: every global access of a warp is one contiguous 256-byte run
+    float2* tile = reinterpret_cast<float2*>(smem);            // [TM][TN + 1] complex sums
+    {
+        const int fr = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        uint32_t vr[32], vi[32];
+        if (blocks_done > 0) {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+            tmem_ld32(taddr, vr);
+            tmem_ld32(taddr + TN, vi);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) vr[q] = vi[q] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) tile[fr * (TN + 1) + half * 32 + q] = make_float2(__uint_as_float(vr[q]), __uint_as_float(vi[q]));
+    }
+    __syncthreads();
+    for (int e = tid; e < TM * TN; e += kTcThreads) {
+        const int fr = e / TN, q = e % TN;
+        const long long f = f0 + fr;
+        const int o = o0 + q;
+        if (f >= F || o >= Odim || !act_s[fr]) continue;
+        const float2 s = tile[fr * (TN + 1) + q];
+        if (MODE == 0) {
+            const int blk = o / g.Nr;                                  // row block (Mr = Nr)
+            const float2 yv = y[f * g.n + o], zo = w.Z[f * g.n + o];
+            const float bb = w.b[f * g.Lout + blk];
+            const float2 zn = make_float2(yv.x - s.x + bb * zo.x, yv.y - s.y + bb * zo.y);   // scamp.py:48
+            w.Z[f * g.n + o] = zn;
+            w.Zs[f * g.n + o] = cdiv_real(zn, w.phi[f * g.Lout + blk]);                      // z / phi_use
+        } else {
+            const float tau = w.tau[f * g.Lin + o / g.Nt];                                   // column block (Mc = Nt)
+            const float2 xo = w.Xh[f * g.N + o];
+            w.Xmap[f * g.N + o] = make_float2(fmaf(tau, s.x, xo.x), fmaf(tau, s.y, xo.y));   // scamp.py:56
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+__global__ void transpose_c64_kernel(const float2* __restrict__ A, float2* __restrict__ At, int n, int N) {
+    __shared__ float2 tile[32][33];
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && j < N) ? A[(size_t)i * N + j] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, i = i0 + threadIdx.x;
+        if (i < n && j < N) At[(size_t)j * n + i] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace
+
+int scamp_tc_prepare(const float2* A, float2* At, int n, int N, cudaStream_t stream) {
+    transpose_c64_kernel<<<dim3((N + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, stream>>>(A, At, n, N);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "transpose_c64_kernel launch");
+}
+
+int scamp_tc_gemm(int mode, const ScampWs& w, const Geom& g, const float2* Bm, const float2* y, long long F, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal),
+                               "cudaFuncSetAttribute(scamp_tc<0>)"))
+            return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal),
+                               "cudaFuncSetAttribute(scamp_tc<1>)"))
+            return e;
+        attr_set = true;
+    }
+    const int Odim = mode == 0 ? g.n : g.N;
+    const dim3 grid((Odim + TN - 1) / TN, (unsigned)((F + TM - 1) / TM));
+    if (mode == 0)
+        scamp_tc_gemm_kernel<0><<<grid, kTcThreads, kSmemTotal, stream>>>(w, g, Bm, y, F);
+    else
+        scamp_tc_gemm_kernel<1><<<grid, kTcThreads, kSmemTotal, stream>>>(w, g, Bm, y, F);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "scamp_tc_gemm_kernel launch");
+}
+
+}  // namespace ampsm
