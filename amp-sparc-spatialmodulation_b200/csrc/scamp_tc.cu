@@ -22,17 +22,20 @@ namespace ampsm {
 namespace {
 
 constexpr int TM = 128;          // frames per tile (UMMA M)
-constexpr int TN = 64;           // outputs per tile (UMMA N)
+constexpr int kMaxKBlocks = 1024; // K blocks per tile the non-zero bitmap can hold (K <= 32768)
 constexpr int TK = 32;           // reduction elements per staged block (4 MMA K-steps of 8)
 constexpr int kTcThreads = 256;
-constexpr int kTmemCols = 128;   // D_re | D_im, 64 float32 columns each
+constexpr int kTmemCols = 128;   // D_re | D_im, up to 64 float32 columns each
 
 constexpr int kXPlane = TM * TK * 4;         // bytes of one frame-tile plane (16 KiB)
-constexpr int kBPlane = TN * TK * 4;         // bytes of one design-tile plane (8 KiB)
 constexpr int kSmemX = 0;                    // planes: Xr_hi, Xr_lo, Xi_hi, Xi_lo
-constexpr int kSmemB = 4 * kXPlane;          // planes: Br_hi, Br_lo, Bi_hi, Bi_lo
-constexpr int kSmemBar = kSmemB + 4 * kBPlane;
-constexpr int kSmemTotal = kSmemBar + 64;
+constexpr int kSmemB = 4 * kXPlane;          // planes: Br_hi, Br_lo, Bi_hi, Bi_lo (TN * TK * 4 bytes each)
+template <int TN>
+struct TcSmem {
+    static constexpr int bplane = TN * TK * 4;
+    static constexpr int bar = kSmemB + 4 * bplane;
+    static constexpr int total = bar + 64;
+};
 
 // K-major, no swizzle: 8 rows x 16 bytes core matrices; a plane is [K chunk of 4][row group of 8][8 rows][16 B]
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -43,8 +46,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;                                  // descriptor version 1 (Blackwell)
     return d;                                                // base offset 0, layout type SWIZZLE_NONE
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 64, optional negate-A
-__device__ __forceinline__ uint32_t umma_idesc(bool neg_a) {
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = TN, optional negate-A
+template <int TN>
+__device__ __forceinline__ constexpr uint32_t umma_idesc(bool neg_a) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -82,13 +86,15 @@ __device__ __forceinline__ void split_store(unsigned char* hi_plane, unsigned ch
 }
 
 // Bm: the B-source matrix [Odim][Kdim] complex64 row-major (A for MODE 0, A^T for MODE 1)
-template <int MODE>
+template <int MODE, int TN>
 __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w, Geom g, const float2* __restrict__ Bm,
                                                                       const float2* __restrict__ y, long long F) {
+    constexpr int kBPlane = TcSmem<TN>::bplane;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_base_s;
     __shared__ int act_s[TM];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    __shared__ uint32_t nzbits[kMaxKBlocks / 32];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TcSmem<TN>::bar);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long f0 = (long long)blockIdx.y * TM;
     const int o0 = blockIdx.x * TN;                       // first output of this tile
@@ -126,20 +132,33 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
     constexpr int kXItems = TM * (TK / 4) / kTcThreads;    // (row, K chunk) items of the frame tile per thread   (4)
     constexpr int kBItems = TN * (TK / 4) / kTcThreads;    // ... of the design tile                              (2)
     static_assert(TM * (TK / 4) % kTcThreads == 0 && TN * (TK / 4) % kTcThreads == 0, "items must divide over the threads");
+    static_assert(TN == 32 || TN == 64, "epilogue mapping");
     const bool vec_ok = (Kdim & 1) == 0;                   // 16-byte aligned rows
-    auto nonzero_block = [&](int k0) {
-        // zero-tile map of A (32 x 32 granularity): both 32-output halves of this tile against this K block
+    // which K blocks hold a non-zero 32 x 32 tile of A for this output tile: one K block per thread, a bitmap in shared memory
+    // (a serial scan would chain hundreds of dependent global loads in front of the first MMA)
+    const int nkb = (Kdim + TK - 1) / TK;
+    for (int kb0 = 0; kb0 < nkb; kb0 += kTcThreads) {
+        const int kb = kb0 + tid;
         bool nz = false;
+        if (kb < nkb) {
 #pragma unroll
-        for (int hh = 0; hh < TN / TILE; ++hh) {
-            const int ot = (o0 + hh * TILE) / TILE, kt = k0 / TILE;
-            if (o0 + hh * TILE < Odim) nz |= (MODE == 0 ? w.nz[ot * w.nzc + kt] : w.nz[kt * w.nzc + ot]) != 0;
+            for (int hh = 0; hh < (TN + TILE - 1) / TILE; ++hh) {
+                const int ot = (o0 + hh * TILE) / TILE;
+                if (o0 + hh * TILE < Odim) nz |= (MODE == 0 ? w.nz[ot * w.nzc + kb] : w.nz[kb * w.nzc + ot]) != 0;
+            }
         }
-        return nz;
-    };
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) nzbits[(kb0 >> 5) + warp] = m;
+    }
+    __syncthreads();
     auto next_block = [&](int k0) {                        // first non-zero K block at or after k0 (Kdim if none)
-        while (k0 < Kdim && !nonzero_block(k0)) k0 += TK;
-        return k0;
+        int kb = k0 / TK;
+        while (kb < nkb) {
+            const uint32_t wbits = nzbits[kb >> 5] >> (kb & 31);
+            if (wbits) return (kb + __ffs(wbits) - 1) * TK;
+            kb = (kb | 31) + 1;
+        }
+        return Kdim;
     };
     // global memory -> registers (issued BEFORE waiting for the previous block's MMAs: the loads fly under them)
     float4 xv[kXItems][2];
@@ -194,6 +213,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
         }
     };
 
+    // shared-memory descriptors of the eight planes (K step j adds 2 j LBO to the start-address field)
+    const uint32_t d_re = tmem_base, d_im = tmem_base + TN;
+    uint64_t xd[4], bd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        xd[q] = umma_desc(smem_u32(Xp[q]), kXLbo, kSbo);
+        bd[q] = umma_desc(smem_u32(Bp[q]), kBLbo, kSbo);
+    }
     uint32_t phase = 0;
     int blocks_done = 0;
     int k0 = next_block(0);
@@ -208,14 +235,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d_re = tmem_base, d_im = tmem_base + TN;
-            const uint32_t id_pos = umma_idesc(false), id_neg = umma_idesc(true);
-            const uint32_t xa[4] = {smem_u32(Xp[0]), smem_u32(Xp[1]), smem_u32(Xp[2]), smem_u32(Xp[3])};   // Xr_hi, Xr_lo, Xi_hi, Xi_lo
-            const uint32_t ba[4] = {smem_u32(Bp[0]), smem_u32(Bp[1]), smem_u32(Bp[2]), smem_u32(Bp[3])};   // Br_hi, Br_lo, Bi_hi, Bi_lo
 #pragma unroll
             for (int j = 0; j < TK / 8; ++j) {
-                const uint32_t xo = (uint32_t)(2 * j) * kXLbo, bo = (uint32_t)(2 * j) * kBLbo;
-                uint32_t acc = (blocks_done > 0 || j > 0) ? 1u : 0u;
+                const uint64_t xo = (uint64_t)((2 * j) * kXLbo >> 4), bo = (uint64_t)((2 * j) * kBLbo >> 4);   // start-address field
+                const uint32_t acc = (blocks_done > 0 || j > 0) ? 1u : 0u;
                 // (x plane pair, b plane pair, accumulator, negate) for the four real products of the complex product
                 //   MODE 0: re = XrBr - XiBi, im = XrBi + XiBr;   MODE 1 (conj): re = XrBr + XiBi, im = XiBr - XrBi
                 const int xs[4] = {0, 2, 0, 2}, bs[4] = {0, 2, 2, 0};
@@ -224,11 +247,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t dst = (q < 2) ? d_re : d_im;
                     const uint32_t accq = (q == 0 || q == 2) ? acc : 1u;
-                    const uint32_t id = ng[q] ? id_neg : id_pos;
+                    const uint32_t id = ng[q] ? umma_idesc<TN>(true) : umma_idesc<TN>(false);
                     // 3xTF32: hi*hi + hi*lo + lo*hi
-                    umma_tf32(dst, umma_desc(xa[xs[q]] + xo, kXLbo, kSbo), umma_desc(ba[bs[q]] + bo, kBLbo, kSbo), id, accq);
-                    umma_tf32(dst, umma_desc(xa[xs[q]] + xo, kXLbo, kSbo), umma_desc(ba[bs[q] + 1] + bo, kBLbo, kSbo), id, 1u);
-                    umma_tf32(dst, umma_desc(xa[xs[q] + 1] + xo, kXLbo, kSbo), umma_desc(ba[bs[q]] + bo, kBLbo, kSbo), id, 1u);
+                    umma_tf32(dst, xd[xs[q]] + xo, bd[bs[q]] + bo, id, accq);
+                    umma_tf32(dst, xd[xs[q]] + xo, bd[bs[q] + 1] + bo, id, 1u);
+                    umma_tf32(dst, xd[xs[q] + 1] + xo, bd[bs[q]] + bo, id, 1u);
                 }
             }
             umma_commit(bar);                              // arrives when every MMA issued so far has completed
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
     // 32-63) -> shared memory (the operand planes are free now), then the fused update with consecutive threads on
     // consecutive outputs: every global access of a warp is one contiguous 256-byte run
     float2* tile = reinterpret_cast<float2*>(smem);            // [TM][TN + 1] complex sums
-    {
+    if (warp < 4 * (TN / 32)) {
         const int fr = (warp & 3) * 32 + lane;
         const int half = warp >> 2;
         uint32_t vr[32], vi[32];
@@ -263,23 +286,49 @@ __global__ void __launch_bounds__(kTcThreads, 2) scamp_tc_gemm_kernel(ScampWs w,
         for (int q = 0; q < 32; ++q) tile[fr * (TN + 1) + half * 32 + q] = make_float2(__uint_as_float(vr[q]), __uint_as_float(vi[q]));
     }
     __syncthreads();
-    for (int e = tid; e < TM * TN; e += kTcThreads) {
-        const int fr = e / TN, q = e % TN;
-        const long long f = f0 + fr;
-        const int o = o0 + q;
-        if (f >= F || o >= Odim || !act_s[fr]) continue;
-        const float2 s = tile[fr * (TN + 1) + q];
-        if (MODE == 0) {
-            const int blk = o / g.Nr;                                  // row block (Mr = Nr)
-            const float2 yv = y[f * g.n + o], zo = w.Z[f * g.n + o];
-            const float bb = w.b[f * g.Lout + blk];
-            const float2 zn = make_float2(yv.x - s.x + bb * zo.x, yv.y - s.y + bb * zo.y);   // scamp.py:48
-            w.Z[f * g.n + o] = zn;
-            w.Zs[f * g.n + o] = cdiv_real(zn, w.phi[f * g.Lout + blk]);                      // z / phi_use
-        } else {
-            const float tau = w.tau[f * g.Lin + o / g.Nt];                                   // column block (Mc = Nt)
-            const float2 xo = w.Xh[f * g.N + o];
-            w.Xmap[f * g.N + o] = make_float2(fmaf(tau, s.x, xo.x), fmaf(tau, s.y, xo.y));   // scamp.py:56
+    // eight elements per thread at a time: all global loads of a batch are issued before the first use
+    constexpr int kEpiBatch = 8;
+    for (int e0 = tid; e0 < TM * TN; e0 += kTcThreads * kEpiBatch) {
+        float2 in0[kEpiBatch], in1[kEpiBatch];
+        float sc0[kEpiBatch], sc1[kEpiBatch];
+        bool ok[kEpiBatch];
+#pragma unroll
+        for (int u = 0; u < kEpiBatch; ++u) {
+            const int e = e0 + u * kTcThreads;
+            const int fr = e / TN, q = e % TN;
+            const long long f = f0 + fr;
+            const int o = o0 + q;
+            ok[u] = e < TM * TN && f < F && o < Odim && act_s[fr];
+            in0[u] = in1[u] = make_float2(0.f, 0.f);
+            sc0[u] = sc1[u] = 0.f;
+            if (ok[u]) {
+                if (MODE == 0) {
+                    const int blk = o / g.Nr;                          // row block (Mr = Nr)
+                    in0[u] = y[f * g.n + o];
+                    in1[u] = w.Z[f * g.n + o];
+                    sc0[u] = w.b[f * g.Lout + blk];
+                    sc1[u] = w.phi[f * g.Lout + blk];
+                } else {
+                    in0[u] = w.Xh[f * g.N + o];
+                    sc0[u] = w.tau[f * g.Lin + o / g.Nt];              // column block (Mc = Nt)
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEpiBatch; ++u) {
+            if (!ok[u]) continue;
+            const int e = e0 + u * kTcThreads;
+            const int fr = e / TN, q = e % TN;
+            const long long f = f0 + fr;
+            const int o = o0 + q;
+            const float2 s = tile[fr * (TN + 1) + q];
+            if (MODE == 0) {
+                const float2 zn = make_float2(in0[u].x - s.x + sc0[u] * in1[u].x, in0[u].y - s.y + sc0[u] * in1[u].y);   // scamp.py:48
+                w.Z[f * g.n + o] = zn;
+                w.Zs[f * g.n + o] = cdiv_real(zn, sc1[u]);                                                              // z / phi_use
+            } else {
+                w.Xmap[f * g.N + o] = make_float2(fmaf(sc0[u], s.x, in0[u].x), fmaf(sc0[u], s.y, in0[u].y));             // scamp.py:56
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -312,22 +361,30 @@ int scamp_tc_prepare(const float2* A, float2* At, int n, int N, cudaStream_t str
 }
 
 int scamp_tc_gemm(int mode, const ScampWs& w, const Geom& g, const float2* Bm, const float2* y, long long F, cudaStream_t stream) {
+    // the residual GEMM has few outputs (n): 32-wide tiles give it twice the CTAs (two per SM overlap staging and MMAs)
+    constexpr int TN0 = 32, TN1 = 64;
     static bool attr_set = false;
     if (!attr_set) {
-        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal),
+        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<0, TN0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN0>::total),
                                "cudaFuncSetAttribute(scamp_tc<0>)"))
             return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal),
+        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<1, TN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN1>::total),
                                "cudaFuncSetAttribute(scamp_tc<1>)"))
             return e;
         attr_set = true;
     }
+    const int Kdim = mode == 0 ? g.N : g.n;
+    if ((Kdim + TK - 1) / TK > kMaxKBlocks) {
+        set_error("SCAMP tensor-core GEMM: reduction length %d exceeds %d", Kdim, kMaxKBlocks * TK);
+        return AMPSM_ENOFIT;
+    }
     const int Odim = mode == 0 ? g.n : g.N;
-    const dim3 grid((Odim + TN - 1) / TN, (unsigned)((F + TM - 1) / TM));
+    const int TNm = mode == 0 ? TN0 : TN1;
+    const dim3 grid((Odim + TNm - 1) / TNm, (unsigned)((F + TM - 1) / TM));
     if (mode == 0)
-        scamp_tc_gemm_kernel<0><<<grid, kTcThreads, kSmemTotal, stream>>>(w, g, Bm, y, F);
+        scamp_tc_gemm_kernel<0, TN0><<<grid, kTcThreads, TcSmem<TN0>::total, stream>>>(w, g, Bm, y, F);
     else
-        scamp_tc_gemm_kernel<1><<<grid, kTcThreads, kSmemTotal, stream>>>(w, g, Bm, y, F);
+        scamp_tc_gemm_kernel<1, TN1><<<grid, kTcThreads, TcSmem<TN1>::total, stream>>>(w, g, Bm, y, F);
     count_launch();
     return check_cuda(cudaGetLastError(), "scamp_tc_gemm_kernel launch");
 }
