@@ -43,6 +43,7 @@ static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, S
     w.nzc = (g.N + TILE - 1) / TILE;
     w.nz = take((size_t)((g.n + TILE - 1) / TILE) * w.nzc);
     w.At = (float2*)take(scamp_use_tc(F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
+    w.notclose = (int*)take((size_t)F * 4);
     if (ws) *ws = w;
     return o;
 }
@@ -75,6 +76,7 @@ __global__ void scamp_init_kernel(ScampWs w, Geom g, const float2* __restrict__ 
     if (threadIdx.x == 0) {
         w.active[f] = 1;
         w.iters[f] = 0;
+        w.notclose[f] = 0;
     }
 }
 
@@ -271,6 +273,86 @@ __global__ void __launch_bounds__(256) scamp_denoise_kernel(ScampWs w, Geom g, D
     }
 }
 
+// ---- fast denoiser (float32 exp, per-section shift, no trajectory): one CTA per (column block, frame), one warp per section.
+// Mean only (scamp.py:61-68): exponents as float64 products, float32 ex2 of the shifted difference, everything in registers --
+// no scratch round trip through global memory (the generic kernel parks 3 N values per frame there).  psi of the block
+// (scamp.py:59) and its allclose test (scamp.py:105) are fused; a frame is retired by scamp_exit_kernel once none of its
+// blocks raised `notclose`.
+template <int MA>     // antennas per lane, M <= 32 MA
+__global__ void __launch_bounds__(256) scamp_denoise_fast_kernel(ScampWs w, Geom g, DevAlphabet al, long long F) {
+    __shared__ float wsum[8];
+    const long long f = blockIdx.y;
+    const int c = blockIdx.x;                                  // column block (Mc = Nt columns = Na sections)
+    if (f >= F || !w.active[f]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = g.M, K = al.K;
+    const float tau = w.tau[f * g.Lin + c];
+    const float rt = __frcp_rn(tau / 2.0f);                    // s / (tau / 2) as complex64 / real (scamp.py:63)
+    const float2* xmap = w.Xmap + f * g.N + (size_t)c * g.Nt;
+    float2* xh = w.Xh + f * g.N + (size_t)c * g.Nt;
+    float energy = 0.f;
+    for (int sec = warp; sec < g.Na; sec += 8) {
+        double qr[MA], qi[MA];
+        float lmax = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < MA; ++a) {
+            const int m = lane + 32 * a;
+            qr[a] = qi[a] = 0.0;
+            if (m < M) {
+                const float2 s = xmap[sec * M + m];
+                const float q_r = __fmul_rn(s.x, rt), q_i = __fmul_rn(s.y, rt);
+                qr[a] = (double)q_r;
+                qi[a] = (double)q_i;
+                for (int k = 0; k < K; ++k) lmax = fmaxf(lmax, fmaf(q_r, al.ref[k], q_i * al.imf[k]));
+            }
+        }
+        const double shift = (double)warp_max(lmax);           // a common shift of the section, nothing else
+        float s0 = 0.f, s1r[MA], s1i[MA];
+#pragma unroll
+        for (int a = 0; a < MA; ++a) {
+            s1r[a] = s1i[a] = 0.f;
+            if (lane + 32 * a < M) {
+                for (int k = 0; k < K; ++k) {
+                    const double x = fma(qr[a], al.re[k], qi[a] * al.im[k]);
+                    const float e = exp2f((float)(x - shift) * 1.4426950408889634f);
+                    s0 += e;
+                    s1r[a] = fmaf(al.ref[k], e, s1r[a]);
+                    s1i[a] = fmaf(al.imf[k], e, s1i[a]);
+                }
+            }
+        }
+        const float rz = 1.0f / warp_sum(s0);
+#pragma unroll
+        for (int a = 0; a < MA; ++a) {
+            const int m = lane + 32 * a;
+            if (m < M) {
+                const float2 v = make_float2(s1r[a] * rz, s1i[a] * rz);
+                xh[sec * M + m] = v;
+                energy = fmaf(v.x, v.x, fmaf(v.y, v.y, energy));
+            }
+        }
+    }
+    energy = warp_sum(energy);
+    if (lane == 0) wsum[warp] = energy;
+    __syncthreads();
+    if (tid == 0) {
+        float acc = 0.f;
+        for (int i = 0; i < 8; ++i) acc += wsum[i];
+        const float pn = 1.0f - acc / (float)g.Na;             // scamp.py:59
+        const float po = w.psi[f * g.Lin + c];
+        if (!(fabsf(pn - po) <= __fadd_rn(kAtol, fabsf(__fmul_rn(kRtol, po))))) w.notclose[f] = 1;
+        w.psi[f * g.Lin + c] = pn;
+    }
+}
+
+__global__ void scamp_exit_kernel(ScampWs w, Geom g, int t, long long F) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F || !w.active[f]) return;
+    w.iters[f] = t + 1;
+    if (g.early_exit && !w.notclose[f]) w.active[f] = 0;       // scamp.py:105
+    w.notclose[f] = 0;
+}
+
 __global__ void scamp_finish_kernel(ScampWs w, Geom g, float2* xmmse, float* psi, int* iters, float* traj, long long F) {
     const long long f = blockIdx.x;
     if (f >= F) return;
@@ -320,7 +402,16 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
             scamp_gemm_kernel<0><<<grid_res, 256, 0, stream>>>(w, g, a.A, a.y, F);
             scamp_gemm_kernel<1><<<grid_est, 256, 0, stream>>>(w, g, a.A, a.y, F);
         }
-        if (exp64)
+        // float32-exp mode without trajectory: fused register-resident denoiser (one warp per section) + exit kernel
+        const bool fast_dn = !exp64 && g.shift_mode == 0 && !a.traj && g.M <= 128 && g.Nt == g.Na * g.M && F <= 65535 && !getenv("AMPSM_SCAMP_GENERIC_DENOISER");
+        if (fast_dn) {
+            const dim3 gd((unsigned)g.Lin, (unsigned)F);
+            if (g.M <= 32) scamp_denoise_fast_kernel<1><<<gd, 256, 0, stream>>>(w, g, a.al, F);
+            else if (g.M <= 64) scamp_denoise_fast_kernel<2><<<gd, 256, 0, stream>>>(w, g, a.al, F);
+            else scamp_denoise_fast_kernel<4><<<gd, 256, 0, stream>>>(w, g, a.al, F);
+            scamp_exit_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(w, g, t, F);
+            count_launch();
+        } else if (exp64)
             scamp_denoise_kernel<true><<<(unsigned)F, 256, 0, stream>>>(w, g, a.al, a.io.x_true, a.traj, t, F);
         else
             scamp_denoise_kernel<false><<<(unsigned)F, 256, 0, stream>>>(w, g, a.al, a.io.x_true, a.traj, t, F);

@@ -21,6 +21,7 @@ struct ScampWs {
     unsigned char* nz;  // [ceil(n/TILE)][ceil(N/TILE)]
     int nzc;         // columns of nz
     float2* At;      // [N][n] transpose of A (tensor-core path only)
+    int* notclose;   // [F] set by the fast denoiser when a column block of the frame failed the exit test
 };
 
 // tensor-core GEMMs (scamp_tc.cu): mode 0 = residual with Bm = A, mode 1 = estimate with Bm = A^T

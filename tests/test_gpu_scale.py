@@ -355,8 +355,9 @@ def test_monte_carlo_sweep_exports_reference_schema(tmp_path):
 
 @pytest.mark.parametrize("shape", [(64, 2, 8, 8, 3), (128, 4, 16, 6, 2)])
 def test_scamp_tensor_core_gemms_match_simt_path(shape, monkeypatch):
-    """Batches of >= 128 frames run both SCAMP GEMMs on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, scamp_tc.cu);
-    the SIMT float32 tiles (AMPSM_SCAMP_SIMT=1) are the comparison: same exits, same decisions, estimates to float32
+    """Batches of >= 128 frames run both SCAMP GEMMs on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, scamp_tc.cu) and
+    the fused one-warp-per-section denoiser; the SIMT float32 tiles with the generic denoiser (AMPSM_SCAMP_SIMT=1,
+    AMPSM_SCAMP_GENERIC_DENOISER=1 -- the path the golden fixtures pin) are the comparison: same exits, same decisions, estimates to float32
     rounding.  Ragged on purpose: frames not a multiple of 128, outputs not a multiple of 64."""
     Nt, Na, Nr, Lin, Lh = shape
     F = 300
@@ -373,11 +374,13 @@ def test_scamp_tensor_core_gemms_match_simt_path(shape, monkeypatch):
     a = pkg.SCAMP(cfg, outputs=True).detect(W, A, y, snr, x, sym, idx)
     ca = a.counters_dict()
     monkeypatch.setenv("AMPSM_SCAMP_SIMT", "1")
+    monkeypatch.setenv("AMPSM_SCAMP_GENERIC_DENOISER", "1")      # the reference path: SIMT GEMM tiles + the generic denoiser
     b = pkg.SCAMP(cfg, outputs=True).detect(W, A, y, snr, x, sym, idx)
     cb = b.counters_dict()
+    monkeypatch.delenv("AMPSM_SCAMP_GENERIC_DENOISER")
     assert ca["frames"] == cb["frames"] == F and ca["nan_frames"] == 0
     ia, ib = a.iters.cpu().numpy(), b.iters.cpu().numpy()
-    assert (np.abs(ia - ib) <= 1).mean() > 0.99 and (ia == ib).mean() > 0.9
+    assert (np.abs(ia - ib) <= 1).mean() > 0.99 and (ia == ib).mean() > 0.75      # psi = 1 - (~1): the exit test sits at float32 resolution
     # frames that met the exit test at the same iteration must agree to rounding; frames that run out of iterations without
     # converging amplify any rounding difference chaotically and are only counted
     conv = torch.as_tensor((ia == ib) & (ia < 20), device=DEV)
