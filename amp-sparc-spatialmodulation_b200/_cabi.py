@@ -108,8 +108,6 @@ def make_problem(config, frames, *, R=0, early_exit=True, shift='section', exp='
                  max_iters=None):
     """Geometry + switches for one call of `frames` frames (index-bit truncation as loss.py:20 with B=frames)."""
     import math
-    if config.mode == 'random':
-        raise AmpsmError("generator_mode='random' is outside the sectioned hot path (SURVEY.md section 8f)")
     p = Problem()
     p.n, p.N, p.R = config.Nr * config.Lout, config.Nt * config.Lin, R
     p.Nt, p.Na, p.Nr, p.Lin, p.Lout = config.Nt, config.Na, config.Nr, config.Lin, config.Lout
@@ -119,7 +117,7 @@ def make_problem(config, frames, *, R=0, early_exit=True, shift='section', exp='
     p.exp_f64 = {'f32': 0, 'f64': 1}[exp]
     if p.shift_mode == 1:
         p.exp_f64 = 1
-    p.decision = 0 if config.mode == 'sparc' else 1
+    p.decision = {'sparc': 0, 'segmented': 1, 'random': 2}[config.mode]      # decision rule and, for 'random', the i.i.d. prior
     count = config.Lin * max(int(frames), 1) * config.Na
     p.index_bits_kept = int(math.ceil(math.log2(count))) if count > 0 else 0
     p.kernel = {'auto': 0, 'generic': 1, 'fast': 2, 'pair': 3}[kernel]

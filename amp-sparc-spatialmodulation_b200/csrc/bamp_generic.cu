@@ -178,9 +178,13 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
             }
             __syncthreads();
             // ---- denoiser (bamp.py:66-77): tau = cov/2
-            double gshift = 0.0;
-            if (EXP64 && g.shift_mode == 1) gshift = block_absmax_exponent(g, al, xmap_s, cov_s, 0.f, true, red);
-            block_denoise<EXP64>(g, al, xmap_s, cov_s, 0.f, true, gshift, xhn_s, varn_s, scr);
+            if (g.decision == 2) {                                   // generator_mode 'random' (bamp.py:46): i.i.d. prior
+                block_denoise_iid(g, al, xmap_s, cov_s, xhn_s, varn_s);
+            } else {
+                double gshift = 0.0;
+                if (EXP64 && g.shift_mode == 1) gshift = block_absmax_exponent(g, al, xmap_s, cov_s, 0.f, true, red);
+                block_denoise<EXP64>(g, al, xmap_s, cov_s, 0.f, true, gshift, xhn_s, varn_s, scr);
+            }
             __syncthreads();
             // ---- exit test on var (bamp.py:140) and state update
             bool close = true;

@@ -165,6 +165,35 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
     }
 }
 
+// ``random`` mode (bamp.py:79-101): i.i.d. prior P0 delta_0 + Ps sum_k delta_{s_k}; G(s) = exp(-|r - s|^2 / cov) in float64 with
+// no shift, an exactly-zero normaliser replaced by 1e-9.  Ps / P0 are float32 tensors in the reference (bamp.py:40).
+__device__ inline void block_denoise_iid(const Geom& g, const DevAlphabet& al, const float2* r, const float* cov, float2* xh_out,
+                                         float* var_out) {
+    const double sparsity = (double)g.Na / (double)g.Nt;
+    const double Ps = (double)(float)(sparsity / al.K), P0 = (double)(float)(1.0 - sparsity);
+    for (int j = threadIdx.x; j < g.N; j += blockDim.x) {
+        const double rr = (double)r[j].x, ri = (double)r[j].y, c = (double)cov[j];
+        const double a0 = hypot(rr, ri);
+        double norm = P0 * exp(-(a0 * a0) / c);
+        double s1r = 0.0, s1i = 0.0, s2 = 0.0, gs = 0.0;
+        for (int k = 0; k < al.K; ++k) {
+            const double d = hypot(rr - al.re[k], ri - al.im[k]);
+            const double G = exp(-(d * d) / c);
+            const double m = hypot(al.re[k], al.im[k]);
+            gs += G;
+            s1r += al.re[k] * G;
+            s1i += al.im[k] * G;
+            s2 += m * m * G;
+        }
+        norm += Ps * gs;
+        if (norm == 0.0) norm = 1e-9;                                  // regularize_zero (bamp.py:99-101)
+        const double er = Ps * s1r / norm, ei = Ps * s1i / norm;
+        const double ea = hypot(er, ei);
+        xh_out[j] = make_float2((float)er, (float)ei);
+        var_out[j] = (float)(Ps * s2 / norm - ea * ea);
+    }
+}
+
 // ---- hard decision ------------------------------------------------------------------------------------------
 struct Pick {
     double v;
@@ -268,6 +297,90 @@ __device__ inline void block_loss(const Geom& g, const DevAlphabet& al, long lon
     const float2* xt = io.x_true + frame * (long long)g.N;
     double sq_all = 0.0, sq_f = 0.0, sq_m = 0.0, sq_l = 0.0;
     unsigned long long idx_err = 0, sym_err = 0, ibit = 0, sbit = 0;
+    if (g.decision == 2) {
+        // ---- 'random' mode (loss.py:252-280): per time slot the Na entries of largest |x| (np.abs(x).argsort()[-Na:],
+        // NaN sorts last = largest), each decided to its nearest symbol (first minimum, strict '<', complex128 distance);
+        // decided positions in ascending order pair with the true ones (loss.py:278, 165-172).  One warp per slot.
+        for (int slot = warp; slot < g.Lin; slot += nwarps) {
+            const int base = slot * g.Nt;
+            unsigned taken = 0u;                                     // bit i: entry lane + 32 i already picked
+            int my_pos = -1, my_k = -1;                              // lane a < Na holds the a-th pick
+            for (int a = 0; a < g.Na; ++a) {
+                float bv = -1.f;
+                int bi = -1;
+                for (int i = 0; lane + 32 * i < g.Nt; ++i) {
+                    if (taken & (1u << i)) continue;
+                    const int j = lane + 32 * i;
+                    const CT x = xmap[base + j];
+                    float v = hypotf((float)x.x, (float)x.y);
+                    if (v != v) v = INFINITY;                        // NaN sorts last
+                    if (v > bv || (v == bv && j > bi)) { bv = v; bi = j; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+                }
+                if (bi >= 0 && (bi & 31) == lane) taken |= 1u << (bi >> 5);
+                if (lane == a) my_pos = bi;
+            }
+            if (lane < g.Na && my_pos >= 0) {
+                const CT x = xmap[base + my_pos];
+                double d = INFINITY;
+                for (int k = 0; k < al.K; ++k) {
+                    const double ds = hypot((double)x.x - al.re[k], (double)x.y - al.im[k]);
+                    if (ds < d) { d = ds; my_k = k; }
+                }
+                if (my_k < 0) my_pos = -1;                           // no finite distance: the entry stays empty
+            }
+            // ascending order of the decided positions: rank by counting (empty picks go last)
+            const int key = (lane < g.Na && my_pos >= 0) ? my_pos : 0x7fffffff;
+            int rank = 0;
+            for (int o = 0; o < g.Na; ++o) {
+                const int other = __shfl_sync(0xffffffffu, key, o);
+                rank += (other < key) || (other == key && o < lane);
+            }
+            if (lane < g.Na && my_pos >= 0) {
+                // (the reference pairs the sorted decided list with the sorted true list over the WHOLE call; a slot with
+                // fewer than Na decisions -- only possible with NaN estimates -- would misalign its arrays and numpy raises;
+                // here such a slot is paired position by position within the slot)
+                const long long ih = (g.frame_base + frame) * (long long)g.N + base + my_pos;
+                const long long it = io.idx_true[(frame * g.Lin + slot) * g.Na + rank];
+                const long long sh = al.gray[my_k], st = io.sym_true[(frame * g.Lin + slot) * g.Na + rank];
+                idx_err += (ih != it);
+                sym_err += (sh != st);
+                const unsigned long long imask = g.index_bits_kept >= 64 ? ~0ull : ((1ull << g.index_bits_kept) - 1ull);
+                ibit += __popcll((unsigned long long)(ih ^ it) & imask);
+                sbit += __popcll((unsigned long long)(sh ^ st) & ((1ull << al.sbits) - 1ull));
+            }
+            // value compare of the decided slot against x, squared error of the MMSE estimate (all lanes run the shuffles)
+            bool wrong = false, nan_seen = false;
+            for (int j0 = 0; j0 < g.Nt; j0 += 32) {
+                const int j = j0 + lane;
+                float2 h = make_float2(0.f, 0.f);
+                for (int o = 0; o < g.Na; ++o) {
+                    const int pos = __shfl_sync(0xffffffffu, my_pos, o), kk = __shfl_sync(0xffffffffu, my_k, o);
+                    if (pos == j && kk >= 0) h = make_float2((float)al.re[kk], (float)al.im[kk]);
+                }
+                if (j < g.Nt) {
+                    const float2 t = xt[base + j];
+                    wrong |= (h.x != t.x) || (h.y != t.y);
+                    const float2 e = xmmse[base + j];
+                    const float dr = e.x - t.x, di = e.y - t.y;
+                    const double se = (double)dr * dr + (double)di * di;
+                    sq_all += se;
+                    if (slot == 0) sq_f += se;
+                    if (slot == mid) sq_m += se;
+                    if (slot == g.Lin - 1) sq_l += se;
+                    const CT xm = xmap[base + j];
+                    nan_seen |= (xm.x != xm.x) || (xm.y != xm.y);
+                }
+            }
+            if (__any_sync(0xffffffffu, wrong) && lane == 0) flags[1 + slot] = 1;
+            if (__any_sync(0xffffffffu, nan_seen) && lane == 0) flags[0] = 1;
+        }
+    } else
     for (int sec = warp; sec < g.L; sec += nwarps) {
         const int base = sec * g.M;
         const int slot = sec / g.Na;
@@ -306,6 +419,15 @@ __device__ inline void block_loss(const Geom& g, const DevAlphabet& al, long lon
     sq_f = warp_sum(sq_f);
     sq_m = warp_sum(sq_m);
     sq_l = warp_sum(sq_l);
+    if (g.decision == 2) {          // random mode books its label counters on lanes 0..Na-1
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            idx_err += __shfl_xor_sync(0xffffffffu, idx_err, o);
+            sym_err += __shfl_xor_sync(0xffffffffu, sym_err, o);
+            ibit += __shfl_xor_sync(0xffffffffu, ibit, o);
+            sbit += __shfl_xor_sync(0xffffffffu, sbit, o);
+        }
+    }
     if (lane == 0) {
         atomicAdd(&bc->sq[0], sq_all);
         atomicAdd(&bc->sq[1], sq_f);

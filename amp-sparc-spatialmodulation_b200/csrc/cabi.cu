@@ -35,7 +35,10 @@ static int make_geom(const ampsm_problem* p, const ampsm_alphabet* a, Geom* g, D
     if (p->n < 1 || p->N < 1 || p->Nt < 1 || p->Na < 1 || p->Nr < 1 || p->Lin < 1 || p->Lout < 1 || p->max_iters < 1) {
         set_error("non-positive dimension in ampsm_problem"); return AMPSM_EINVAL;
     }
-    if (p->Nt % p->Na != 0) { set_error("Na=%d must divide Nt=%d (sectioned modes)", p->Na, p->Nt); return AMPSM_EINVAL; }
+    const bool iid = p->decision == 2;          // generator_mode 'random': i.i.d. prior, Na active entries anywhere in a time slot
+    if (p->decision < 0 || p->decision > 2) { set_error("decision=%d outside 0..2", p->decision); return AMPSM_EINVAL; }
+    if (!iid && p->Nt % p->Na != 0) { set_error("Na=%d must divide Nt=%d (sectioned modes)", p->Na, p->Nt); return AMPSM_EINVAL; }
+    if (iid && (p->Na > p->Nt || p->Na > 32 || p->Nt > 1024)) { set_error("random mode needs Na <= min(Nt, 32) and Nt <= 1024"); return AMPSM_EINVAL; }
     if (p->N != p->Nt * p->Lin || p->n != p->Nr * p->Lout) {
         set_error("N must equal Nt*Lin and n must equal Nr*Lout (got N=%d n=%d)", p->N, p->n); return AMPSM_EINVAL;
     }
@@ -44,7 +47,8 @@ static int make_geom(const ampsm_problem* p, const ampsm_alphabet* a, Geom* g, D
     if (p->index_bits_kept < 0 || p->index_bits_kept > 64) { set_error("index_bits_kept outside 0..64"); return AMPSM_EINVAL; }
     g->n = p->n; g->N = p->N; g->R = p->R;
     g->Nt = p->Nt; g->Na = p->Na; g->Nr = p->Nr; g->Lin = p->Lin; g->Lout = p->Lout;
-    g->M = p->Nt / p->Na; g->L = p->Na * p->Lin;
+    g->M = iid ? p->Nt : p->Nt / p->Na;          // random mode: a 'section' is one time slot of Nt entries holding Na labels
+    g->L = iid ? p->Lin : p->Na * p->Lin;
     g->max_iters = p->max_iters; g->early_exit = p->early_exit; g->shift_mode = p->shift_mode;
     g->decision = p->decision; g->index_bits_kept = p->index_bits_kept; g->frame_base = p->frame_base;
     al->K = a->K;
@@ -231,13 +235,14 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     if (frames < 0 || (frames > 0 && (!H || !y))) { set_error("BAMP: H / y is NULL or frames < 0"); return AMPSM_EINVAL; }
     if (H_frame_stride != 0 && H_frame_stride < (int64_t)p->n * p->N) { set_error("BAMP: H_frame_stride smaller than n*N"); return AMPSM_EINVAL; }
     if (frames == 0) return 0;
+    if (p->decision == 2 && p->kernel > 1) { set_error("BAMP random mode runs the generic kernel only"); return AMPSM_ENOFIT; }
     k.H = (const float2*)H; k.H_stride = H_frame_stride; k.y = (const float2*)y;
     k.sigma2 = (float)sigma2; k.sigma2_pf = sigma2_per_frame;
     k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
     k.io.counters = (unsigned long long*)counters;
     k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0) {
+    if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0 && p->decision != 2) {
         if (p->kernel == 3 || (p->kernel == 0 && getenv("AMPSM_PAIR"))) {   // measured slower than the one-warp kernel: opt-in
             const int rc = launch_bamp_pair(k, st);
             if (rc != AMPSM_ENOFIT || p->kernel == 3) return rc;
@@ -293,6 +298,7 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
                       const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* var, int32_t* iters,
                       float* traj, uint64_t* counters, void* stream) {
     VampArgs k{};
+    if (p && p->decision == 2) { set_error("VAMP has no working random mode in the reference (vamp.py:84 unpacks two values from a denoiser that returns one)"); return AMPSM_EINVAL; }
     if (int e = make_geom(p, a, &k.g, &k.al, true)) return e;
     if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
     if (frames < 0 || (frames > 0 && (!U || !s || !Vh || !y))) { set_error("VAMP: U / s / Vh / y is NULL or frames < 0"); return AMPSM_EINVAL; }
@@ -403,6 +409,7 @@ int ampsm_scamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t 
                        const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* psi, int32_t* iters,
                        float* traj, uint64_t* counters, void* workspace, void* stream) {
     ScampArgs k{};
+    if (p && p->decision == 2) { set_error("SCAMP is defined for sectioned messages only (scamp.py:61-68)"); return AMPSM_EINVAL; }
     if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
     if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
     if (frames < 0 || (frames > 0 && (!W || !A || !y))) { set_error("SCAMP: W / A / y is NULL or frames < 0"); return AMPSM_EINVAL; }

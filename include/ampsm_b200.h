@@ -55,7 +55,9 @@ typedef struct {
     int32_t shift_mode;      /* 0: per-section max shift (finite everywhere);
                                 1: frame-global max|x| in float64 as bamp.py:70 (NaN-faithful, slower)     */
     int32_t exp_f64;         /* 1: denoiser exponents/exp in float64 as the reference; 0: float32 exp      */
-    int32_t decision;        /* 0: MAP decision (loss.py:282-302, mode 'sparc'); 1: segmented (223-250)    */
+    int32_t decision;        /* 0: MAP decision (loss.py:282-302, mode 'sparc'); 1: segmented (223-250);
+                                2: generator_mode 'random' -- i.i.d.-prior denoiser (bamp.py:79-97) and the top-Na
+                                decision (loss.py:252-280); labels are then Lin*Na per frame; BAMP generic only */
     int32_t index_bits_kept; /* low bits of the index XOR that Loss.de2bi keeps (loss.py:20,168)           */
     int32_t kernel;          /* 0: auto, 1: generic shared-memory kernel, 2: register-resident kernel, one warp
                                 per frame, 3: register-resident kernel, two warps per frame (64 x 32 shapes)   */

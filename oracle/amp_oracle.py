@@ -7,6 +7,7 @@ do (they call the CUDA library and fail loudly when it is missing).
 What it follows (reference file:line, all under /root/reference):
   * ``sm_denoiser``   -> bamp.py:66-77 (mean + variance, tau halved), scamp.py:61-68 (mean only, tau halved),
                          vamp.py:96-119 (scalar tau, NOT halved)
+  * ``iid_denoiser``  -> bamp.py:79-101 (``random`` mode: i.i.d. prior P0 delta_0 + Ps sum_k delta_{s_k}, no shift)
   * ``bamp_detect``   -> bamp.py:12-25 (state), 59-64 (one iteration), 116-143 (loop + allclose exit)
   * ``scamp_detect``  -> scamp.py:8-25, 43-59, 77-108
   * ``vamp_detect``   -> vamp.py:12-28, 66-94, 159-191
@@ -80,17 +81,38 @@ def sm_denoiser(s, tau, symbols, L, M, halve_tau, shift='reference', want_var=Tr
     return out_mean, var.reshape(F, L * M).astype(F32)
 
 
+def iid_denoiser(r, cov, symbols, sparsity):
+    """``BAMPLayer.random_denoiser`` (bamp.py:79-101): posterior mean / variance under the i.i.d. prior
+    ``P0 delta_0 + Ps sum_k delta_{s_k}`` with ``G(s) = exp(-|r - s|^2 / cov)`` evaluated in float64 WITHOUT any shift
+    (an exact-zero normaliser is replaced by 1e-9, ``regularize_zero``).  ``Ps`` / ``P0`` are float32 tensors in the
+    reference (bamp.py:40 <- config.py:86-114: Ps = sparsity / K for modulated alphabets, K = 1 for OOK)."""
+    sym = np.asarray(symbols, dtype=np.complex128)
+    Ps = np.float64(F32(sparsity / len(sym)))
+    P0 = np.float64(F32(1.0 - sparsity))
+    r128 = np.ascontiguousarray(r, dtype=C64).astype(np.complex128)[..., None]
+    cov64 = np.asarray(cov, dtype=F32).astype(np.float64)[..., None]
+    with np.errstate(all='ignore'):
+        G0 = np.exp(-np.abs(r128) ** 2 / cov64)                              # bamp.py:91-92
+        Gs = np.exp(-np.abs(r128 - sym) ** 2 / cov64)
+        norm = P0 * G0 + Ps * Gs.sum(axis=-1, keepdims=True)                 # bamp.py:93
+        norm = np.where(norm == 0.0, 1e-9, norm)                             # regularize_zero (bamp.py:99-101)
+        ex = Ps * (sym * Gs).sum(axis=-1, keepdims=True) / norm              # bamp.py:94
+        var = Ps * (np.abs(sym) ** 2 * Gs).sum(axis=-1, keepdims=True) / norm - np.abs(ex) ** 2   # bamp.py:95
+    return ex[..., 0].astype(C64), var[..., 0].astype(F32)
+
+
 def _mse(xmmse, x_true):
     d = xmmse - x_true
     return (d.real.astype(np.float64) ** 2 + d.imag.astype(np.float64) ** 2).mean(axis=1)
 
 
-def bamp_detect(H, y, sigma2, symbols, L, M, max_iters, early_exit=True, shift='reference', x_true=None):
+def bamp_detect(H, y, sigma2, symbols, L, M, max_iters, early_exit=True, shift='reference', x_true=None, iid_sparsity=None):
     """BAMP over F frames.  H: (n,N) shared or (F,n,N) per frame, complex64; y: (F,n) complex64.
 
     Returns dict(xmap, xmmse, var, iters, traj) -- ``traj`` holds per-iteration per-frame
     ``tau`` (mean effective noise variance), ``var`` (mean posterior variance) and, when ``x_true`` is given,
-    ``mse``; entries of frames that already exited repeat their last value.
+    ``mse``; entries of frames that already exited repeat their last value.  ``iid_sparsity`` (= Na/Nt) selects the
+    ``random``-mode denoiser (bamp.py:46,79-97) instead of the sectioned one.
     """
     y = np.ascontiguousarray(y, dtype=C64)
     F, n = y.shape
@@ -129,7 +151,10 @@ def bamp_detect(H, y, sigma2, symbols, L, M, max_iters, early_exit=True, shift='
             cov_a = (F32(1) / mv(Pt, (F32(1) / u_new).astype(F32), a)).astype(F32)   # bamp.py:62
             g = ((y[a] - z_new) / u_new).astype(C64)
             xmap_a = (xmmse[a] + cov_a * mv(Hh, g, a)).astype(C64)     # bamp.py:63
-            xm, vr = sm_denoiser(xmap_a, cov_a, symbols, L, M, True, shift)   # bamp.py:64
+            if iid_sparsity is None:
+                xm, vr = sm_denoiser(xmap_a, cov_a, symbols, L, M, True, shift)   # bamp.py:64
+            else:
+                xm, vr = iid_denoiser(xmap_a, cov_a, symbols, iid_sparsity)
         done = _allclose_rows(vr, var[a])
         z[a], u[a], xmap[a], cov[a], xmmse[a], var[a] = z_new, u_new, xmap_a, cov_a, xm, vr
         iters[a] = t + 1

@@ -4,6 +4,8 @@ Vectorised numpy restatement of the reference ``Loss`` (/root/reference/loss.py)
   * ``map_decision``        -> loss.py:282-302 (mode 'sparc'; first maximum of Re(x conj(sym)) in complex128,
                                row-major over (antenna, symbol); NaN wins as in np.argmax)
   * ``segmented_decision``  -> loss.py:223-250 (strongest antenna by |x|, then nearest symbol, first minimum)
+  * ``random_decision``     -> loss.py:252-280 (mode 'random': the Na strongest entries of every time slot, each
+                               mapped to its nearest symbol)
   * ``error_counters``      -> the integer counts / squared-error sums behind loss.py:105-179
   * ``rates_from_counters`` -> the 14 rates of loss.py:27 formed exactly as loss.py:116-178 forms them
 
@@ -53,6 +55,32 @@ def segmented_decision(xmap, symbols, gray, M):
     return xhat, ant, k
 
 
+def random_decision(xmap, symbols, gray, Nt, Na):
+    """loss.py:252-280 per time slot of Nt entries: positions of the Na largest |x| (``argsort()[-Na:]``), each decided
+    to the nearest symbol (first minimum of the complex128 distance).  Returns (xhat (S, Nt) complex64, xgray (S, Nt))."""
+    xs = np.ascontiguousarray(xmap, dtype=np.complex64).reshape(-1, Nt)
+    sym = np.asarray(symbols, dtype=np.complex128)
+    gray = np.asarray(gray, dtype=np.int64)
+    xhat = np.zeros_like(xs)
+    xgray = np.zeros(xs.shape, dtype=np.int64)
+    top = np.abs(xs).argsort(axis=1)[:, -Na:]                          # loss.py:266
+    rows = np.arange(xs.shape[0])[:, None]
+    picked = xs[rows, top]                                            # (S, Na) complex64
+    with np.errstate(all='ignore'):
+        dist = np.abs(picked[:, :, None].astype(np.complex128) - sym[None, None, :])
+    k = np.zeros(top.shape, dtype=np.int64)
+    best = np.full(top.shape, np.inf)
+    for i in range(sym.shape[0]):                                     # strict '<' keeps the first minimum (loss.py:271)
+        better = dist[:, :, i] < best
+        k = np.where(better, i, k)
+        best = np.where(better, dist[:, :, i], best)
+    won = best < np.inf
+    r2 = np.broadcast_to(rows, top.shape)
+    xhat[r2[won], top[won]] = sym[k[won]]
+    xgray[r2[won], top[won]] = gray[k[won]]
+    return xhat, xgray
+
+
 def error_counters(xmap, xmmse, x, sym_true, idx_true, symbols, gray, dims, iters=None, decision='sparc',
                    index_bits_kept=None):
     """Counts behind the 14 metrics for a call holding F frames (loss.py:67-179).
@@ -66,10 +94,13 @@ def error_counters(xmap, xmmse, x, sym_true, idx_true, symbols, gray, dims, iter
     xmmse = np.asarray(xmmse, dtype=np.complex64).reshape(-1, Lin, Nt)
     x = np.asarray(x, dtype=np.complex64).reshape(-1, Lin, Nt)
     F = x.shape[0]
-    decide = map_decision if decision == 'sparc' else segmented_decision
-    xhat_sec, ant, k = decide(xmap, symbols, gray, M)
-    xhat = xhat_sec.reshape(-1, Lin, Nt)
     gray = np.asarray(gray, dtype=np.int64)
+    if decision == 'random':
+        xhat_sec, xgray_r = random_decision(xmap, symbols, gray, Nt, Na)
+    else:
+        decide = map_decision if decision == 'sparc' else segmented_decision
+        xhat_sec, ant, k = decide(xmap, symbols, gray, M)
+    xhat = xhat_sec.reshape(-1, Lin, Nt)
 
     d = (xmmse - x)
     se = d.real.astype(np.float64) ** 2 + d.imag.astype(np.float64) ** 2          # (F, Lin, Nt)
@@ -79,8 +110,11 @@ def error_counters(xmap, xmmse, x, sym_true, idx_true, symbols, gray, dims, iter
 
     flat = xhat_sec.ravel()
     idx_hat = np.sort(flat.nonzero()[0])                              # loss.py:300
-    xgray = np.zeros(xhat_sec.shape, dtype=np.int64)
-    xgray[np.arange(xhat_sec.shape[0]), ant] = gray[k]
+    if decision == 'random':
+        xgray = xgray_r
+    else:
+        xgray = np.zeros(xhat_sec.shape, dtype=np.int64)
+        xgray[np.arange(xhat_sec.shape[0]), ant] = gray[k]
     sym_hat = xgray.ravel()[idx_hat]
     idx_true = np.asarray(idx_true, dtype=np.int64)
     sym_true = np.asarray(sym_true, dtype=np.int64)

@@ -243,6 +243,11 @@ if __name__ == "__main__":
         run_vamp('vamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 4, seed=8)
     if want('vamp_c2_na4'):
         run_vamp('vamp_c2_na4', (64, 4, 32, 1, 1, 'QPSK'), {}, [2, 8], 4, seed=9)
+    # 'random' mode (i.i.d. prior, random_denoiser bamp.py:79-97, random_decision loss.py:252-280; B=1 only in the reference)
+    if want('bamp_random'):
+        run_bamp('bamp_random', (32, 4, 16, 1, 1, 'QPSK'), dict(mode='random'), [0, 6, 12], 8, seed=10)
+    if want('bamp_random_isi'):
+        run_bamp('bamp_random_isi', (16, 2, 8, 3, 2, '16QAM'), dict(trunc='tail', mode='random'), [4, 12], 6, seed=11)
     # SCAMP: small coupled instance, design matrix shared by groups of 4 frames (res=4)
     if want('scamp_small'):
         run_scamp('scamp_small', (32, 2, 8, 8, 3, 'QPSK'), dict(trunc='tail'), [4, 8], 8, seed=5, res=4)

@@ -227,3 +227,43 @@ def test_loss_kernel_nan_estimates_follow_argmax_rule():
     want = counters_for(cfg, xmap, g["xmmse"], g["x"], g["sym"], g["idx"])
     assert_counts_equal("nan", L.counters, want)
     assert L.counters["nan_frames"] == 2
+
+
+@pytest.mark.parametrize("name", ["bamp_random", "bamp_random_isi"])
+def test_bamp_random_mode_matches_reference_goldens(name):
+    """generator_mode='random' (bamp.py:46,79-97; loss.py:252-280) through the generic kernel, one call per SNR point:
+    exit iterations, estimates, trajectories and every error count against the reference's own run."""
+    g = load_golden(name)
+    F, N = g["x"].shape
+    cfg1 = config_from_meta(g["meta"])
+    per = cfg1.Lin * cfg1.Na                                    # labels per frame
+    for snr_db in sorted(set(g["snr_db"].tolist())):
+        sel = np.nonzero(g["snr_db"] == snr_db)[0]
+        cfg = config_from_meta(g["meta"], batch=len(sel), device=DEV)
+        amp = pkg.BAMP(cfg, trajectory=True, exp="f64")
+        idx = (g["idx"][sel].reshape(len(sel), per) + (np.arange(len(sel)) * N)[:, None]).reshape(-1)
+        amp(t(g["H"][sel]), t(g["y"][sel]).unsqueeze(-1), 10 ** (snr_db / 10), t(g["x"][sel]).unsqueeze(-1),
+            g["sym"][sel].reshape(-1), idx)
+        d = amp.last
+        iters = d.iters.cpu().numpy()
+        assert np.abs(iters - g["iters"][sel]).max() <= 1
+        conv = g["iters"][sel] <= cfg.N_Layers // 2
+        per_frame = np.abs(d.xmmse.cpu().numpy().reshape(len(sel), N) - g["xmmse"][sel]).max(axis=1)
+        assert per_frame[conv].max(initial=0.0) < 2e-3
+        tr = d.traj.cpu().numpy()
+        check_trajectory(name + ".tau", tr[:, :, 0], g["tau"][sel])
+        check_trajectory(name + ".var", tr[:, :, 1], g["varm"][sel], loose=0.2)
+        # Loss kernel alone on the REFERENCE's estimates: every count as the oracle (which reproduces the reference's rates)
+        L = pkg.Loss(cfg)
+        c = L._count(t(g["xmap"][sel]), t(g["xmmse"][sel]), t(g["x"][sel]), g["sym"][sel].reshape(-1), idx)
+        want = lo.error_counters(g["xmap"][sel], g["xmmse"][sel], g["x"][sel], g["sym"][sel].reshape(-1), idx, cfg.symbols,
+                                 cfg.gray, dict(Nt=cfg.Nt, Na=cfg.Na, Lin=cfg.Lin), decision='random')
+        assert_counts_equal(f"{name}@{snr_db}dB loss", c, want)
+        assert c["sqerr"] == pytest.approx(want["sqerr"], rel=1e-5, abs=1e-9)
+        # fused epilogue of the detector on its own estimates: converged frames decide like the reference
+        have = d.counters_dict()
+        assert have["frames"] == len(sel) and have["nan_frames"] == 0
+        if conv.all():
+            mine = lo.error_counters(g["xmap"][sel], g["xmmse"][sel], g["x"][sel], g["sym"][sel].reshape(-1), idx, cfg.symbols,
+                                     cfg.gray, dict(Nt=cfg.Nt, Na=cfg.Na, Lin=cfg.Lin), decision='random')
+            assert_counts_equal(f"{name}@{snr_db}dB fused", have, mine)

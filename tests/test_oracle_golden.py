@@ -138,3 +138,30 @@ def test_oracle_empty_and_single_frame():
     rall = ao.bamp_detect(g["H"][:4], g["y"][:4], g["sigma2"][:4], cfg.symbols, cfg.L, cfg.M, 20)
     assert np.array_equal(r1["iters"], rall["iters"][:1])
     assert np.allclose(r1["xmmse"], rall["xmmse"][:1], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["bamp_random", "bamp_random_isi"])
+def test_bamp_random_mode_oracle_matches_reference(name):
+    """generator_mode='random': i.i.d.-prior denoiser (bamp.py:79-97) and the top-Na decision (loss.py:252-280)."""
+    g = load_golden(name)
+    cfg = config_from_meta(g["meta"])
+    assert cfg.mode == 'random'
+    r = ao.bamp_detect(g["H"], g["y"], g["sigma2"], cfg.symbols, None, None, cfg.N_Layers, x_true=g["x"],
+                       iid_sparsity=cfg.Na / cfg.Nt)
+    assert np.abs(r["iters"] - g["iters"]).max() <= 1
+    conv = g["iters"] < cfg.N_Layers
+    per_frame = np.abs(r["xmmse"] - g["xmmse"]).max(axis=1)
+    assert per_frame[conv].max(initial=0.0) < 2e-3 and np.median(per_frame) < 1e-4
+    check_trajectory(name + ".tau", r["traj"]["tau"].T, g["tau"])
+    check_trajectory(name + ".var", r["traj"]["var"].T, g["varm"], loose=0.2)
+    # the reference's own Loss dict of every frame (B = 1) from the oracle's counters on the REFERENCE's estimates
+    dims = dict(Nt=cfg.Nt, Na=cfg.Na, Lin=cfg.Lin)
+    for f in range(g["x"].shape[0]):
+        c = lo.error_counters(g["xmap"][f:f + 1], g["xmmse"][f:f + 1], g["x"][f:f + 1], g["sym"][f], g["idx"][f], cfg.symbols,
+                              cfg.gray, dims, decision='random')
+        rates = lo.rates_from_counters(c, dict(Na=cfg.Na, Lin=cfg.Lin), cfg.index_bits, cfg.symbol_bits)
+        for i, k in enumerate(lo.KEYS):
+            want = g["loss"][f][i]
+            if np.isnan(want):
+                continue
+            assert abs(rates[k] - want) <= 1e-6 * max(1.0, abs(want)), (f, k, rates[k], want)
