@@ -472,4 +472,23 @@ int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t fr
     return launch_loss(k, (cudaStream_t)stream);
 }
 
+int ampsm_shrink(int kind, const ampsm_alphabet* a, double P0, double Ps, int64_t elems, int32_t M, const void* r,
+                 const float* cov, int64_t cov_stride, void* out_c, float* out_f, double* der_sum, void* stream) {
+    if (kind < AMPSM_SHRINK_BAYES || kind > AMPSM_SHRINK_SW_OOK) { set_error("Shrink: kind=%d outside 0..2", kind); return AMPSM_EINVAL; }
+    if (!a || a->K < 1 || a->K > AMPSM_MAX_K) { set_error("Shrink: bad alphabet"); return AMPSM_EINVAL; }
+    if (elems < 0 || (cov_stride != 0 && cov_stride != 1)) { set_error("Shrink: elems < 0 or cov_stride not in {0, 1}"); return AMPSM_EINVAL; }
+    if (elems == 0) return 0;
+    if (!r || !cov) { set_error("Shrink: r / cov is NULL"); return AMPSM_EINVAL; }
+    if ((kind != AMPSM_SHRINK_OOK && !out_c) || (kind != AMPSM_SHRINK_BAYES && !out_f)) { set_error("Shrink: output pointer is NULL"); return AMPSM_EINVAL; }
+    if (kind == AMPSM_SHRINK_SW_OOK && (M < 1 || elems % M != 0)) { set_error("Shrink: section size M=%d must divide elems", M); return AMPSM_EINVAL; }
+    if (kind == AMPSM_SHRINK_OOK && !(Ps > 0.0)) { set_error("Shrink: Ps must be positive"); return AMPSM_EINVAL; }
+    ShrinkArgs k{};
+    k.al.K = a->K;
+    for (int i = 0; i < a->K; ++i) { k.al.ref[i] = (float)a->re[i]; k.al.imf[i] = (float)a->im[i]; }
+    k.P0 = (float)P0; k.Ps = (float)Ps;
+    k.r = (const float2*)r; k.cov = cov; k.cov_stride = cov_stride; k.elems = elems; k.M = M;
+    k.out_c = (float2*)out_c; k.out_f = out_f; k.sum = der_sum;
+    return launch_shrink(k, kind, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -88,6 +88,19 @@ struct LossArgs {
     long long frames;
 };
 
+struct ShrinkArgs {
+    DevAlphabet al;
+    float P0, Ps;                // config.P0, config.Ps as float32 tensors (shrink.py:18)
+    const float2* r;             // [elems] complex64
+    const float* cov;            // [elems] (cov_stride = 1) or one value (cov_stride = 0)
+    long long cov_stride;
+    long long elems;
+    int M;                       // section size (sw_shrinkOOK)
+    float2* out_c;
+    float* out_f;
+    double* sum;
+};
+
 int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
 int launch_bamp_pair(const BampArgs& a, cudaStream_t stream);       // two warps per frame (64 x 32 shapes), else AMPSM_ENOFIT
@@ -96,6 +109,7 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
 int launch_loss(const LossArgs& a, cudaStream_t stream);
+int launch_shrink(const ShrinkArgs& a, int kind, cudaStream_t stream);   // kind 0 bayes, 1 shrinkOOK, 2 sw_shrinkOOK
 // batched thin SVD H = U diag(s) Vh of dense [frames][n][N] complex64 matrices, n <= 32 (svd_jacobi.cu); sweeps optional
 int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);

@@ -193,6 +193,23 @@ int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t fr
                      uint64_t* counters, void* stream);
 
 /*
+ * Shrink -- replaces shrink.Shrink.forward / sw_shrinkOOK (shrink.py:45-75, 77-95, 139-157), the element-wise
+ * denoisers of the reference's `random`-mode VAMP variant (vamp2.py:46), complex64 / float32 as the reference.
+ *   kind  : AMPSM_SHRINK_BAYES  out_c[i] = Ps sum_k s_k G_k / (P0 G_0 + Ps sum_k G_k)           (shrink.py:77-95)
+ *           AMPSM_SHRINK_OOK    out_f[i] = 1 / (1 + eta + 1e-9); *der_sum += sum_i nan_to_num(2 eta out^2 / cov),
+ *                               the caller forms dxdr = der_sum / elems (zero *der_sum first)     (shrink.py:139-157)
+ *           AMPSM_SHRINK_SW_OOK per section of M entries: out_c = Exp, out_f = Exp (1 - Exp)      (shrink.py:58-75)
+ *   P0, Ps: config.P0 / config.Ps (config.py:76-114);  r : complex64 [elems];  cov : float [elems] (cov_stride = 1)
+ *           or one value (cov_stride = 0, the 0-dim gamma of vamp2.py:59).
+ * `shrink` and `lasso` raise in the reference itself (shrink.py:113, 135) and have no entry here.
+ */
+#define AMPSM_SHRINK_BAYES  0
+#define AMPSM_SHRINK_OOK    1
+#define AMPSM_SHRINK_SW_OOK 2
+int ampsm_shrink(int kind, const ampsm_alphabet* a, double P0, double Ps, int64_t elems, int32_t M, const void* r,
+                 const float* cov, int64_t cov_stride, void* out_c, float* out_f, double* der_sum, void* stream);
+
+/*
  * Measurement helpers (bench.py): FP32 FFMA throughput of the device in TFLOP/s (the roofline denominator for
  * the shared-memory / register resident iterations, which MEASURED_PEAKS.json does not hold), and the number of
  * kernel launches this library has made since the last reset (bench.py's gpu_launches).

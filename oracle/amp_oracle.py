@@ -327,3 +327,55 @@ def _denoise_double(r, sig2, symbols, L, M, shift):
         var0 = np.abs(xmmse) ** 2 * (1 - per_antenna / norm)
         spread = (np.abs(xmmse[..., None] - sym) ** 2 * eta).sum(axis=-1) / norm
     return xmmse.reshape(F, L * M).astype(C64), (var0 + spread).reshape(F, L * M).astype(F32)
+
+
+# ---- Shrink family (shrink.py:58-157): element-wise denoisers of the reference's ``random``-mode VAMP variant ------
+_EXP_MAX = F32(np.log(np.finfo(np.float32).max))      # shrink.py:163-166 (regularize_exp): a[a >= max] = max - 1
+TOL = F32(1.0e-9)                                      # shrink.py:28
+
+
+def _regularize_exp(a):
+    a = a.astype(F32).copy()
+    a[a >= _EXP_MAX] = _EXP_MAX - F32(1)
+    return a
+
+
+def shrink_bayes(r, cov, symbols, P0, Ps):
+    """shrink.py:77-95: posterior mean under P0 delta_0 + Ps sum_k delta_{s_k}, everything in complex64 / float32
+    (the symbols are cast to complex64 here, shrink.py:26).  r: (..., ) complex64, cov broadcastable float32."""
+    r = np.asarray(r, C64)[..., None]
+    cov = np.asarray(cov, F32)[..., None] if np.ndim(cov) else F32(cov)
+    sym = np.asarray(symbols).astype(C64)
+    P0, Ps = F32(P0), F32(Ps)
+    G0 = np.exp(-(np.abs(r) ** 2).astype(F32) / cov).astype(F32)
+    Gs = np.exp(-(np.abs(r - sym) ** 2).astype(F32) / cov).astype(F32)
+    norm = (P0 * G0 + Ps * Gs.sum(-1, keepdims=True, dtype=F32)).astype(F32)
+    norm[norm == 0] = TOL                                 # regularize_zero, shrink.py:159-161
+    return ((Ps * (sym * Gs).sum(-1, keepdims=True).astype(C64)) / norm).astype(C64)[..., 0]
+
+
+def shrink_ook(r, cov, P0, Ps):
+    """shrink.py:139-157: OOK posterior mean 1 / (1 + eta + tol) and the batch mean of its derivative."""
+    re = np.asarray(r).real.astype(F32)
+    cov = np.asarray(cov, F32)
+    theta = np.log(F32(P0) / F32(Ps)).astype(F32)
+    eta = np.exp(_regularize_exp(theta + (F32(1) - F32(2) * re) / cov)).astype(F32)
+    e = (F32(1) / (F32(1) + eta + TOL)).astype(F32)
+    with np.errstate(invalid='ignore', over='ignore'):
+        der = np.nan_to_num((F32(2) * eta * e ** 2 / cov).astype(F32), nan=0.0)
+    return e, F32(der.mean(dtype=np.float64))
+
+
+def shrink_sw_ook(r, cov, L, M):
+    """shrink.py:58-75: section-wise OOK denoiser -- extrinsic log-ratio of 'exactly one active entry per section'."""
+    re = np.asarray(r).real.astype(F32)
+    cov = np.asarray(cov, F32)
+    B = re.shape[0]
+    Lr = _regularize_exp(((F32(2) * re - F32(1)) / cov).reshape(B, L, M))
+    eL = np.exp(Lr).astype(F32)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        Le = -np.log(eL.sum(-1, keepdims=True, dtype=F32) - eL).astype(F32)
+    eta = np.exp(_regularize_exp(Lr + Le)).astype(F32)
+    E = (eta / (F32(1) + eta)).astype(F32)
+    V = (E * (F32(1) - E)).astype(F32)
+    return E.reshape(B, L * M).astype(C64), V.reshape(B, L * M)

@@ -23,6 +23,7 @@ from channel import Channel  # noqa: E402
 from config import Config    # noqa: E402
 from data import Data        # noqa: E402
 from loss import Loss        # noqa: E402
+from shrink import Shrink    # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KEYS = ['fer', 'nMSE', 'nMSEf', 'nMSEm', 'nMSEL', 'ver', 'verf', 'verm', 'verL', 'ber', 'iber', 'sber', 'ier', 'ser']
@@ -195,6 +196,32 @@ def run_loss_only(name, args, kwargs, frames, seed):
     print(name, 'loss', dict(zip(KEYS, loss_vec(L).round(5))))
 
 
+def run_shrink(name, seed):
+    """Reference Shrink denoisers (shrink.py:58-157) on fixed-seed inputs: 'bayes' (complex QPSK prior) and
+    'shrinkOOK' / 'sw_shrinkOOK' (OOK)."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    cq = cfg(16, 2, 8, 1, 1, 'QPSK', mode='random', batch=6)
+    co = cfg(16, 2, 8, 1, 1, 'OOK', mode='segmented', batch=6)
+    N = 16
+    for tag, c in (('q', cq), ('o', co)):
+        x, _, _ = Data(c).generate_message()
+        r = (x.numpy() + (rng.normal(size=(6, N, 1)) + 1j * rng.normal(size=(6, N, 1))) * 0.3).astype(np.complex64)
+        cov = (0.05 + 0.4 * rng.uniform(size=(6, N, 1))).astype(np.float32)
+        out[f'r_{tag}'], out[f'cov_{tag}'] = r.reshape(6, N), cov.reshape(6, N)
+    rq, covq = torch.tensor(out['r_q']).reshape(6, N, 1), torch.tensor(out['cov_q']).reshape(6, N, 1)
+    ro, covo = torch.tensor(out['r_o']).reshape(6, N, 1), torch.tensor(out['cov_o']).reshape(6, N, 1)
+    out['bayes'] = Shrink(cq, 'bayes')(rq.clone(), covq.clone()).numpy().reshape(6, N)
+    # 'shrink' raises UnboundLocalError in the reference (d0 is used inside the tuple assignment that defines it,
+    # shrink.py:113) and 'lasso' AttributeError (self.lmda, shrink.py:135): nothing to pin for those two.
+    e, d = Shrink(co, 'shrinkOOK')(ro.clone(), covo.clone())
+    out['ook_exp'], out['ook_dxdr'] = e.numpy().reshape(6, N), np.float32(d.numpy())
+    e, v = Shrink(co, 'shrinkOOK').sw_shrinkOOK(ro.clone(), covo.clone())
+    out['sw_exp'], out['sw_var'] = e.numpy().reshape(6, N), v.numpy().reshape(6, N)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def save(name, out, batch_loss_vec, gidx, meta):
     arrays = {}
     for k, v in out.items():
@@ -251,6 +278,8 @@ if __name__ == "__main__":
     # SCAMP: small coupled instance, design matrix shared by groups of 4 frames (res=4)
     if want('scamp_small'):
         run_scamp('scamp_small', (32, 2, 8, 8, 3, 'QPSK'), dict(trunc='tail'), [4, 8], 8, seed=5, res=4)
+    if want('shrink'):
+        run_shrink('shrink', seed=12)
     # Loss alone at B>1
     if want('loss_qpsk'):
         run_loss_only('loss_qpsk', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), 24, seed=6)

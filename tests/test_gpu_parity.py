@@ -267,3 +267,36 @@ def test_bamp_random_mode_matches_reference_goldens(name):
             mine = lo.error_counters(g["xmap"][sel], g["xmmse"][sel], g["x"][sel], g["sym"][sel].reshape(-1), idx, cfg.symbols,
                                      cfg.gray, dict(Nt=cfg.Nt, Na=cfg.Na, Lin=cfg.Lin), decision='random')
             assert_counts_equal(f"{name}@{snr_db}dB fused", have, mine)
+
+
+def test_shrink_family_matches_reference_goldens():
+    """Shrink 'bayes', 'shrinkOOK', sw_shrinkOOK (shrink.py:58-157) through ampsm_shrink: float32 arithmetic like the
+    reference, tolerance 2e-6 absolute on outputs in [0, 1] (two float32 exp evaluations apart); a scalar cov
+    broadcasts like the 0-dim gamma of vamp2.py:59; 'shrink' / 'lasso' fail as they do in the reference."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "shrink.npz"))
+    cq = pkg.Config(16, 2, 8, 1, 1, batch=6, generator_mode='random', alphabet='QPSK', channel_profile='uniform', device=DEV)
+    co = pkg.Config(16, 2, 8, 1, 1, batch=6, generator_mode='segmented', alphabet='OOK', channel_profile='uniform', device=DEV)
+    rq, cvq = t(g["r_q"]).unsqueeze(-1), t(g["cov_q"]).unsqueeze(-1)
+    ro, cvo = t(g["r_o"]).unsqueeze(-1), t(g["cov_o"]).unsqueeze(-1)
+    b = pkg.Shrink(cq, "bayes")(rq, cvq)
+    assert b.shape == rq.shape and b.dtype == torch.complex64
+    assert np.abs(b.cpu().numpy().reshape(6, 16) - g["bayes"]).max() < 2e-6
+    e, dxdr = pkg.Shrink(co, "shrinkOOK")(ro, cvo)
+    assert e.dtype == torch.float32 and dxdr.dim() == 0
+    assert np.abs(e.cpu().numpy().reshape(6, 16) - g["ook_exp"]).max() < 2e-6
+    assert abs(float(dxdr) - float(g["ook_dxdr"])) < 2e-6 * abs(float(g["ook_dxdr"]))
+    E, V = pkg.Shrink(co, "shrinkOOK").sw_shrinkOOK(ro, cvo)
+    assert np.abs(E.cpu().numpy().reshape(6, 16) - g["sw_exp"]).max() < 2e-6
+    assert np.abs(V.cpu().numpy().reshape(6, 16) - g["sw_var"]).max() < 2e-6
+    # scalar cov, larger ragged size, against the oracle
+    rng = np.random.default_rng(3)
+    r = (rng.normal(size=(6, 1000 * 16)) + 1j * rng.normal(size=(6, 1000 * 16))).astype(np.complex64) * 0.7
+    cbig = pkg.Config(16000, 2, 8, 1, 1, batch=6, generator_mode='random', alphabet='QPSK', channel_profile='uniform', device=DEV)
+    got = pkg.Shrink(cbig, "bayes")(t(r).unsqueeze(-1), torch.tensor(0.3)).cpu().numpy().reshape(r.shape)
+    assert np.abs(got - ao.shrink_bayes(r, np.float32(0.3), cbig.symbols, cbig.P0, cbig.Ps)).max() < 2e-6
+    with pytest.raises(UnboundLocalError):
+        pkg.Shrink(cq, "shrink")(rq, cvq)
+    with pytest.raises(AttributeError):
+        pkg.Shrink(cq, "lasso")(rq, cvq)

@@ -165,3 +165,21 @@ def test_bamp_random_mode_oracle_matches_reference(name):
             if np.isnan(want):
                 continue
             assert abs(rates[k] - want) <= 1e-6 * max(1.0, abs(want)), (f, k, rates[k], want)
+
+
+def _shrink_configs():
+    import amp_sparc_spatialmodulation_b200 as pkg
+    cq = pkg.Config(16, 2, 8, 1, 1, batch=6, generator_mode='random', alphabet='QPSK', channel_profile='uniform', device='cpu')
+    co = pkg.Config(16, 2, 8, 1, 1, batch=6, generator_mode='segmented', alphabet='OOK', channel_profile='uniform', device='cpu')
+    return cq, co
+
+
+def test_shrink_oracle_matches_reference():
+    """Shrink.bayes / shrinkOOK / sw_shrinkOOK (shrink.py:58-157) against the reference's own outputs."""
+    g = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "shrink.npz"))
+    cq, co = _shrink_configs()
+    assert np.abs(ao.shrink_bayes(g["r_q"], g["cov_q"], cq.symbols, cq.P0, cq.Ps) - g["bayes"]).max() < 2e-6
+    e, dxdr = ao.shrink_ook(g["r_o"], g["cov_o"], co.P0, co.Ps)
+    assert np.abs(e - g["ook_exp"]).max() < 1e-6 and abs(dxdr - g["ook_dxdr"]) < 1e-6 * abs(g["ook_dxdr"]) + 1e-8
+    E, V = ao.shrink_sw_ook(g["r_o"], g["cov_o"], co.Na * co.Lin, co.Nt // co.Na)
+    assert np.abs(E - g["sw_exp"]).max() < 1e-6 and np.abs(V - g["sw_var"]).max() < 1e-6
