@@ -18,7 +18,7 @@ COUNTER_NAMES = ['frames', 'frame_err', 'slot_err', 'slot_err_first', 'slot_err_
 SQERR_NAMES = ['sqerr', 'sqerr_first', 'sqerr_mid', 'sqerr_last']
 
 # every symbol include/ampsm_b200.h declares (checked by tests/test_cabi_symbols.py)
-EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_host",
+EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_taps", "ampsm_bamp_detect_host",
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
            "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops",
@@ -60,6 +60,7 @@ def lib():
     bamp = [PP, AP, i64, vp, i64, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_bamp_detect.argtypes = bamp + [vp]
     L.ampsm_bamp_detect_host.argtypes = bamp + [i32]
+    L.ampsm_bamp_detect_taps.argtypes = [PP, AP, i64, vp, i64, i32, i32] + bamp[5:] + [vp]
     vamp = [PP, AP, i64, i32, vp, i64, vp, i64, vp, i64, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_vamp_detect.argtypes = vamp + [vp]
     L.ampsm_vamp_detect_host.argtypes = vamp + [i32]

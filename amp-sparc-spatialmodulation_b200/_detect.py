@@ -70,8 +70,9 @@ class Detector(nn.Module):
         return up(symbols), up(indices)
 
     def _problem(self, frames, **kw):
-        return _cabi.make_problem(self.config, frames, early_exit=self.early_exit, shift=self.shift, exp=self.exp,
-                                  kernel=self.kernel, **kw)
+        opts = dict(early_exit=self.early_exit, shift=self.shift, exp=self.exp, kernel=self.kernel)
+        opts.update(kw)
+        return _cabi.make_problem(self.config, frames, **opts)
 
     def _wrap(self, det: Detection) -> Loss:
         """Reference behaviour of forward(): reset the module's own Loss and fill it (bamp.py:135,142)."""

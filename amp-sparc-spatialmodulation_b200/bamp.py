@@ -12,23 +12,71 @@ from . import _cabi
 from ._detect import Detection, Detector, ptr
 
 
+def matrix_from_taps(taps: torch.Tensor, Lin: int, Lout: int, cyclic: bool = False) -> torch.Tensor:
+    """Dense block-Toeplitz matrix (..., Nr*Lout, Nt*Lin) of taps (..., Lh, Nr, Nt): block (i, j) = taps[i - j] for
+    0 <= i - j < Lh, the difference taken modulo Lin when `cyclic` (the layouts of channel.py:56-72 and 89-91)."""
+    Lh, Nr, Nt = taps.shape[-3:]
+    d = torch.arange(Lout, device=taps.device)[:, None] - torch.arange(Lin, device=taps.device)[None, :]
+    if cyclic:
+        d = d % Lin
+    valid = (d >= 0) & (d < Lh)
+    blocks = taps[..., d.clamp(0, Lh - 1), :, :] * valid[:, :, None, None]          # (..., Lout, Lin, Nr, Nt)
+    return blocks.transpose(-3, -2).reshape(*taps.shape[:-3], Lout * Nr, Lin * Nt)
+
+
+def taps_from_matrix(H: torch.Tensor, config, chunk_bytes: int = 1 << 28):
+    """(taps (..., Lh, Nr, Nt), cyclic) when the dense H (..., n, N) is exactly the block-Toeplitz matrix of its first
+    block column -- what Channel.generate_channel / generate_as_sparc produce -- else None.  The check rebuilds the dense
+    matrix from the candidate taps (in chunks of frames) and compares bit for bit."""
+    Nr, Nt, Lin, Lout, Lh = config.Nr, config.Nt, config.Lin, config.Lout, min(config.Lh, config.Lout)
+    if H.shape[-2:] != (Nr * Lout, Nt * Lin) or Lh > Lin:
+        return None
+    blocks = H.reshape(*H.shape[:-2], Lout, Nr, Lin, Nt)
+    taps = blocks[..., :Lh, :, 0, :].contiguous()
+    lead = H.shape[:-2]
+    Hf, tf = H.reshape(-1, Nr * Lout, Nt * Lin), taps.reshape(-1, Lh, Nr, Nt)
+    per = max(1, chunk_bytes // (Hf[0].numel() * 8))
+    for cyclic in ((False, True) if Lout == Lin and Lh > 1 else (False,)):
+        if all(torch.equal(matrix_from_taps(tf[f0:f0 + per], Lin, Lout, cyclic), Hf[f0:f0 + per])
+               for f0 in range(0, Hf.shape[0], per)):
+            return taps.reshape(*lead, Lh, Nr, Nt), cyclic
+    return None
+
+
 class BAMP(Detector):
-    def detect(self, H, y, SNR, x=None, symbols=None, indices=None, frame_base=0) -> Detection:
-        """Enqueue the kernel on the current stream and return device-side results without synchronising."""
-        dev = self._cuda_device(y, H)
+    """``structured='auto'`` (default): when ``Lin > 1`` and the matrix handed to ``forward`` is exactly block-Toeplitz
+    (what the reference's generators build), the kernel applies it from its ``Lh`` tap matrices (``detect_taps``) instead of
+    reading the dense array every iteration; ``structured=False`` always runs the dense kernels."""
+
+    def __init__(self, config, *args, structured='auto', **kw) -> None:
+        super().__init__(config, *args, **kw)
+        self.structured = structured
+
+    def detect_taps(self, taps, y, SNR, x=None, symbols=None, indices=None, cyclic=False, frame_base=0) -> Detection:
+        """BAMP on a structured ISI channel given by its taps, (Lh, Nr, Nt) shared by the call or (F, Lh, Nr, Nt) per frame
+        (``Channel.generate_channel(return_taps=True)``); the dense (Nr*Lout, Nt*Lin) matrix is never formed."""
+        dev = self._cuda_device(y, taps)
         cfg = self.config
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
         y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
         F = y.shape[0]
-        H = H.to(dev, torch.complex64).contiguous()
-        if H.dim() == 2:
-            stride = 0
-        elif H.dim() == 3 and H.shape[0] == F:
-            stride = n * N
-        else:
-            raise RuntimeError(f"H must be (n, N) or (frames, n, N); got {tuple(H.shape)} for {F} frames")
-        if tuple(H.shape[-2:]) != (n, N):
-            raise RuntimeError(f"H has shape {tuple(H.shape)}, expected (..., {n}, {N})")
+        taps = taps.to(dev, torch.complex64).contiguous()
+        Lh = taps.shape[-3]
+        if tuple(taps.shape[-2:]) != (cfg.Nr, cfg.Nt) or taps.dim() not in (3, 4) or (taps.dim() == 4 and taps.shape[0] != F):
+            raise RuntimeError(f"taps must be (Lh, {cfg.Nr}, {cfg.Nt}) or ({F}, Lh, {cfg.Nr}, {cfg.Nt}); got {tuple(taps.shape)}")
+        stride = 0 if taps.dim() == 3 else Lh * cfg.Nr * cfg.Nt
+        xt, sym, idx, counters, iters, xmap, xmmse, var, traj = self._alloc(F, N, x, symbols, indices, dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().ampsm_bamp_detect_taps(
+                self._problem(F, frame_base=frame_base, kernel='generic'), self._alphabet, F, taps.data_ptr(), stride, Lh,
+                1 if cyclic else 0, y.data_ptr(), float(self.E / SNR), None, ptr(xt), ptr(sym), ptr(idx), ptr(xmap),
+                ptr(xmmse), ptr(var), iters.data_ptr(), ptr(traj), counters.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ampsm_bamp_detect_taps")
+        return Detection(F, counters, iters, xmap, xmmse, var, traj)
+
+    def _alloc(self, F, N, x, symbols, indices, dev):
+        cfg = self.config
         xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
         sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
         counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
@@ -37,6 +85,29 @@ class BAMP(Detector):
         xmmse = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
         var = torch.empty(F, N, 1, dtype=torch.float32, device=dev) if self.outputs else None
         traj = torch.empty(F, cfg.N_Layers, 3, dtype=torch.float32, device=dev) if self.trajectory else None
+        return xt, sym, idx, counters, iters, xmap, xmmse, var, traj
+
+    def detect(self, H, y, SNR, x=None, symbols=None, indices=None, frame_base=0) -> Detection:
+        """Enqueue the kernel on the current stream and return device-side results without synchronising."""
+        dev = self._cuda_device(y, H)
+        cfg = self.config
+        n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
+        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        F = y.shape[0]
+        H = H.to(dev, torch.complex64).contiguous()
+        if self.structured and cfg.Lin > 1 and self.kernel in ('auto', 'generic') and H.dim() in (2, 3):
+            st = taps_from_matrix(H, cfg)
+            if st is not None:
+                return self.detect_taps(st[0], y, SNR, x, symbols, indices, cyclic=st[1], frame_base=frame_base)
+        if H.dim() == 2:
+            stride = 0
+        elif H.dim() == 3 and H.shape[0] == F:
+            stride = n * N
+        else:
+            raise RuntimeError(f"H must be (n, N) or (frames, n, N); got {tuple(H.shape)} for {F} frames")
+        if tuple(H.shape[-2:]) != (n, N):
+            raise RuntimeError(f"H has shape {tuple(H.shape)}, expected (..., {n}, {N})")
+        xt, sym, idx, counters, iters, xmap, xmmse, var, traj = self._alloc(F, N, x, symbols, indices, dev)
         sigma2 = self.E / SNR                                # bamp.py:134
         with torch.cuda.device(dev):
             rc = _cabi.lib().ampsm_bamp_detect(

@@ -46,8 +46,14 @@ class Channel:
         tail = H[-Nr:, -Nt * Lh:-Nt]
         return [tail[:, :Nt * (Lh - l - 1)] for l in range(Lh - 1)]
 
-    def generate_channel(self) -> torch.Tensor:
-        """Block-Toeplitz MIMO-ISI matrix, (Nr*Lout) x (Nt*Lin) (channel.py:40-73)."""
+    def _as_taps(self, h):
+        """(Nr, Nt, Lh) numpy taps -> (Lh, Nr, Nt) tensor, the layout of ampsm_bamp_detect_taps / BAMP.detect_taps."""
+        return torch.tensor(np.ascontiguousarray(np.moveaxis(h, -1, 0)), dtype=self.dtype, requires_grad=False,
+                            device=self.device)
+
+    def generate_channel(self, return_taps: bool = False) -> torch.Tensor:
+        """Block-Toeplitz MIMO-ISI matrix, (Nr*Lout) x (Nt*Lin) (channel.py:40-73).  ``return_taps=True`` (an addition)
+        also returns the scaled taps (Lh, Nr, Nt) the matrix is built from -- same random draws either way."""
         Nr, Nt, Lh, Lin = self.Nr, self.Nt, self.Lh, self.Lin
         h = self._taps() * np.sqrt(self.pdp * self.Lout / Nr / Lin / 2)
         H = np.zeros((Lin * Nr, Lin * Nt), dtype=self.npdtype)
@@ -61,10 +67,12 @@ class Channel:
         elif self.trunc == 'cyclic':
             for l, blk in enumerate(self._wrap_rows(H)):
                 H[l * Nr:(l + 1) * Nr, -blk.shape[1]:] = blk
-        return torch.tensor(H, dtype=self.dtype, requires_grad=False, device=self.device)
+        H = torch.tensor(H, dtype=self.dtype, requires_grad=False, device=self.device)
+        return (H, self._as_taps(h)) if return_taps else H
 
-    def generate_as_sparc(self):
-        """Base matrix W (Lout x Lin) and design matrix A with per-block variance W (channel.py:75-95)."""
+    def generate_as_sparc(self, return_taps: bool = False):
+        """Base matrix W (Lout x Lin) and design matrix A with per-block variance W (channel.py:75-95).
+        ``return_taps=True`` (an addition) appends the taps sqrt(W[l, 0]) h_l, (Lh, Nr, Nt), A is built from."""
         W = np.zeros((self.Lout, self.Lin))
         for l in range(self.Lh):
             W += np.eye(self.Lout, self.Lin, -l) * self.pdp[l]
@@ -73,9 +81,10 @@ class Channel:
         A = np.zeros((self.Nr * self.Lout, self.Nt * self.Lin), dtype=self.npdtype)
         for l in range(self.Lh):
             A += np.kron(np.eye(self.Lout, self.Lin, -l) * np.sqrt(W), h[:, :, l])
+        taps = h * np.sqrt(np.array([W[l, 0] if l < self.Lout else 0.0 for l in range(self.Lh)]))
         W = torch.tensor(W, dtype=torch.float32, requires_grad=False, device=self.device)
         A = torch.tensor(A, dtype=self.dtype, requires_grad=False, device=self.device)
-        return W, A
+        return (W, A, self._as_taps(taps)) if return_taps else (W, A)
 
     def generate_as_random(self) -> torch.Tensor:
         """i.i.d. CN(0, 1/(Lin*Nr)) matrix from the torch generator (channel.py:97-101)."""

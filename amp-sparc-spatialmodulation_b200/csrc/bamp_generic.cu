@@ -2,6 +2,12 @@
 // The frame's channel matrix is staged into shared memory once with a 1-D bulk TMA copy (cp.async.bulk +
 // mbarrier) and all iterations run in-kernel; matrices that do not fit are read through L2 instead.
 // Follows bamp.py:12-25 (state), 59-64 (iteration), 66-77 (denoiser), 116-143 (loop, exit, Loss).
+//
+// Structured operator (OPK > 0, ampsm_bamp_detect_taps): for ISI channels (Lh > 1, Lin > 1) the reference's matrix is
+// block-Toeplitz -- block (i, j) of H is the Nr x Nt tap matrix g[i - j] (channel.py:53-72, 85-91).  Only the taps
+// [Lh][Nr][Nt] live in shared memory (rows padded by one element: conflict-free for both passes) and H, H^H, |H|^2,
+// |H|^2^T are applied as block convolutions: a thread owns TI consecutive time slots of one antenna, so every tap it
+// loads is used TI times and there are no cross-lane reductions.  Slots outside the frame point at a zeroed slot.
 #include "blockops.cuh"
 #include "kernels.h"
 
@@ -13,7 +19,9 @@ struct BampPlan {
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-__host__ __device__ inline BampPlan bamp_plan(const Geom& g, bool stage, bool exp64) {
+__host__ __device__ inline size_t taps_ld(const Geom& g) { return (size_t)g.Nt + 1; }
+
+__host__ __device__ inline BampPlan bamp_plan(const Geom& g, bool stage, bool exp64, int Lh = 0) {
     BampPlan p;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -21,16 +29,19 @@ __host__ __device__ inline BampPlan bamp_plan(const Geom& g, bool stage, bool ex
         o = align16(o + bytes);
         return at;
     };
-    p.H = take(stage ? (size_t)g.n * g.N * 8 : 0);
+    // operator: the dense matrix, or Lh tap matrices with padded rows; vectors read by the block convolutions carry one
+    // extra all-zero time slot (Nr resp. Nt entries)
+    p.H = take(!stage ? 0 : (Lh > 0 ? (size_t)Lh * g.Nr * taps_ld(g) * 8 : (size_t)g.n * g.N * 8));
+    const size_t nz = Lh > 0 ? (size_t)g.Nr : 0, Nz = Lh > 0 ? (size_t)g.Nt : 0;
     p.y = take((size_t)g.n * 8);
     p.z = take((size_t)g.n * 8);
-    p.g = take((size_t)g.n * 8);
+    p.g = take(((size_t)g.n + nz) * 8);
     p.u = take((size_t)g.n * 4);
-    p.w = take((size_t)g.n * 4);
-    p.xh = take((size_t)g.N * 8);
+    p.w = take(((size_t)g.n + nz) * 4);
+    p.xh = take(((size_t)g.N + Nz) * 8);
     p.xh_new = take((size_t)g.N * 8);
     p.xmap = take((size_t)g.N * 8);
-    p.var = take((size_t)g.N * 4);
+    p.var = take(((size_t)g.N + Nz) * 4);
     p.var_new = take((size_t)g.N * 4);
     p.cov = take((size_t)g.N * 4);
     p.scr = take((size_t)g.N * 3 * (exp64 ? 8 : 4));
@@ -64,14 +75,15 @@ __device__ inline void block_sum3(double& a, double& b, double& c, double* red) 
     __syncthreads();
 }
 
-template <bool EXP64>
+// OPK: 0 dense matrix; otherwise the structured operator with OPK time slots per thread
+template <bool EXP64, int OPK>
 __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant__ BampArgs a) {
     using E = typename ExpT<EXP64>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     const Geom& g = a.g;
     const DevAlphabet& al = a.al;
     const bool stage = a.stage_H != 0;
-    const BampPlan P = bamp_plan(g, stage, EXP64);
+    const BampPlan P = bamp_plan(g, stage, EXP64, OPK ? a.Lh : 0);
     float2* Hs = reinterpret_cast<float2*>(smem + P.H);
     float2* y_s = reinterpret_cast<float2*>(smem + P.y);
     float2* z_s = reinterpret_cast<float2*>(smem + P.z);
@@ -94,9 +106,14 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
     const int n = g.n, N = g.N;
     const uint32_t Hbytes = (uint32_t)((size_t)n * N * 8);
     const bool shared_H = a.H_stride == 0;
+    const int ldt = OPK ? (stage ? (int)taps_ld(g) : g.Nt) : 0;          // row stride of a tap matrix
 
     counters_reset(bc);
-    if (stage && tid == 0) {
+    if (OPK) {                                                              // the zero slots (never written again)
+        for (int i = tid; i < g.Nr; i += blockDim.x) { g_s[n + i] = make_float2(0.f, 0.f); w_s[n + i] = 0.f; }
+        for (int j = tid; j < g.Nt; j += blockDim.x) { xh_s[N + j] = make_float2(0.f, 0.f); var_s[N + j] = 0.f; }
+    }
+    if (!OPK && stage && tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
     }
@@ -109,7 +126,11 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
         const float2* Hm = stage ? Hs : Hg;
         if (stage && !(shared_H && H_loaded)) {
             // all threads finished reading the previous frame's matrix (barrier at the end of the last frame)
-            if (tid == 0) {
+            if (OPK) {
+                const int rows = a.Lh * g.Nr;
+                for (int e = tid; e < rows * g.Nt; e += blockDim.x) Hs[(size_t)(e / g.Nt) * ldt + e % g.Nt] = Hg[e];
+                H_loaded = true;
+            } else if (tid == 0) {
                 mbar_expect_tx(mbar, Hbytes);
                 tma_load_1d(Hs, Hg, Hbytes, mbar);
             }
@@ -125,7 +146,7 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
             xh_s[j] = make_float2(0.f, 0.f);   // bamp.py:20
             var_s[j] = 1.0f;                   // bamp.py:21
         }
-        if (stage && !(shared_H && H_loaded)) {
+        if (!OPK && stage && !(shared_H && H_loaded)) {
             mbar_wait(mbar, phase);
             phase ^= 1u;
             H_loaded = true;
@@ -135,46 +156,120 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
         int t_done = 0;
         for (int t = 0; t < g.max_iters; ++t) {
             // ---- row pass: v = |H|^2 var, Hx = H xhat; then z, u and the column pass operands (bamp.py:59-61)
-            for (int i = warp; i < n; i += nwarps) {
-                const float2* Hrow = Hm + (size_t)i * N;
-                float av = 0.f, ar = 0.f, ai = 0.f;
-                for (int j = lane; j < N; j += 32) {
-                    const float2 h = Hrow[j];
-                    const float2 x = xh_s[j];
-                    av = fmaf(fmaf(h.x, h.x, h.y * h.y), var_s[j], av);
-                    ar = fmaf(h.x, x.x, fmaf(-h.y, x.y, ar));
-                    ai = fmaf(h.x, x.y, fmaf(h.y, x.x, ai));
+            auto row_update = [&](int i, float av, float ar, float ai) {
+                const float2 yv = y_s[i], zo = z_s[i];
+                const float2 resid = make_float2(yv.x - zo.x, yv.y - zo.y);
+                const float2 corr = cdiv_real(make_float2(av * resid.x, av * resid.y), u_s[i]);   // old u
+                const float2 zn = make_float2(ar - corr.x, ai - corr.y);
+                const float un = av + sigma2;
+                z_s[i] = zn;
+                u_s[i] = un;
+                g_s[i] = cdiv_real(make_float2(yv.x - zn.x, yv.y - zn.y), un);
+                w_s[i] = __frcp_rn(un);
+            };
+            if constexpr (OPK == 0) {
+                for (int i = warp; i < n; i += nwarps) {
+                    const float2* Hrow = Hm + (size_t)i * N;
+                    float av = 0.f, ar = 0.f, ai = 0.f;
+                    for (int j = lane; j < N; j += 32) {
+                        const float2 h = Hrow[j];
+                        const float2 x = xh_s[j];
+                        av = fmaf(fmaf(h.x, h.x, h.y * h.y), var_s[j], av);
+                        ar = fmaf(h.x, x.x, fmaf(-h.y, x.y, ar));
+                        ai = fmaf(h.x, x.y, fmaf(h.y, x.x, ai));
+                    }
+                    av = warp_sum(av);
+                    ar = warp_sum(ar);
+                    ai = warp_sum(ai);
+                    if (lane == 0) row_update(i, av, ar, ai);
                 }
-                av = warp_sum(av);
-                ar = warp_sum(ar);
-                ai = warp_sum(ai);
-                if (lane == 0) {
-                    const float2 yv = y_s[i], zo = z_s[i];
-                    const float2 resid = make_float2(yv.x - zo.x, yv.y - zo.y);
-                    const float2 corr = cdiv_real(make_float2(av * resid.x, av * resid.y), u_s[i]);   // old u
-                    const float2 zn = make_float2(ar - corr.x, ai - corr.y);
-                    const float un = av + sigma2;
-                    z_s[i] = zn;
-                    u_s[i] = un;
-                    g_s[i] = cdiv_real(make_float2(yv.x - zn.x, yv.y - zn.y), un);
-                    w_s[i] = __frcp_rn(un);
+            } else {
+                // out(i, r) = sum_l sum_t g_l[r][t] x(i - l, t): thread = (tile of OPK output slots, receive antenna r)
+                const int tiles = (g.Lout + OPK - 1) / OPK;
+                for (int w = tid; w < tiles * g.Nr; w += blockDim.x) {
+                    const int r = w % g.Nr, i0 = (w / g.Nr) * OPK;
+                    float av[OPK], ar[OPK], ai[OPK];
+#pragma unroll
+                    for (int k = 0; k < OPK; ++k) av[k] = ar[k] = ai[k] = 0.f;
+                    for (int l = 0; l < a.Lh; ++l) {
+                        int js[OPK];                                       // first entry of the input slot (zero slot if none)
+#pragma unroll
+                        for (int k = 0; k < OPK; ++k) {
+                            int j = i0 + k - l;
+                            if (a.cyclic && j < 0) j += g.Lin;
+                            js[k] = (j >= 0 && j < g.Lin ? j : g.Lin) * g.Nt;
+                        }
+                        const float2* trow = Hm + (size_t)(l * g.Nr + r) * ldt;
+                        for (int c = 0; c < g.Nt; ++c) {
+                            const float2 h = trow[c];
+                            const float p = fmaf(h.x, h.x, h.y * h.y);
+#pragma unroll
+                            for (int k = 0; k < OPK; ++k) {
+                                const float2 x = xh_s[js[k] + c];
+                                av[k] = fmaf(p, var_s[js[k] + c], av[k]);
+                                ar[k] = fmaf(h.x, x.x, fmaf(-h.y, x.y, ar[k]));
+                                ai[k] = fmaf(h.x, x.y, fmaf(h.y, x.x, ai[k]));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < OPK; ++k)
+                        if (i0 + k < g.Lout) row_update((i0 + k) * g.Nr + r, av[k], ar[k], ai[k]);
                 }
             }
             __syncthreads();
             // ---- column pass: cov = 1/(|H|^2^T (1/u)), xmap = xhat + cov * H^H((y-z)/u) (bamp.py:62-63)
-            for (int j = tid; j < N; j += blockDim.x) {
-                float ac = 0.f, ar = 0.f, ai = 0.f;
-                for (int i = 0; i < n; ++i) {
-                    const float2 h = Hm[(size_t)i * N + j];
-                    const float2 gv = g_s[i];
-                    ac = fmaf(fmaf(h.x, h.x, h.y * h.y), w_s[i], ac);
-                    ar = fmaf(h.x, gv.x, fmaf(h.y, gv.y, ar));
-                    ai = fmaf(h.x, gv.y, fmaf(-h.y, gv.x, ai));
-                }
+            auto col_update = [&](int j, float ac, float ar, float ai) {
                 const float cov = __frcp_rn(ac);
                 const float2 x = xh_s[j];
                 xmap_s[j] = make_float2(fmaf(cov, ar, x.x), fmaf(cov, ai, x.y));
                 cov_s[j] = cov;
+            };
+            if constexpr (OPK == 0) {
+                for (int j = tid; j < N; j += blockDim.x) {
+                    float ac = 0.f, ar = 0.f, ai = 0.f;
+                    for (int i = 0; i < n; ++i) {
+                        const float2 h = Hm[(size_t)i * N + j];
+                        const float2 gv = g_s[i];
+                        ac = fmaf(fmaf(h.x, h.x, h.y * h.y), w_s[i], ac);
+                        ar = fmaf(h.x, gv.x, fmaf(h.y, gv.y, ar));
+                        ai = fmaf(h.x, gv.y, fmaf(-h.y, gv.x, ai));
+                    }
+                    col_update(j, ac, ar, ai);
+                }
+            } else {
+                // out(j, t) = sum_l sum_r conj(g_l[r][t]) q(j + l, r): thread = (tile of OPK input slots, transmit antenna t)
+                const int tiles = (g.Lin + OPK - 1) / OPK;
+                for (int w = tid; w < tiles * g.Nt; w += blockDim.x) {
+                    const int tx = w % g.Nt, j0 = (w / g.Nt) * OPK;
+                    float ac[OPK], ar[OPK], ai[OPK];
+#pragma unroll
+                    for (int k = 0; k < OPK; ++k) ac[k] = ar[k] = ai[k] = 0.f;
+                    for (int l = 0; l < a.Lh; ++l) {
+                        int is[OPK];
+#pragma unroll
+                        for (int k = 0; k < OPK; ++k) {
+                            int i = j0 + k + l;
+                            if (a.cyclic && i >= g.Lin) i -= g.Lin;
+                            is[k] = (i < g.Lout ? i : g.Lout) * g.Nr;
+                        }
+                        const float2* tcol = Hm + (size_t)l * g.Nr * ldt + tx;
+                        for (int r = 0; r < g.Nr; ++r) {
+                            const float2 h = tcol[(size_t)r * ldt];
+                            const float p = fmaf(h.x, h.x, h.y * h.y);
+#pragma unroll
+                            for (int k = 0; k < OPK; ++k) {
+                                const float2 gv = g_s[is[k] + r];
+                                ac[k] = fmaf(p, w_s[is[k] + r], ac[k]);
+                                ar[k] = fmaf(h.x, gv.x, fmaf(h.y, gv.y, ar[k]));
+                                ai[k] = fmaf(h.x, gv.y, fmaf(-h.y, gv.x, ai[k]));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < OPK; ++k)
+                        if (j0 + k < g.Lin) col_update((j0 + k) * g.Nt + tx, ac[k], ar[k], ai[k]);
+                }
             }
             __syncthreads();
             // ---- denoiser (bamp.py:66-77): tau = cov/2
@@ -255,18 +350,25 @@ int launch_bamp_generic(const BampArgs& args, bool exp64, cudaStream_t stream) {
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     BampArgs a = args;
     const Geom& g = a.g;
-    // bulk TMA needs 16-byte aligned, 16-byte multiple transfers
-    const bool tma_ok = ((size_t)g.n * g.N * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.H) % 16) == 0 &&
-                        ((size_t)a.H_stride * 8) % 16 == 0 && (size_t)g.n * g.N * 8 < (1u << 20);
-    BampPlan plan = bamp_plan(g, tma_ok, exp64);
-    a.stage_H = tma_ok && plan.total <= (size_t)smem_max;
-    if (!a.stage_H) plan = bamp_plan(g, false, exp64);
+    const int Lh = a.taps ? a.Lh : 0;
+    if (Lh) { a.H = a.taps; a.H_stride = a.taps_stride; }
+    // dense: bulk TMA needs 16-byte aligned, 16-byte multiple transfers; taps are staged by plain loads
+    const bool stage_ok = Lh ? true
+                             : ((size_t)g.n * g.N * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.H) % 16) == 0 &&
+                                   ((size_t)a.H_stride * 8) % 16 == 0 && (size_t)g.n * g.N * 8 < (1u << 20);
+    BampPlan plan = bamp_plan(g, stage_ok, exp64, Lh);
+    a.stage_H = stage_ok && plan.total <= (size_t)smem_max;
+    if (!a.stage_H) plan = bamp_plan(g, false, exp64, Lh);
     if (plan.total > (size_t)smem_max) {
         set_error("BAMP generic kernel: per-frame vectors need %zu B of shared memory (> %d B)", plan.total, smem_max);
         return AMPSM_ENOFIT;
     }
     const int threads = g.N >= 128 ? 256 : (g.N >= 64 ? 128 : ((long long)g.n * g.N <= 64 ? 32 : 64));
-    auto kern = exp64 ? bamp_generic_kernel<true> : bamp_generic_kernel<false>;
+    // structured operator: four time slots per thread when that still gives every thread a work item in the row pass
+    const int opk = !Lh ? 0 : (((g.Lout + 3) / 4) * g.Nr >= threads / 2 ? 4 : 1);
+    auto kern = opk == 0 ? (exp64 ? bamp_generic_kernel<true, 0> : bamp_generic_kernel<false, 0>)
+              : opk == 1 ? (exp64 ? bamp_generic_kernel<true, 1> : bamp_generic_kernel<false, 1>)
+                         : (exp64 ? bamp_generic_kernel<true, 4> : bamp_generic_kernel<false, 4>);
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total),
                            "cudaFuncSetAttribute(bamp_generic)"))
         return e;

@@ -257,6 +257,29 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     return launch_bamp_generic(k, p->exp_f64 != 0, st);
 }
 
+int ampsm_bamp_detect_taps(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* taps,
+                           int64_t taps_frame_stride, int32_t Lh, int32_t cyclic, const void* y, double sigma2,
+                           const float* sigma2_per_frame, const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                           void* xmap, void* xmmse, float* var, int32_t* iters, float* traj, uint64_t* counters, void* stream) {
+    BampArgs k{};
+    if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || (frames > 0 && (!taps || !y))) { set_error("BAMP taps: taps / y is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (Lh < 1 || (cyclic != 0 && cyclic != 1)) { set_error("BAMP taps: Lh < 1 or cyclic not in {0, 1}"); return AMPSM_EINVAL; }
+    if (cyclic && (p->Lout != p->Lin || Lh > p->Lin)) { set_error("BAMP taps: cyclic operator needs Lout == Lin and Lh <= Lin"); return AMPSM_EINVAL; }
+    if (!cyclic && (p->Lout < p->Lin || p->Lout > p->Lin + Lh - 1)) { set_error("BAMP taps: Lout=%d outside Lin..Lin+Lh-1", p->Lout); return AMPSM_EINVAL; }
+    const int64_t tap_elems = (int64_t)Lh * p->Nr * p->Nt;
+    if (taps_frame_stride != 0 && taps_frame_stride < tap_elems) { set_error("BAMP taps: taps_frame_stride smaller than Lh*Nr*Nt"); return AMPSM_EINVAL; }
+    if (p->kernel > 1) { set_error("BAMP taps: the structured operator runs in the generic kernel only"); return AMPSM_ENOFIT; }
+    if (frames == 0) return 0;
+    k.taps = (const float2*)taps; k.taps_stride = taps_frame_stride; k.Lh = Lh; k.cyclic = cyclic;
+    k.y = (const float2*)y; k.sigma2 = (float)sigma2; k.sigma2_pf = sigma2_per_frame;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
+    return launch_bamp_generic(k, p->exp_f64 != 0, (cudaStream_t)stream);
+}
+
 int ampsm_bamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H,
                            int64_t H_frame_stride, const void* y, double sigma2, const float* sigma2_per_frame,
                            const void* x_true, const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse,

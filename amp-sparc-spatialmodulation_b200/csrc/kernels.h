@@ -34,6 +34,11 @@ struct BampArgs {
     float* traj;
     long long frames;
     int stage_H;
+    // structured (block-Toeplitz) operator of ampsm_bamp_detect_taps, generic kernel only; taps == nullptr: dense H
+    const float2* taps;          // [Lh][Nr][Nt], block (i, j) of H = taps[i - j]
+    long long taps_stride;       // complex elements between frames, 0 = shared
+    int Lh;
+    int cyclic;                  // 1: i - j is taken modulo Lin (channel_truncation 'cyclic', channel.py:67-72)
 };
 
 struct VampArgs {

@@ -104,6 +104,24 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
                       void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
                       uint64_t* counters, void* stream);
 
+/*
+ * BAMP on a structured ISI channel -- same detector as ampsm_bamp_detect (bamp.py:116-143), with the reference's
+ * block-Toeplitz matrix (channel.py:53-72 generate_channel, 85-91 generate_as_sparc) given by its taps instead of the
+ * dense (Nr*Lout) x (Nt*Lin) array: block (i, j) of H (output slot i, input slot j) is taps[i - j] for 0 <= i - j < Lh
+ * and zero otherwise; with cyclic = 1 the difference is taken modulo Lin (channel_truncation 'cyclic').  'trunc' is
+ * Lout = Lin, 'tail' is Lout = Lin + Lh - 1, both with cyclic = 0.
+ *   taps : complex64 [Lh][Nr][Nt] shared by all frames (taps_frame_stride = 0) or [frames][Lh][Nr][Nt]
+ *          (stride in complex elements); the scaling of channel.py:55 / 87-91 (sqrt(W) h) already applied.
+ * Every other argument as ampsm_bamp_detect.  H, H^H, |H|^2 and |H|^2^T are applied as block convolutions from the taps
+ * held in shared memory: Lh*Nr*Nt*8 bytes per frame instead of n*N*8 (24 x 128 x 3 taps: 72 KiB vs 25 MiB at Lin = 32).
+ */
+int ampsm_bamp_detect_taps(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                           const void* taps, int64_t taps_frame_stride, int32_t Lh, int32_t cyclic, const void* y,
+                           double sigma2, const float* sigma2_per_frame,
+                           const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                           void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                           uint64_t* counters, void* stream);
+
 int ampsm_bamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
                            const void* H, int64_t H_frame_stride, const void* y,
                            double sigma2, const float* sigma2_per_frame,

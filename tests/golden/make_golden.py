@@ -53,7 +53,7 @@ def batch_loss(config_args, frames, xmap, xmmse, x, sym, idx, N):
     return loss_vec(L), gidx
 
 
-def run_bamp(name, args, kwargs, snrs_db, frames, seed, matrix='channel'):
+def run_bamp(name, args, kwargs, snrs_db, frames, seed, matrix='channel', taps_only=False):
     c = cfg(*args, **kwargs)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -79,7 +79,20 @@ def run_bamp(name, args, kwargs, snrs_db, frames, seed, matrix='channel'):
                     break
             L = amp(H, y, snr, x, s, i)                      # the stock forward; must agree with the stepping
             assert L.loss['T'] == t + 1
-            for k, v in (('H', H.numpy()), ('y', y.numpy().reshape(n)), ('x', x.numpy().reshape(N)), ('sym', s),
+            Hstore = H.numpy()
+            if taps_only:
+                # large ISI matrices: keep only the first block column (the Lh tap matrices); the reference's H is
+                # exactly the block-Toeplitz matrix of these taps, checked here before anything is written
+                Hn, (Nr, Nt, Lin, Lout, Lh) = H.numpy(), (c.Nr, c.Nt, c.Lin, c.Lout, c.Lh)
+                Hstore = np.stack([Hn[l * Nr:(l + 1) * Nr, :Nt] for l in range(Lh)])
+                re = np.zeros_like(Hn)
+                for io in range(Lout):
+                    for ji in range(Lin):
+                        d = (io - ji) % Lin if c.trunc == 'cyclic' and matrix == 'channel' else io - ji
+                        if 0 <= d < Lh:
+                            re[io * Nr:(io + 1) * Nr, ji * Nt:(ji + 1) * Nt] = Hstore[d]
+                assert np.array_equal(re, Hn)
+            for k, v in (('H', Hstore), ('y', y.numpy().reshape(n)), ('x', x.numpy().reshape(N)), ('sym', s),
                          ('idx', i), ('sigma2', amp.E / snr), ('snr_db', snr_db), ('xmap', tr.xmap.numpy().reshape(N)),
                          ('xmmse', tr.xmmse.numpy().reshape(N)), ('var', tr.var.numpy().reshape(N)), ('iters', t + 1),
                          ('tau', tau), ('varm', varm), ('mse', mse), ('loss', loss_vec(L))):
@@ -255,6 +268,13 @@ if __name__ == "__main__":
     # multi-section ISI frame, matrix drawn as in bamp_model.py:56 (generate_as_sparc)
     if want('bamp_isi'):
         run_bamp('bamp_isi', (16, 2, 8, 3, 2, 'QPSK'), dict(trunc='tail'), [2, 8], 12, seed=1, matrix='sparc')
+    # structured-operator fixtures (taps only): cyclic and truncated convolution; a frame large enough for the four-slot tiles
+    if want('bamp_isi_cyc'):
+        run_bamp('bamp_isi_cyc', (32, 2, 12, 8, 3, 'QPSK'), dict(trunc='cyclic'), [4, 9], 6, seed=21, taps_only=True)
+    if want('bamp_isi_trunc'):
+        run_bamp('bamp_isi_trunc', (32, 2, 12, 8, 3, 'QPSK'), dict(trunc='trunc'), [4, 9], 6, seed=22, matrix='sparc', taps_only=True)
+    if want('bamp_isi_big'):
+        run_bamp('bamp_isi_big', (64, 4, 24, 24, 3, 'QPSK'), dict(trunc='tail'), [3, 7], 3, seed=23, taps_only=True)
     # 'segmented' decision rule (B=1 only in the reference)
     if want('bamp_seg'):
         run_bamp('bamp_seg', (16, 2, 8, 3, 2, '8PSK'), dict(trunc='tail', mode='segmented'), [4, 10], 8, seed=2, matrix='sparc')

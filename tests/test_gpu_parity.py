@@ -300,3 +300,72 @@ def test_shrink_family_matches_reference_goldens():
         pkg.Shrink(cq, "shrink")(rq, cvq)
     with pytest.raises(AttributeError):
         pkg.Shrink(cq, "lasso")(rq, cvq)
+
+
+ISI_TAPS = ["bamp_isi_cyc", "bamp_isi_trunc", "bamp_isi_big"]
+
+
+@pytest.mark.parametrize("name", ISI_TAPS)
+@pytest.mark.parametrize("exp", ["f64", "f32"])
+def test_bamp_structured_operator_matches_reference_goldens(name, exp):
+    """ampsm_bamp_detect_taps (block-convolution operator from the Lh tap matrices; cyclic / truncated / tail layouts of
+    channel.py:56-72, 89-91; one- and four-slot tiles) against the reference run on the dense matrix: exit iteration
+    within 1, trajectories within the tolerances of parity_utils, every error count identical.  The dense kernel on the
+    rebuilt matrix must take the same decisions, and BAMP.forward on a dense block-Toeplitz matrix must route itself
+    through the structured operator."""
+    from amp_sparc_spatialmodulation_b200.bamp import matrix_from_taps, taps_from_matrix
+    g = load_golden(name)
+    F, N = g["x"].shape
+    cyclic = g["meta"]["kwargs"].get("trunc") == "cyclic" and g["meta"]["matrix"] == "channel"
+    for snr_db in sorted(set(g["snr_db"].tolist())):
+        sel = np.nonzero(g["snr_db"] == snr_db)[0]
+        cfg = config_from_meta(g["meta"], batch=len(sel), device=DEV)
+        idx = (g["idx"][sel].reshape(len(sel), -1) + (np.arange(len(sel)) * N)[:, None]).reshape(-1)
+        args = (t(g["y"][sel]).unsqueeze(-1), 10 ** (snr_db / 10), t(g["x"][sel]).unsqueeze(-1), g["sym"][sel].reshape(-1), idx)
+        amp = pkg.BAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section")
+        taps = t(g["H"][sel])                                            # (frames, Lh, Nr, Nt)
+        d = amp.detect_taps(taps, *args, cyclic=cyclic)
+        iters = d.iters.cpu().numpy()
+        assert np.abs(iters - g["iters"][sel]).max() <= 1, (iters, g["iters"][sel])
+        per_frame = np.abs(d.xmmse.cpu().numpy().reshape(len(sel), N) - g["xmmse"][sel]).max(axis=1)
+        assert per_frame.max() < 1e-2 and np.median(per_frame) < 1e-4
+        tr = d.traj.cpu().numpy()
+        check_trajectory(name + ".tau", tr[:, :, 0], g["tau"][sel])
+        check_trajectory(name + ".var", tr[:, :, 1], g["varm"][sel])
+        xmap = d.xmap.cpu().numpy().reshape(len(sel), N)
+        assert decision_mismatch_frames(cfg, xmap, g["xmap"][sel]).size == 0
+        want = counters_for(cfg, g["xmap"][sel], g["xmmse"][sel], g["x"][sel], g["sym"][sel], idx)
+        assert_counts_equal(f"{name}@{snr_db}dB taps", d.counters_dict(), want)
+        # dense kernel on the rebuilt matrix, and the automatic routing of forward()
+        H = matrix_from_taps(taps, cfg.Lin, cfg.Lout, cyclic)
+        st = taps_from_matrix(H, cfg)
+        assert st is not None and st[1] == cyclic and torch.equal(st[0], taps)
+        dense = pkg.BAMP(cfg, exp=exp, shift="reference" if exp == "f64" else "section", structured=False).detect(H, *args)
+        assert_counts_equal(f"{name}@{snr_db}dB dense", dense.counters_dict(), want)
+        assert np.abs(dense.xmmse.cpu().numpy().reshape(len(sel), N) - g["xmmse"][sel]).max() < 1e-2
+        auto = pkg.BAMP(cfg, exp=exp, shift="reference" if exp == "f64" else "section").detect(H, *args)
+        assert torch.equal(auto.xmmse, d.xmmse) and torch.equal(auto.iters, d.iters)
+
+
+def test_bamp_structured_operator_shared_taps_and_unstructured_matrix():
+    """One tap set shared by the frames of a call (taps_frame_stride = 0) equals per-frame copies; a dense matrix that is
+    not block-Toeplitz stays on the dense kernel."""
+    from amp_sparc_spatialmodulation_b200.bamp import matrix_from_taps, taps_from_matrix
+    g = load_golden("bamp_isi_cyc")
+    F, N = g["x"].shape
+    cfg = config_from_meta(g["meta"], batch=F, device=DEV)
+    taps = t(g["H"][0])
+    H = matrix_from_taps(taps, cfg.Lin, cfg.Lout, True)
+    x = t(g["x"])
+    y = (H @ x.T).T.contiguous() + 0.05 * t(g["y"])
+    idx = global_idx(g, N)
+    amp = pkg.BAMP(cfg)
+    a = amp.detect_taps(taps, y.unsqueeze(-1), 10.0, x.unsqueeze(-1), g["sym"].reshape(-1), idx, cyclic=True)
+    b = amp.detect_taps(taps.expand(F, *taps.shape).contiguous(), y.unsqueeze(-1), 10.0, x.unsqueeze(-1), g["sym"].reshape(-1),
+                        idx, cyclic=True)
+    assert torch.equal(a.xmmse, b.xmmse) and a.counters_dict() == b.counters_dict()
+    Hb = H.clone()
+    Hb[0, -1] += 0.25
+    assert taps_from_matrix(Hb, cfg) is None
+    c = amp.detect(Hb, y.unsqueeze(-1), 10.0, x.unsqueeze(-1), g["sym"].reshape(-1), idx)
+    assert c.counters_dict()["frames"] == F

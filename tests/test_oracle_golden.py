@@ -183,3 +183,22 @@ def test_shrink_oracle_matches_reference():
     assert np.abs(e - g["ook_exp"]).max() < 1e-6 and abs(dxdr - g["ook_dxdr"]) < 1e-6 * abs(g["ook_dxdr"]) + 1e-8
     E, V = ao.shrink_sw_ook(g["r_o"], g["cov_o"], co.Na * co.Lin, co.Nt // co.Na)
     assert np.abs(E - g["sw_exp"]).max() < 1e-6 and np.abs(V - g["sw_var"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["bamp_isi_cyc", "bamp_isi_trunc", "bamp_isi_big"])
+def test_bamp_oracle_matches_reference_on_structured_isi(name):
+    """Fixtures that store only the Lh tap matrices of the reference's block-Toeplitz H (channel.py:56-72, 89-91): the
+    dense matrix rebuilt by matrix_from_taps drives the oracle to the reference's trajectories and estimates."""
+    import torch
+    from amp_sparc_spatialmodulation_b200.bamp import matrix_from_taps
+    g = load_golden(name)
+    cfg = config_from_meta(g["meta"])
+    cyclic = g["meta"]["kwargs"].get("trunc") == "cyclic" and g["meta"]["matrix"] == "channel"
+    H = matrix_from_taps(torch.as_tensor(g["H"]), cfg.Lin, cfg.Lout, cyclic).numpy()
+    r = ao.bamp_detect(H, g["y"], g["sigma2"], cfg.symbols, cfg.L, cfg.M, cfg.N_Layers, x_true=g["x"])
+    assert np.abs(r["iters"] - g["iters"]).max() <= 1
+    per_frame = np.abs(r["xmmse"] - g["xmmse"]).max(axis=1)
+    assert per_frame.max() < 1e-2 and np.median(per_frame) < 1e-4
+    check_trajectory(name + ".tau", r["traj"]["tau"].T, g["tau"])
+    check_trajectory(name + ".var", r["traj"]["var"].T, g["varm"])
+    assert decision_mismatch_frames(cfg, r["xmap"], g["xmap"]).size == 0
