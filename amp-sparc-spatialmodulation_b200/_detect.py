@@ -9,6 +9,7 @@ from torch import nn
 from . import _cabi
 from .config import Config
 from .loss import Loss
+from ._tensors import dense, ptr  # noqa: F401  (re-exported for the detector modules)
 
 
 @dataclass
@@ -83,7 +84,3 @@ class Detector(nn.Module):
         T = c['iters'] / max(c['frames'], 1)
         self.L.record(c, int(T) if float(T).is_integer() else T)
         return self.L
-
-
-def ptr(t):
-    return None if t is None else t.data_ptr()

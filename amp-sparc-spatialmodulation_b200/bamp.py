@@ -9,7 +9,7 @@ persistent CUDA kernel (csrc/bamp_generic.cu, csrc/bamp_fast.cu) reached through
 import torch
 
 from . import _cabi
-from ._detect import Detection, Detector, ptr
+from ._detect import Detection, Detector, ptr, dense
 
 
 def matrix_from_taps(taps: torch.Tensor, Lin: int, Lout: int, cyclic: bool = False) -> torch.Tensor:
@@ -58,9 +58,9 @@ class BAMP(Detector):
         dev = self._cuda_device(y, taps)
         cfg = self.config
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
-        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        y = dense(y, dev, torch.complex64, -1, n)
         F = y.shape[0]
-        taps = taps.to(dev, torch.complex64).contiguous()
+        taps = dense(taps, dev, torch.complex64)
         Lh = taps.shape[-3]
         if tuple(taps.shape[-2:]) != (cfg.Nr, cfg.Nt) or taps.dim() not in (3, 4) or (taps.dim() == 4 and taps.shape[0] != F):
             raise RuntimeError(f"taps must be (Lh, {cfg.Nr}, {cfg.Nt}) or ({F}, Lh, {cfg.Nr}, {cfg.Nt}); got {tuple(taps.shape)}")
@@ -77,7 +77,7 @@ class BAMP(Detector):
 
     def _alloc(self, F, N, x, symbols, indices, dev):
         cfg = self.config
-        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        xt = None if x is None else dense(x, dev, torch.complex64, -1, N)
         sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
         counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
         iters = torch.empty(F, dtype=torch.int32, device=dev)
@@ -92,9 +92,9 @@ class BAMP(Detector):
         dev = self._cuda_device(y, H)
         cfg = self.config
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
-        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        y = dense(y, dev, torch.complex64, -1, n)
         F = y.shape[0]
-        H = H.to(dev, torch.complex64).contiguous()
+        H = dense(H, dev, torch.complex64)
         if self.structured and cfg.Lin > 1 and self.kernel in ('auto', 'generic') and H.dim() in (2, 3):
             st = taps_from_matrix(H, cfg)
             if st is not None:

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from ._tensors import dense
 from .config import Config
 
 
@@ -80,9 +81,9 @@ class Loss:
         lib = _cabi.lib()
         dev = xmap.device if xmap.is_cuda else torch.device('cuda', torch.cuda.current_device())
         N = self.Nt * self.Lin
-        xm = xmap.to(dev, torch.complex64).reshape(-1, N).contiguous()
-        xe = xmmse.to(dev, torch.complex64).reshape(-1, N).contiguous()
-        xt = x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        xm = dense(xmap, dev, torch.complex64, -1, N)
+        xe = dense(xmmse, dev, torch.complex64, -1, N)
+        xt = dense(x, dev, torch.complex64, -1, N)
         F = xt.shape[0]
         sym = torch.as_tensor(np.ascontiguousarray(symbols, dtype=np.int64)).to(dev)
         idx = torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)).to(dev)

@@ -7,7 +7,7 @@ shared by the F frames of the call, so both mat-vecs of an iteration become comp
 import torch
 
 from . import _cabi
-from ._detect import Detection, Detector, ptr
+from ._detect import Detection, Detector, ptr, dense
 
 
 class SCAMP(Detector):
@@ -15,13 +15,13 @@ class SCAMP(Detector):
         dev = self._cuda_device(y, A)
         cfg = self.config
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
-        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        y = dense(y, dev, torch.complex64, -1, n)
         F = y.shape[0]
-        W = W.to(dev, torch.float32).contiguous()
-        A = A.to(dev, torch.complex64).contiguous()
+        W = dense(W, dev, torch.float32)
+        A = dense(A, dev, torch.complex64)
         if tuple(A.shape) != (n, N) or tuple(W.shape) != (cfg.Lout, cfg.Lin):
             raise RuntimeError(f"expected W ({cfg.Lout}, {cfg.Lin}) and A ({n}, {N}); got {tuple(W.shape)}, {tuple(A.shape)}")
-        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        xt = None if x is None else dense(x, dev, torch.complex64, -1, N)
         sym, idx = self._labels(symbol, index, dev) if xt is not None else (None, None)
         counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
         iters = torch.empty(F, dtype=torch.int32, device=dev)

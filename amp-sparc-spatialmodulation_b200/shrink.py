@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from ._detect import Detector
+from ._detect import Detector, dense
 from .config import Config
 
 _KINDS = ("bayes", "shrink", "lasso", "shrinkOOK")
@@ -30,7 +30,7 @@ class Shrink(nn.Module):
     def _run(self, kind, r, cov):
         dev = Detector._cuda_device(r, cov)
         shape = tuple(r.shape)
-        rc64 = r.to(dev, torch.complex64).contiguous()
+        rc64 = dense(r, dev, torch.complex64)
         cov = torch.as_tensor(cov, dtype=torch.float32).to(dev)
         if cov.numel() == 1:
             stride, covf = 0, cov.reshape(1).contiguous()

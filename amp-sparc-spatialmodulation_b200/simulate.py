@@ -9,8 +9,10 @@ and scored by their fused Loss epilogue; frames are sharded over the ranks of ``
 (SURVEY.md section 8e).  Rank 0 turns the counters into the reference's 14 rates and writes ``<path>/<EbN0dB>.json`` with
 the reference's schema (loss.py:304-323); the sweep stops early once FER < 1e-3 (bamp_model.py:66).
 
-Channels (``Lin = Lh = 1``, one matrix per frame):
-  'iid'        H ~ CN(0, 1/Nr) i.i.d.                                     (channel.py:97-101, generate_as_random)
+Channels (one draw per frame):
+  'iid'        H ~ CN(0, 1/Nr) i.i.d.; with Lin > 1 or Lh > 1 the frame is an ISI block: Lh tap matrices
+               ~ CN(0, pdp_l Lout / (Nr Lin)) as channel.py:53-55, applied as a (truncated / tail / cyclic) block
+               convolution -- the dense block-Toeplitz matrix is never formed (BAMP.detect_taps)
   'kronecker'  H = Rr^(1/2) G Rt^(1/2), G i.i.d. CN(0, 1/Nr), exponential correlation R[i,j] = rho^|i-j|
                -- BASELINE.json config 5; the reference has no correlated generator
 Detectors: 'bamp' (H as is), 'vamp' (batched Jacobi SVD of every H on the device + iterations, one C-ABI call).
@@ -53,7 +55,9 @@ def device_frames(cfg: Config, frames: int, snr: float, gen: torch.Generator, ch
     """One chunk of frames on the generator's device: per-frame H (frames, n, N), y (frames, n), x (frames, N), Gray labels
     (frames * L,) and flat non-zero positions (frames * L,) as Data.generate_message returns them (data.py:74-91)."""
     if cfg.Lin != 1 or cfg.Lh != 1:
-        raise _cabi.AmpsmError("device_frames generates one flat-fading matrix per frame (Lin = Lh = 1)")
+        if channel != 'iid':
+            raise _cabi.AmpsmError("ISI frames (Lin > 1 or Lh > 1) are generated with i.i.d. taps only")
+        return device_isi_frames(cfg, frames, snr, gen)
     dev = gen.device
     n, N, M, L = cfg.n, cfg.N, cfg.M, cfg.L
     H = torch.view_as_complex(torch.randn(frames, n, N, 2, device=dev, generator=gen) * float(np.sqrt(1 / cfg.Nr / 2)))
@@ -76,6 +80,38 @@ def device_frames(cfg: Config, frames: int, snr: float, gen: torch.Generator, ch
     return H.contiguous(), y.contiguous(), x, gray[k].reshape(-1).contiguous(), idx
 
 
+def device_isi_frames(cfg: Config, frames: int, snr: float, gen: torch.Generator):
+    """ISI frames on the generator's device: per-frame taps (frames, Lh, Nr, Nt) with the scaling of channel.py:55
+    (uniform or exponential power-delay profile), y = block convolution of the message with the taps ('trunc', 'tail' or
+    'cyclic', channel.py:56-72) + noise.  Returns (taps, y, x, labels, flat indices) like device_frames; the first element
+    goes to BAMP.detect_taps instead of BAMP.detect."""
+    dev = gen.device
+    Nt, Nr, Lin, Lout, Lh, M, L, N, n = cfg.Nt, cfg.Nr, cfg.Lin, cfg.Lout, cfg.Lh, cfg.M, cfg.L, cfg.N, cfg.n
+    pdp = np.exp(-np.arange(Lh)) if cfg.profile == 'exponential' else np.ones(Lh)
+    pdp = pdp / pdp.sum()
+    scale = torch.as_tensor(np.sqrt(pdp * Lout / Nr / Lin / 2), dtype=torch.float32, device=dev)
+    taps = torch.view_as_complex((torch.randn(frames, Lh, Nr, Nt, 2, device=dev, generator=gen)
+                                  * scale[None, :, None, None, None]).contiguous())
+    ant = torch.randint(0, M, (frames, L), device=dev, generator=gen)
+    k = torch.randint(0, cfg.K, (frames, L), device=dev, generator=gen)
+    sym = torch.as_tensor(np.asarray(cfg.symbols)).to(dev, torch.complex64)
+    gray = torch.as_tensor(np.asarray(cfg.gray)).to(dev, torch.int64)
+    pos = ant + torch.arange(L, device=dev) * M                            # section s covers entries [s M, (s+1) M)
+    x = torch.zeros(frames, N, dtype=torch.complex64, device=dev)
+    x.scatter_(1, pos, sym[k])
+    xs = x.view(frames, Lin, Nt)
+    y = torch.zeros(frames, Lin + Lh - 1, Nr, dtype=torch.complex64, device=dev)     # full linear convolution
+    for l in range(Lh):                                                    # out slot i = in slot j + l
+        y[:, l:l + Lin] += torch.einsum('frt,fjt->fjr', taps[:, l], xs)
+    if cfg.trunc == 'cyclic':                                              # the post-transient wraps to the first slots
+        y[:, :Lh - 1] += y[:, Lin:]
+    y = y[:, :Lout].reshape(frames, n)
+    sigma2 = (cfg.Na / cfg.Nr) / snr
+    y = y + torch.view_as_complex(torch.randn(frames, n, 2, device=dev, generator=gen) * float(np.sqrt(sigma2 / 2)))
+    idx = (pos + torch.arange(frames, device=dev)[:, None] * N).reshape(-1).contiguous()
+    return taps, y.contiguous(), x, gray[k].reshape(-1).contiguous(), idx
+
+
 class MonteCarlo:
     """SNR sweep of one detector over device-generated frames, sharded over the ranks of torch.distributed."""
 
@@ -89,6 +125,8 @@ class MonteCarlo:
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.rate = config.code_rate
         self.min_snr = config.shannon_limit_dB                              # bamp_model.py:27
+        if (config.Lin != 1 or config.Lh != 1) and algorithm != 'bamp':
+            raise ValueError("ISI frames (Lin > 1 or Lh > 1) run through BAMP's structured operator only")
         if algorithm == 'bamp':
             self.amp = BAMP(config, outputs=False, **detector_kw)
         elif algorithm == 'vamp':
@@ -108,7 +146,9 @@ class MonteCarlo:
         while f0 < hi:
             nf = min(self.chunk, hi - f0)
             H, y, x, lab, idx = device_frames(self.config, nf, snr, gen, self.channel, self.rho_t, self.rho_r)
-            if self.algorithm == 'bamp':
+            if self.algorithm == 'bamp' and H.dim() == 4:                  # ISI frames: H holds the taps
+                det = self.amp.detect_taps(H, y, snr, x, lab, idx, cyclic=self.config.trunc == 'cyclic', frame_base=0)
+            elif self.algorithm == 'bamp':
                 det = self.amp.detect(H, y, snr, x, lab, idx, frame_base=0)
             else:
                 det = self.amp.detect_from_channel(H, y, snr, x, lab, idx, frame_base=0)
@@ -179,6 +219,9 @@ def main(argv=None):
     ap.add_argument("--Nt", type=int, default=64)
     ap.add_argument("--Na", type=int, default=1)
     ap.add_argument("--Nr", type=int, default=32)
+    ap.add_argument("--Lin", type=int, default=1, help="time slots per frame (block length)")
+    ap.add_argument("--Lh", type=int, default=1, help="channel taps (ISI when > 1)")
+    ap.add_argument("--truncation", default="trunc", choices=["trunc", "tail", "cyclic"])
     ap.add_argument("--alphabet", default="16QAM")
     ap.add_argument("--iterations", type=int, default=20)
     ap.add_argument("--frames", type=int, default=1 << 20, help="frames per SNR point (all ranks together)")
@@ -197,8 +240,8 @@ def main(argv=None):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = Config(a.Nt, a.Na, a.Nr, 1, 1, batch=a.chunk, generator_mode='sparc', iterations=a.iterations, alphabet=a.alphabet,
-                 channel_profile='uniform', device=f"cuda:{local}")
+    cfg = Config(a.Nt, a.Na, a.Nr, a.Lin, a.Lh, batch=a.chunk, generator_mode='sparc', iterations=a.iterations,
+                 alphabet=a.alphabet, channel_profile='uniform', channel_truncation=a.truncation, device=f"cuda:{local}")
     mc = MonteCarlo(cfg, a.alg, frames_per_point=a.frames, chunk=a.chunk, channel=a.channel, rho_t=a.rho_t, rho_r=a.rho_r,
                     seed=a.seed, path=a.path)
     pts = mc.simulate(final=a.final, start=a.start, step=a.step)

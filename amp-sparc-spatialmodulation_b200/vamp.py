@@ -8,7 +8,7 @@ axis.  complex128 factors select the float64 linear stage (the reference fed wit
 import torch
 
 from . import _cabi
-from ._detect import Detection, Detector, ptr
+from ._detect import Detection, Detector, ptr, dense
 
 
 class VAMP(Detector):
@@ -22,9 +22,9 @@ class VAMP(Detector):
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
         dbl = Vh.dtype == torch.complex128
         ct, rt = (torch.complex128, torch.float64) if dbl else (torch.complex64, torch.float32)
-        y = y.to(dev, ct).reshape(-1, n).contiguous()
+        y = dense(y, dev, ct, -1, n)
         F = y.shape[0]
-        U, s, Vh = U.to(dev, ct).contiguous(), s.to(dev, rt).contiguous(), Vh.to(dev, ct).contiguous()
+        U, s, Vh = dense(U, dev, ct), dense(s, dev, rt), dense(Vh, dev, ct)
         R = Vh.shape[-2]
         if tuple(Vh.shape[-2:]) != (R, N) or tuple(U.shape[-2:]) != (n, R) or s.shape[-1] != R:
             raise RuntimeError(f"factor shapes U{tuple(U.shape)} s{tuple(s.shape)} Vh{tuple(Vh.shape)} do not match n={n}, N={N}")
@@ -35,7 +35,7 @@ class VAMP(Detector):
                 return size
             raise RuntimeError(f"factor with shape {tuple(t.shape)} is neither shared nor per-frame for {F} frames")
         sU, ss, sV = stride(U, 2, n * R), stride(s, 1, R), stride(Vh, 2, R * N)
-        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        xt = None if x is None else dense(x, dev, torch.complex64, -1, N)
         sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
         counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
         iters = torch.empty(F, dtype=torch.int32, device=dev)
@@ -61,12 +61,12 @@ class VAMP(Detector):
         dev = self._cuda_device(y, H)
         cfg = self.config
         n, N = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin
-        y = y.to(dev, torch.complex64).reshape(-1, n).contiguous()
+        y = dense(y, dev, torch.complex64, -1, n)
         F = y.shape[0]
-        H = H.to(dev, torch.complex64).contiguous()
+        H = dense(H, dev, torch.complex64)
         if tuple(H.shape) != (F, n, N):
             raise RuntimeError(f"H{tuple(H.shape)} is not ({F}, {n}, {N})")
-        xt = None if x is None else x.to(dev, torch.complex64).reshape(-1, N).contiguous()
+        xt = None if x is None else dense(x, dev, torch.complex64, -1, N)
         sym, idx = self._labels(symbols, indices, dev) if xt is not None else (None, None)
         counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
         iters = torch.empty(F, dtype=torch.int32, device=dev)
@@ -91,7 +91,7 @@ def svd_batched(H, return_sweeps=False):
     vamp_model.py:58 (one-sided Jacobi, one warp per matrix; singular-vector phases differ from LAPACK's)."""
     if not H.is_cuda:
         raise _cabi.AmpsmError("svd_batched runs on the GPU only (no CPU fallback)")
-    H = H.to(torch.complex64).contiguous()
+    H = H.to(torch.complex64).resolve_conj().contiguous()
     F, n, N = H.shape
     U = torch.empty(F, n, n, dtype=torch.complex64, device=H.device)
     s = torch.empty(F, n, dtype=torch.float32, device=H.device)

@@ -166,3 +166,41 @@ def test_device_frames_generator_is_consistent_on_cpu():
     root = exp_corr_root(8, 0.9, 'cpu').to(torch.complex128)
     i = torch.arange(8, dtype=torch.float64)
     assert float(((root @ root).real - 0.9 ** (i[:, None] - i[None, :]).abs()).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("trunc", ["trunc", "tail", "cyclic"])
+def test_device_isi_frames_match_the_dense_block_toeplitz_matrix(trunc):
+    """ISI frames of the sweep driver: y - H x with H rebuilt from the taps (matrix_from_taps, the layout of
+    channel.py:56-72) is pure noise of variance Na/Nr/SNR, and the taps carry the power of channel.py:55."""
+    import torch
+    from amp_sparc_spatialmodulation_b200.bamp import matrix_from_taps
+    from amp_sparc_spatialmodulation_b200.simulate import device_frames
+    cfg = pkg.Config(12, 2, 6, 5, 3, batch=512, generator_mode='sparc', iterations=20, alphabet='QPSK',
+                     channel_profile='exponential', channel_truncation=trunc, device='cpu')
+    gen = torch.Generator(device='cpu').manual_seed(9)
+    snr = 1e6
+    taps, y, x, lab, idx = device_frames(cfg, 512, snr, gen)
+    assert taps.shape == (512, 3, 6, 12) and y.shape == (512, cfg.n)
+    H = matrix_from_taps(taps, cfg.Lin, cfg.Lout, trunc == 'cyclic')
+    resid = y - (H @ x.unsqueeze(-1)).squeeze(-1)
+    sigma2 = (cfg.Na / cfg.Nr) / snr
+    assert float(resid.abs().max()) < 20 * np.sqrt(sigma2) + 1e-5
+    assert torch.equal(x.reshape(-1).nonzero().reshape(-1), idx)
+    pdp = np.exp(-np.arange(3)); pdp /= pdp.sum()
+    power = taps.abs().pow(2).mean(dim=(0, 2, 3)).numpy()
+    assert np.allclose(power, pdp * cfg.Lout / cfg.Nr / cfg.Lin, rtol=0.05)
+
+
+def test_dense_materialises_lazy_conjugate_views():
+    """_tensors.dense: what reaches a kernel pointer is plain memory holding the tensor's VALUES (conj / neg bits resolved)."""
+    import torch
+    from amp_sparc_spatialmodulation_b200._tensors import dense
+    a = torch.randn(3, 5, dtype=torch.complex64)
+    v = a.mH                                                   # conj-view, non-contiguous
+    d = dense(v, 'cpu', torch.complex64)
+    assert v.is_conj() and not d.is_conj() and d.is_contiguous() and torch.equal(d, a.conj().T.contiguous())
+    w = a.conj()                                               # conj-view with contiguous strides: .contiguous() keeps the bit
+    assert w.contiguous().is_conj() and not dense(w, 'cpu', torch.complex64).is_conj()
+    assert np.array_equal(np.frombuffer(dense(w, 'cpu', torch.complex64).numpy().tobytes(), np.complex64),
+                          a.conj().resolve_conj().numpy().ravel())
+    assert dense(a, 'cpu', torch.complex64, -1, 1).shape == (15, 1)
