@@ -8,13 +8,15 @@
 // [Lh][Nr][Nt] live in shared memory (rows padded by one element: conflict-free for both passes) and H, H^H, |H|^2,
 // |H|^2^T are applied as block convolutions: a thread owns TI consecutive time slots of one antenna, so every tap it
 // loads is used TI times and there are no cross-lane reductions.  Slots outside the frame point at a zeroed slot.
+#include <cstdlib>
+
 #include "blockops.cuh"
 #include "kernels.h"
 
 namespace ampsm {
 
 struct BampPlan {
-    size_t H, y, z, g, u, w, xh, xh_new, xmap, var, var_new, cov, scr, red, flags, bc, mbar, total;
+    size_t H, y, z, g, u, w, xh, xmap, var, var_new, cov, scr, red, flags, bc, mbar, total;
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
@@ -39,12 +41,11 @@ __host__ __device__ inline BampPlan bamp_plan(const Geom& g, bool stage, bool ex
     p.u = take((size_t)g.n * 4);
     p.w = take(((size_t)g.n + nz) * 4);
     p.xh = take(((size_t)g.N + Nz) * 8);
-    p.xh_new = take((size_t)g.N * 8);
     p.xmap = take((size_t)g.N * 8);
     p.var = take(((size_t)g.N + Nz) * 4);
     p.var_new = take((size_t)g.N * 4);
     p.cov = take((size_t)g.N * 4);
-    p.scr = take((size_t)g.N * 3 * (exp64 ? 8 : 4));
+    p.scr = take(denoise_scratch_elems(g) * (exp64 ? 8 : 4));
     p.red = take(32 * 3 * 8);
     p.flags = take((size_t)(1 + g.Lin) * 4);
     p.bc = take(sizeof(BlockCounters));
@@ -75,9 +76,11 @@ __device__ inline void block_sum3(double& a, double& b, double& c, double* red) 
     __syncthreads();
 }
 
+constexpr int kWinLh = 4;   // channel lengths up to this use the sliding-window loops of the structured operator
+
 // OPK: 0 dense matrix; otherwise the structured operator with OPK time slots per thread
 template <bool EXP64, int OPK>
-__global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant__ BampArgs a) {
+__global__ void __launch_bounds__(512) bamp_generic_kernel(const __grid_constant__ BampArgs a) {
     using E = typename ExpT<EXP64>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     const Geom& g = a.g;
@@ -91,7 +94,6 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
     float* u_s = reinterpret_cast<float*>(smem + P.u);
     float* w_s = reinterpret_cast<float*>(smem + P.w);
     float2* xh_s = reinterpret_cast<float2*>(smem + P.xh);
-    float2* xhn_s = reinterpret_cast<float2*>(smem + P.xh_new);
     float2* xmap_s = reinterpret_cast<float2*>(smem + P.xmap);
     float* var_s = reinterpret_cast<float*>(smem + P.var);
     float* varn_s = reinterpret_cast<float*>(smem + P.var_new);
@@ -191,24 +193,67 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
                     float av[OPK], ar[OPK], ai[OPK];
 #pragma unroll
                     for (int k = 0; k < OPK; ++k) av[k] = ar[k] = ai[k] = 0.f;
-                    for (int l = 0; l < a.Lh; ++l) {
-                        int js[OPK];                                       // first entry of the input slot (zero slot if none)
+                    if (a.Lh <= kWinLh) {
+                        // sliding window: the OPK outputs and Lh taps touch only OPK + Lh - 1 input slots; each is loaded
+                        // once per column (window entry q = k - l + kWinLh - 1 is input slot i0 + q - (kWinLh - 1))
+                        constexpr int W = OPK + kWinLh - 1;
+                        int jb[W];
 #pragma unroll
-                        for (int k = 0; k < OPK; ++k) {
-                            int j = i0 + k - l;
+                        for (int q = 0; q < W; ++q) {
+                            int j = i0 + q - (kWinLh - 1);
                             if (a.cyclic && j < 0) j += g.Lin;
-                            js[k] = (j >= 0 && j < g.Lin ? j : g.Lin) * g.Nt;
+                            jb[q] = (j >= 0 && j < g.Lin ? j : g.Lin) * g.Nt;
                         }
-                        const float2* trow = Hm + (size_t)(l * g.Nr + r) * ldt;
+                        const int qmin = kWinLh - a.Lh;
+                        const float2* trow = Hm + (size_t)r * ldt;
+                        const size_t tap_stride = (size_t)g.Nr * ldt;
                         for (int c = 0; c < g.Nt; ++c) {
-                            const float2 h = trow[c];
-                            const float p = fmaf(h.x, h.x, h.y * h.y);
+                            float2 h[kWinLh], xw[W];
+                            float p[kWinLh], vw[W];
+#pragma unroll
+                            for (int l = 0; l < kWinLh; ++l)
+                                if (l < a.Lh) {
+                                    h[l] = trow[l * tap_stride + c];
+                                    p[l] = fmaf(h[l].x, h[l].x, h[l].y * h[l].y);
+                                }
+#pragma unroll
+                            for (int q = 0; q < W; ++q)
+                                if (q >= qmin) {
+                                    xw[q] = xh_s[jb[q] + c];
+                                    vw[q] = var_s[jb[q] + c];
+                                }
+#pragma unroll
+                            for (int l = 0; l < kWinLh; ++l)
+                                if (l < a.Lh) {
+#pragma unroll
+                                    for (int k = 0; k < OPK; ++k) {
+                                        const int q = k - l + kWinLh - 1;
+                                        av[k] = fmaf(p[l], vw[q], av[k]);
+                                        ar[k] = fmaf(h[l].x, xw[q].x, fmaf(-h[l].y, xw[q].y, ar[k]));
+                                        ai[k] = fmaf(h[l].x, xw[q].y, fmaf(h[l].y, xw[q].x, ai[k]));
+                                    }
+                                }
+                        }
+                    } else {
+                        for (int l = 0; l < a.Lh; ++l) {
+                            int js[OPK];                                   // first entry of the input slot (zero slot if none)
 #pragma unroll
                             for (int k = 0; k < OPK; ++k) {
-                                const float2 x = xh_s[js[k] + c];
-                                av[k] = fmaf(p, var_s[js[k] + c], av[k]);
-                                ar[k] = fmaf(h.x, x.x, fmaf(-h.y, x.y, ar[k]));
-                                ai[k] = fmaf(h.x, x.y, fmaf(h.y, x.x, ai[k]));
+                                int j = i0 + k - l;
+                                if (a.cyclic && j < 0) j += g.Lin;
+                                js[k] = (j >= 0 && j < g.Lin ? j : g.Lin) * g.Nt;
+                            }
+                            const float2* trow = Hm + (size_t)(l * g.Nr + r) * ldt;
+                            for (int c = 0; c < g.Nt; ++c) {
+                                const float2 h = trow[c];
+                                const float p = fmaf(h.x, h.x, h.y * h.y);
+#pragma unroll
+                                for (int k = 0; k < OPK; ++k) {
+                                    const float2 x = xh_s[js[k] + c];
+                                    av[k] = fmaf(p, var_s[js[k] + c], av[k]);
+                                    ar[k] = fmaf(h.x, x.x, fmaf(-h.y, x.y, ar[k]));
+                                    ai[k] = fmaf(h.x, x.y, fmaf(h.y, x.x, ai[k]));
+                                }
                             }
                         }
                     }
@@ -245,24 +290,66 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
                     float ac[OPK], ar[OPK], ai[OPK];
 #pragma unroll
                     for (int k = 0; k < OPK; ++k) ac[k] = ar[k] = ai[k] = 0.f;
-                    for (int l = 0; l < a.Lh; ++l) {
-                        int is[OPK];
+                    if (a.Lh <= kWinLh) {
+                        // sliding window over the output slots j0 .. j0 + OPK + Lh - 2 (window entry q = k + l)
+                        constexpr int W = OPK + kWinLh - 1;
+                        int ib[W];
 #pragma unroll
-                        for (int k = 0; k < OPK; ++k) {
-                            int i = j0 + k + l;
+                        for (int q = 0; q < W; ++q) {
+                            int i = j0 + q;
                             if (a.cyclic && i >= g.Lin) i -= g.Lin;
-                            is[k] = (i < g.Lout ? i : g.Lout) * g.Nr;
+                            ib[q] = (i < g.Lout ? i : g.Lout) * g.Nr;
                         }
-                        const float2* tcol = Hm + (size_t)l * g.Nr * ldt + tx;
+                        const int qend = OPK + a.Lh - 1;
+                        const float2* tcol = Hm + tx;
+                        const size_t tap_stride = (size_t)g.Nr * ldt;
                         for (int r = 0; r < g.Nr; ++r) {
-                            const float2 h = tcol[(size_t)r * ldt];
-                            const float p = fmaf(h.x, h.x, h.y * h.y);
+                            float2 h[kWinLh], gw[W];
+                            float p[kWinLh], ww[W];
+#pragma unroll
+                            for (int l = 0; l < kWinLh; ++l)
+                                if (l < a.Lh) {
+                                    h[l] = tcol[l * tap_stride + (size_t)r * ldt];
+                                    p[l] = fmaf(h[l].x, h[l].x, h[l].y * h[l].y);
+                                }
+#pragma unroll
+                            for (int q = 0; q < W; ++q)
+                                if (q < qend) {
+                                    gw[q] = g_s[ib[q] + r];
+                                    ww[q] = w_s[ib[q] + r];
+                                }
+#pragma unroll
+                            for (int l = 0; l < kWinLh; ++l)
+                                if (l < a.Lh) {
+#pragma unroll
+                                    for (int k = 0; k < OPK; ++k) {
+                                        const int q = k + l;
+                                        ac[k] = fmaf(p[l], ww[q], ac[k]);
+                                        ar[k] = fmaf(h[l].x, gw[q].x, fmaf(h[l].y, gw[q].y, ar[k]));
+                                        ai[k] = fmaf(h[l].x, gw[q].y, fmaf(-h[l].y, gw[q].x, ai[k]));
+                                    }
+                                }
+                        }
+                    } else {
+                        for (int l = 0; l < a.Lh; ++l) {
+                            int is[OPK];
 #pragma unroll
                             for (int k = 0; k < OPK; ++k) {
-                                const float2 gv = g_s[is[k] + r];
-                                ac[k] = fmaf(p, w_s[is[k] + r], ac[k]);
-                                ar[k] = fmaf(h.x, gv.x, fmaf(h.y, gv.y, ar[k]));
-                                ai[k] = fmaf(h.x, gv.y, fmaf(-h.y, gv.x, ai[k]));
+                                int i = j0 + k + l;
+                                if (a.cyclic && i >= g.Lin) i -= g.Lin;
+                                is[k] = (i < g.Lout ? i : g.Lout) * g.Nr;
+                            }
+                            const float2* tcol = Hm + (size_t)l * g.Nr * ldt + tx;
+                            for (int r = 0; r < g.Nr; ++r) {
+                                const float2 h = tcol[(size_t)r * ldt];
+                                const float p = fmaf(h.x, h.x, h.y * h.y);
+#pragma unroll
+                                for (int k = 0; k < OPK; ++k) {
+                                    const float2 gv = g_s[is[k] + r];
+                                    ac[k] = fmaf(p, w_s[is[k] + r], ac[k]);
+                                    ar[k] = fmaf(h.x, gv.x, fmaf(h.y, gv.y, ar[k]));
+                                    ai[k] = fmaf(h.x, gv.y, fmaf(-h.y, gv.x, ai[k]));
+                                }
                             }
                         }
                     }
@@ -274,11 +361,11 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
             __syncthreads();
             // ---- denoiser (bamp.py:66-77): tau = cov/2
             if (g.decision == 2) {                                   // generator_mode 'random' (bamp.py:46): i.i.d. prior
-                block_denoise_iid(g, al, xmap_s, cov_s, xhn_s, varn_s);
+                block_denoise_iid(g, al, xmap_s, cov_s, xh_s, varn_s);
             } else {
                 double gshift = 0.0;
                 if (EXP64 && g.shift_mode == 1) gshift = block_absmax_exponent(g, al, xmap_s, cov_s, 0.f, true, red);
-                block_denoise<EXP64>(g, al, xmap_s, cov_s, 0.f, true, gshift, xhn_s, varn_s, scr);
+                block_denoise<EXP64>(g, al, xmap_s, cov_s, 0.f, true, gshift, xh_s, varn_s, scr, 1, denoise_scratch_per_warp(g));
             }
             __syncthreads();
             // ---- exit test on var (bamp.py:140) and state update
@@ -294,7 +381,7 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
                     s_tau += cov_s[j];
                     s_var += varn_s[j];
                     if (a.io.x_true) {
-                        const float2 xt = a.io.x_true[f * N + j], xe = xhn_s[j];
+                        const float2 xt = a.io.x_true[f * N + j], xe = xh_s[j];
                         const double dr = (double)xe.x - xt.x, di = (double)xe.y - xt.y;
                         s_mse += dr * dr + di * di;
                     }
@@ -307,10 +394,7 @@ __global__ void __launch_bounds__(256) bamp_generic_kernel(const __grid_constant
                     tr[2] = (float)(s_mse / N);
                 }
             }
-            for (int j = tid; j < N; j += blockDim.x) {
-                xh_s[j] = xhn_s[j];
-                var_s[j] = varn_s[j];
-            }
+            for (int j = tid; j < N; j += blockDim.x) var_s[j] = varn_s[j];
             __syncthreads();
             t_done = t + 1;
             if (g.early_exit && all_close) break;
@@ -363,12 +447,26 @@ int launch_bamp_generic(const BampArgs& args, bool exp64, cudaStream_t stream) {
         set_error("BAMP generic kernel: per-frame vectors need %zu B of shared memory (> %d B)", plan.total, smem_max);
         return AMPSM_ENOFIT;
     }
-    const int threads = g.N >= 128 ? 256 : (g.N >= 64 ? 128 : ((long long)g.n * g.N <= 64 ? 32 : 64));
-    // structured operator: four time slots per thread when that still gives every thread a work item in the row pass
-    const int opk = !Lh ? 0 : (((g.Lout + 3) / 4) * g.Nr >= threads / 2 ? 4 : 1);
-    auto kern = opk == 0 ? (exp64 ? bamp_generic_kernel<true, 0> : bamp_generic_kernel<false, 0>)
-              : opk == 1 ? (exp64 ? bamp_generic_kernel<true, 1> : bamp_generic_kernel<false, 1>)
-                         : (exp64 ? bamp_generic_kernel<true, 4> : bamp_generic_kernel<false, 4>);
+    int threads = g.N >= 128 ? 256 : (g.N >= 64 ? 128 : ((long long)g.n * g.N <= 64 ? 32 : 64));
+    // structured operator: frames this large leave one CTA per SM (shared memory), so give it 16 warps; then the most time
+    // slots per thread (tap reuse) that still give 60 % of the threads a work item in the row pass
+    if (Lh && g.N >= 2048) threads = 512;
+    if (Lh && getenv("AMPSM_TAPS_THREADS")) threads = atoi(getenv("AMPSM_TAPS_THREADS"));      // tuning switches
+    int opk = 0;
+    if (Lh) {
+        opk = 1;
+        for (int k : {4, 2})
+            if (((g.Lout + k - 1) / k) * g.Nr * 5 >= threads * 3) { opk = k; break; }
+        if (getenv("AMPSM_TAPS_SLOTS")) opk = atoi(getenv("AMPSM_TAPS_SLOTS"));
+        if (opk != 1 && opk != 2 && opk != 4) opk = 1;
+    }
+    void (*kern)(const BampArgs);
+    switch (opk) {
+        case 0: kern = exp64 ? bamp_generic_kernel<true, 0> : bamp_generic_kernel<false, 0>; break;
+        case 1: kern = exp64 ? bamp_generic_kernel<true, 1> : bamp_generic_kernel<false, 1>; break;
+        case 2: kern = exp64 ? bamp_generic_kernel<true, 2> : bamp_generic_kernel<false, 2>; break;
+        default: kern = exp64 ? bamp_generic_kernel<true, 4> : bamp_generic_kernel<false, 4>; break;
+    }
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total),
                            "cudaFuncSetAttribute(bamp_generic)"))
         return e;

@@ -81,6 +81,13 @@ __device__ inline double block_absmax_exponent(const Geom& g, const DevAlphabet&
     return r;
 }
 
+// Denoiser scratch: per-entry planes (3 N) unless a per-warp section buffer is smaller (frames with many short sections)
+constexpr int kDenoiseMaxWarps = 16;
+__host__ __device__ inline bool denoise_scratch_per_warp(const Geom& g) { return (long long)kDenoiseMaxWarps * g.M < g.N; }
+__host__ __device__ inline size_t denoise_scratch_elems(const Geom& g) {
+    return 3 * (size_t)(denoise_scratch_per_warp(g) ? kDenoiseMaxWarps * g.M : g.N);
+}
+
 // Section-wise posterior mean / variance.  s, tau_vec, xh_out, var_out and the scratch arrays live in shared
 // memory (scratch: 3*N values of the exponent type).  No block barrier inside; callers synchronise before
 // reading xh_out / var_out.  var_out may be nullptr (SCAMP needs the mean only).
@@ -88,16 +95,20 @@ template <bool EXP64, typename CT>
 __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const CT* s,
                                      const typename RealOf<CT>::type* tau_vec, typename RealOf<CT>::type tau_scalar,
                                      bool halve, double global_shift, float2* xh_out, float* var_out,
-                                     typename ExpT<EXP64>::type* scr, int tau_div = 1) {
+                                     typename ExpT<EXP64>::type* scr, int tau_div = 1, bool scr_per_warp = false) {
     using E = typename ExpT<EXP64>::type;
     using RT = typename RealOf<CT>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // scratch: three planes indexed by the entry (3 N values), or -- scr_per_warp -- by (warp, position in the section):
+    // a warp only ever needs its current section between the passes (3 * kDenoiseMaxWarps * M values, see denoise_scratch_elems)
+    const int plane = scr_per_warp ? kDenoiseMaxWarps * g.M : g.N;
     E* S0 = scr;
-    E* S1r = scr + g.N;
-    E* S1i = scr + 2 * g.N;
+    E* S1r = scr + plane;
+    E* S1i = scr + 2 * plane;
     const bool ref_shift = EXP64 && g.shift_mode == 1;
     for (int sec = warp; sec < g.L; sec += nwarps) {
         const int base = sec * g.M;
+        const int sb = scr_per_warp ? warp * g.M : base;
         // pass 1: section maximum of the exponents
         double smax = -INFINITY;
         if (!ref_shift) {
@@ -136,16 +147,16 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
                     s1i = fmaf(al.imf[k], e, s1i);
                 }
             }
-            S0[base + m] = s0;
-            S1r[base + m] = s1r;
-            S1i[base + m] = s1i;
+            S0[sb + m] = s0;
+            S1r[sb + m] = s1r;
+            S1i[sb + m] = s1i;
             z_lane += (double)s0;
         }
         const double Z = warp_sum(z_lane);
         __syncwarp();
         // pass 3: mean, and the variance in the reference's two-term form (bamp.py:74-76)
         for (int m = lane; m < g.M; m += 32) {
-            const double xr = (double)S1r[base + m] / Z, xi = (double)S1i[base + m] / Z;
+            const double xr = (double)S1r[sb + m] / Z, xi = (double)S1i[sb + m] / Z;
             xh_out[base + m] = make_float2((float)xr, (float)xi);
             if (var_out) {
                 RT tau = tau_vec ? tau_vec[(base + m) / tau_div] : tau_scalar;
@@ -157,7 +168,7 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
                     const double dr = xr - al.re[k], di = xi - al.im[k];
                     spread += (dr * dr + di * di) * (double)e;
                 }
-                const double p = (double)S0[base + m] / Z;
+                const double p = (double)S0[sb + m] / Z;
                 var_out[base + m] = (float)((xr * xr + xi * xi) * (1.0 - p) + spread / Z);
             }
         }
