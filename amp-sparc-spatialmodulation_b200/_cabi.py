@@ -48,10 +48,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise AmpsmError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("AMPSM_LIB", LIB_PATH)        # development builds of the same library (scripts/build_clk.sh)
+    if not os.path.exists(path):
+        raise AmpsmError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(nvcc, sm_100a).  There is no CPU fallback for the detector hot path.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
     PP, AP = C.POINTER(Problem), C.POINTER(Alphabet)
     L.ampsm_version.restype = C.c_char_p

@@ -23,6 +23,17 @@
 
 namespace ampsm {
 
+// Phase timing for development builds (-DAMPSM_CLK, scripts/phase_clocks.py): lane 0 of every warp accumulates the cycles
+// between phase boundaries; ampsm_debug_clocks() returns the sums over all warps.  Compiled out of the shipped library.
+#ifdef AMPSM_CLK
+__device__ unsigned long long g_clk[16];
+#define CLK_INIT() unsigned clk_last_ = clock()
+#define CLK(p) do { const unsigned now_ = clock(); if (lane == 0) atomicAdd(&clkacc[p], now_ - clk_last_); clk_last_ = now_; } while (0)
+#else
+#define CLK_INIT() do {} while (0)
+#define CLK(p) do {} while (0)
+#endif
+
 // DIRECT = false: the frame's H lands in a per-warp staging buffer (bulk TMA) and |H|^2 lives in registers next to H.
 // DIRECT = true : no staging buffer -- the lanes load their tiles straight from global memory (full 128-byte lines,
 //                 issued right after the last iteration so that they fly under the Loss epilogue of the previous
@@ -32,20 +43,26 @@ namespace ampsm {
 template <int RT, int CTL, int M_, int K_, bool DIRECT>
 struct FastShape {
     static constexpr int n = 4 * RT, N = 8 * CTL;
+    static constexpr int L = N / M_;
     static constexpr int VW = CTL >= 2 ? 2 : 1;            // columns per vector load
     static constexpr int NV = CTL / VW;
     static constexpr int CP = (N + 31) / 32;               // owned columns per lane in the denoiser
     static constexpr int stage_bytes = DIRECT ? 0 : ((n * N * 8 + n * 8 + 127) & ~127);   // H, y
-    static constexpr int rowpart_bytes = n * 8 * 16;
-    static constexpr int colpart_bytes = N * 4 * 16;
+    static constexpr int xrow_bytes = 8 * 16 + 16;           // 8 chunks + pad (see xslot in the kernel)
+    static constexpr int rowpart_bytes = n * xrow_bytes;
+    static constexpr int colpart_bytes = (N / 2) * xrow_bytes;
     static constexpr int ebuf_bytes = 32 * CP * K_ * 4;
     static constexpr int xch_bytes_a = rowpart_bytes > colpart_bytes ? rowpart_bytes : colpart_bytes;
     static constexpr int xch_bytes = ((xch_bytes_a > ebuf_bytes ? xch_bytes_a : ebuf_bytes) + 127) & ~127;
     static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // padded slots (see the kernel)
     static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 20 + 127) & ~127;     // float4 per column + the variance array
     static constexpr int wvec_bytes = ((n > 32 ? n : 32) * 8 + 127) & ~127;
-    static constexpr int state_bytes = 32 * 16 + 32 * 8 + (N > 32 ? N : 32) * 8 + 128;   // z/u, y, xmap, counters
-    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + state_bytes + 128;
+    // per-lane state that is only touched in one phase: z/u, y, xmap | 16 counters | 32 squared-error sums | Loss inputs
+    static constexpr int o_ystate = 32 * 16, o_xmap = o_ystate + 32 * 8, o_cnt = o_xmap + (N > 32 ? N : 32) * 8;
+    static constexpr int o_sq = o_cnt + 64, o_loss = o_sq + 256;
+    static constexpr int o_mbar = (o_loss + LossStage<N, L>::bytes + 15) & ~15;
+    static constexpr int state_bytes = (o_mbar + 16 + 64 + 127) & ~127;            // mbarrier, phase clocks (development builds)
+    static constexpr int warp_bytes = stage_bytes + xch_bytes + rowvec_bytes + colvec_bytes + wvec_bytes + state_bytes;
     static constexpr int warps_per_cta = DIRECT ? 1 : 4;
     static constexpr int ctas_per_sm = DIRECT ? 8 : 2;    // two warps per SM sub-partition either way: 255 registers
 };
@@ -59,7 +76,9 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     constexpr int n = S::n, N = S::N, VW = S::VW, NV = S::NV, CP = S::CP;
     constexpr int L_ = N / M_;
     static_assert(N % M_ == 0, "section size must divide N");
+    static_assert(N % 2 == 0, "the Loss staging copies x_true in 16-byte pieces");
     static_assert(M_ >= 32 ? (M_ % 32 == 0) : (32 % M_ == 0), "sections must tile the warp");
+    using LS = LossStage<N, L_>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int la = lane >> 3, lb = lane & 7;
@@ -74,10 +93,17 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     // per-lane state that is only touched in one phase lives in shared memory, not in registers: the H tile needs them
     unsigned char* st = ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes + S::wvec_bytes;
     float4* rowstate = reinterpret_cast<float4*>(st);                       // {z.re, z.im, u, -} of row `lane`
-    float2* ystate = reinterpret_cast<float2*>(st + 32 * 16);               // y of row `lane`
-    float2* xmapvec = reinterpret_cast<float2*>(st + 32 * 16 + 32 * 8);     // xmap of every column (Loss input)
-    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(st + 32 * 16 + 32 * 8 + (N > 32 ? N : 32) * 8);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(st + S::state_bytes);
+    float2* ystate = reinterpret_cast<float2*>(st + S::o_ystate);           // y of row `lane`
+    float2* xmapvec = reinterpret_cast<float2*>(st + S::o_xmap);            // xmap of every column (Loss input)
+    unsigned* cnt32 = reinterpret_cast<unsigned*>(st + S::o_cnt);           // the warp's counters (Counter enum slots)
+    double* sqacc = reinterpret_cast<double*>(st + S::o_sq);                // per-lane squared-error sums
+    unsigned char* lstage = st + S::o_loss;                                 // x_true, labels of the current frame
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(st + S::o_mbar);
+#ifdef AMPSM_CLK
+    unsigned* clkacc = reinterpret_cast<unsigned*>(st + S::o_mbar + 16);
+    if (lane < 16) clkacc[lane] = 0u;
+    __syncwarp();
+#endif
 
     const Geom& g = a.g;
     const DevAlphabet& al = a.al;
@@ -104,8 +130,8 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
         if (f < a.frames) prefetch(f);
     uint32_t phase = 0;
 
-    // per-warp counters in shared memory (slots as the Counter enum, slot 12 = squared-error sum as double)
-    if (lane < 16) cnt[lane] = 0ull;
+    if (lane < 16) cnt32[lane] = 0u;
+    sqacc[lane] = 0.0;
     __syncwarp();
 
     // H and |H|^2 tiles.  PAIR: every element stays the natural (re, im) register pair it is loaded as, and |H|^2 is
@@ -113,6 +139,9 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     // the issue slots for the same FMA-pipe work) with no register re-packing inside the iteration loop:
     //   H x    : A += h (xx,xx), B += h (xy,xy)   ->  re = A.lo - B.hi, im = B.lo + A.hi
     //   H^H g  : A += h (gx,gy), B += h (gy,-gx)  ->  re = A.lo + A.hi, im = B.lo + B.hi
+    // (B200 register file: one 64-bit operand per lane and cycle -- an FFMA2 whose three operands are all new takes 3
+    // cycles, with one of them in the operand-reuse cache 2, which is the FMA pipe's own rate; scripts/exp/ffma2_issue.cu.
+    // The loops below keep the broadcast operand fixed over consecutive instructions for that reason.)
     constexpr bool PAIR = (VW == 2);
     static_assert(!DIRECT || PAIR, "DIRECT needs the packed tile");
     pair_t Hp[PAIR ? RT : 1][CTL], Pp[PAIR ? RT : 1][PAIR ? NV : 1];
@@ -135,7 +164,133 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     if constexpr (DIRECT)
         if (f < a.frames) load_tile(f);
 
+    // column-vector exchange.  PAIR: per column one float4 {xx,xx,xy,xy} (the broadcast operand pairs of the row
+    // pass), placed so that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without
+    // conflicts, plus the variances as a plain float array (adjacent columns = one operand pair).
+    float* varvec = reinterpret_cast<float*>(colvec + N);
+    // Partial-sum exchange: 8 float4 chunks per row (row pass: one per column group) or per column pair (column pass: 2
+    // columns x 4 row groups), rows 144 bytes apart.  The 16-byte pad puts consecutive rows 4 banks apart, so the eight
+    // lanes of a quarter-warp that write one row (contiguous 128 bytes) and the eight that read one chunk of eight
+    // consecutive rows are both conflict-free -- and every address is one per-lane base plus an immediate (the XOR swizzle
+    // this replaces cost ~20 address registers, which the compiler spilled).
+    auto xslot = [&](int row, int chunk) -> float4& {
+        return *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(xch) + row * S::xrow_bytes + chunk * 16);
+    };
+    auto colslot = [&](int col) {
+        if constexpr (PAIR) {
+            const int t = col >> 4, b = (col >> 1) & 7, e = col & 1;
+            return (t * 2 + e) * 8 + (b ^ (e << 2));
+        } else {
+            return col ^ ((col >> 3) & 1);
+        }
+    };
+    auto publish = [&](int col, float xr, float xi, float v) {
+        if constexpr (PAIR) {
+            colvec[colslot(col)] = make_float4(xr, xr, xi, xi);
+            varvec[col] = v;
+        } else {
+            colvec[colslot(col)] = make_float4(xr, xi, v, 0.f);
+        }
+    };
+    // read back the estimate a column owner published (xhat, var)
+    auto owned = [&](int col, float2& x, float& v) {
+        const float4 q = colvec[colslot(col)];
+        if constexpr (PAIR) {
+            x = make_float2(q.x, q.z);
+            v = varvec[col];
+        } else {
+            x = make_float2(q.x, q.y);
+            v = q.z;
+        }
+    };
+    // row pass: partial sums of v = |H|^2 var and H xhat (bamp.py:59-60) over the lane's columns, into the exchange
+    auto row_pass = [&]() {
+        if constexpr (PAIR) {
+            constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
+#pragma unroll
+            for (int i0 = 0; i0 < RT; i0 += RH) {
+                pair_t A[RH], B[RH], V[RH];
+#pragma unroll
+                for (int i = 0; i < RH; ++i) A[i] = B[i] = V[i] = 0ull;
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    const int col = (t * 8 + lb) * 2;
+                    const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {xx,xx | xy,xy}
+                    const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
+                    const pair_t vp = *reinterpret_cast<const pair_t*>(&varvec[col]);                       // {var_c, var_c+1}
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
+                        B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
+                        A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
+                        B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
+                        V[i] = ffma2(Pp[i0 + i][t], vp, V[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RH; ++i) {
+                    const int row = la * RT + i0 + i;
+                    float al_, ah_, bl_, bh_, vl_, vh_;
+                    unpack2(A[i], al_, ah_);
+                    unpack2(B[i], bl_, bh_);
+                    unpack2(V[i], vl_, vh_);
+                    xslot(row, lb) = make_float4(vl_ + vh_, al_ - bh_, bl_ + ah_, 0.f);
+                }
+                asm volatile("" ::: "memory");
+            }
+        } else {
+            float av[RT], ar[RT], ai[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) av[i] = ar[i] = ai[i] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CTL; ++c) {
+                const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
+                const float4 xv = colvec[colslot(col)];           // {xhat.re, xhat.im, var, -}
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    av[i] = fmaf(P[i][c], xv.z, av[i]);
+                    ar[i] = fmaf(Hr[i][c], xv.x, ar[i]);
+                    ar[i] = fmaf(-Hi[i][c], xv.y, ar[i]);
+                    ai[i] = fmaf(Hr[i][c], xv.y, ai[i]);
+                    ai[i] = fmaf(Hi[i][c], xv.x, ai[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const int row = la * RT + i;
+                xslot(row, lb) = make_float4(av[i], ar[i], ai[i], 0.f);
+            }
+        }
+    };
+    // the first row pass of a frame: xhat = 0, var = 1 (bamp.py:20-22), so H xhat = 0 and v = the row sums of |H|^2 --
+    // the same additions in the same order as row_pass() would perform, without the 4 x RT x CTL products with zero
+    auto row_pass_first = [&]() {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int row = la * RT + i;
+            float v;
+            if constexpr (PAIR) {
+                float lo, hi, l2, h2;
+                unpack2(Pp[i][0], lo, hi);
+#pragma unroll
+                for (int t = 1; t < NV; ++t) {
+                    unpack2(Pp[i][t], l2, h2);
+                    lo += l2;
+                    hi += h2;
+                }
+                v = lo + hi;
+            } else {
+                v = 0.f;
+#pragma unroll
+                for (int c = 0; c < CTL; ++c) v += P[i][c];
+            }
+            xslot(row, lb) = make_float4(v, 0.f, 0.f, 0.f);
+        }
+    };
+
+    CLK_INIT();
     for (; f < a.frames; f += warps_total) {
+        if (a.io.x_true) LS::issue(lstage, a.io, f, lane);      // the Loss inputs of this frame: in shared memory long before the epilogue
         if constexpr (DIRECT) {
             // |H|^2 (bamp.py:18) of the tile that load_tile() brought into registers, paired over adjacent columns
 #pragma unroll
@@ -199,34 +354,6 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
             if (nf < a.frames) prefetch(nf);
         }
         const float sigma2 = a.sigma2_pf ? a.sigma2_pf[f] : a.sigma2;
-        if (a.io.x_true) {   // the Loss epilogue reads these once, right after the last iteration: start the fetch now
-            if (lane * 16 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.x_true + f * N + lane * 16));
-            if (lane == 31) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.idx_true + f * L_));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.sym_true + f * L_));
-            }
-        }
-
-        // column-vector exchange.  PAIR: per column one float4 {xx,xx,xy,xy} (the broadcast operand pairs of the row
-        // pass), placed so that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without
-        // conflicts, plus the variances as a plain float array (adjacent columns = one operand pair).
-        float* varvec = reinterpret_cast<float*>(colvec + N);
-        auto colslot = [&](int col) {
-            if constexpr (PAIR) {
-                const int t = col >> 4, b = (col >> 1) & 7, e = col & 1;
-                return (t * 2 + e) * 8 + (b ^ (e << 2));
-            } else {
-                return col ^ ((col >> 3) & 1);
-            }
-        };
-        auto publish = [&](int col, float xr, float xi, float v) {
-            if constexpr (PAIR) {
-                colvec[colslot(col)] = make_float4(xr, xr, xi, xi);
-                varvec[col] = v;
-            } else {
-                colvec[colslot(col)] = make_float4(xr, xi, v, 0.f);
-            }
-        };
 
         // state (bamp.py:20-25): row owner lane r keeps z_r, u_r; column owner lane keeps xhat, var of col lane+32t
         if (lane < n) {
@@ -236,82 +363,18 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
         for (int t = 0; t < CP; ++t)
             if (lane + 32 * t < N) publish(lane + 32 * t, 0.f, 0.f, 1.0f);   // xhat = 0, var = 1
+        row_pass_first();
         __syncwarp();
-        // read back the estimate a column owner published (xhat, var)
-        auto owned = [&](int col, float2& x, float& v) {
-            const float4 q = colvec[colslot(col)];
-            if constexpr (PAIR) {
-                x = make_float2(q.x, q.z);
-                v = varvec[col];
-            } else {
-                x = make_float2(q.x, q.y);
-                v = q.z;
-            }
-        };
 
+        // The loop is rotated: an iteration starts at the row REDUCTION and ends with the row pass that feeds the next
+        // one, which is skipped when the frame is done (bamp.py:140) -- one row pass less per frame.
         int t_done = 0;
-        for (int it = 0; it < g.max_iters; ++it) {
-            // ================= row pass: v = |H|^2 var, Hx = H xhat (bamp.py:59-60) =================
-            if constexpr (PAIR) {
-                constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
-#pragma unroll
-                for (int i0 = 0; i0 < RT; i0 += RH) {
-                    pair_t A[RH], B[RH], V[RH];
-#pragma unroll
-                    for (int i = 0; i < RH; ++i) A[i] = B[i] = V[i] = 0ull;
-#pragma unroll
-                    for (int t = 0; t < NV; ++t) {
-                        const int col = (t * 8 + lb) * 2;
-                        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {xx,xx | xy,xy}
-                        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
-                        const pair_t vp = *reinterpret_cast<const pair_t*>(&varvec[col]);                       // {var_c, var_c+1}
-#pragma unroll
-                        for (int i = 0; i < RH; ++i) {
-                            A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
-                            B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
-                            A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
-                            B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
-                            V[i] = ffma2(Pp[i0 + i][t], vp, V[i]);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < RH; ++i) {
-                        const int row = la * RT + i0 + i;
-                        float al_, ah_, bl_, bh_, vl_, vh_;
-                        unpack2(A[i], al_, ah_);
-                        unpack2(B[i], bl_, bh_);
-                        unpack2(V[i], vl_, vh_);
-                        xch[row * 8 + (lb ^ (row & 7))] = make_float4(vl_ + vh_, al_ - bh_, bl_ + ah_, 0.f);
-                    }
-                }
-            } else {
-                float av[RT], ar[RT], ai[RT];
-#pragma unroll
-                for (int i = 0; i < RT; ++i) av[i] = ar[i] = ai[i] = 0.f;
-#pragma unroll
-                for (int c = 0; c < CTL; ++c) {
-                    const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
-                    const float4 xv = colvec[colslot(col)];           // {xhat.re, xhat.im, var, -}
-#pragma unroll
-                    for (int i = 0; i < RT; ++i) {
-                        av[i] = fmaf(P[i][c], xv.z, av[i]);
-                        ar[i] = fmaf(Hr[i][c], xv.x, ar[i]);
-                        ar[i] = fmaf(-Hi[i][c], xv.y, ar[i]);
-                        ai[i] = fmaf(Hr[i][c], xv.y, ai[i]);
-                        ai[i] = fmaf(Hi[i][c], xv.x, ai[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    const int row = la * RT + i;
-                    xch[row * 8 + (lb ^ (row & 7))] = make_float4(av[i], ar[i], ai[i], 0.f);
-                }
-            }
-            __syncwarp();
+        CLK(7);                                  // prologue
+        for (int it = 0;; ++it) {
             if (lane < n) {
                 float4 p[8];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) p[b] = xch[lane * 8 + (b ^ (lane & 7))];
+                for (int b = 0; b < 8; ++b) p[b] = xslot(lane, b);
                 // tree, not a chain: this sits on the iteration's critical path
                 const float sv = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
                 const float sr = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
@@ -333,10 +396,11 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 }
             }
             __syncwarp();
+            CLK(1);                              // row reduction, z / u update, operand publish
             // ================= column pass: cov = 1/(|H|^2^T 1/u), H^H((y-z)/u) (bamp.py:62-63) =================
-            float cc[CTL], cr[CTL], ci[CTL];
             if constexpr (PAIR) {
-                // columns in two halves: the accumulators would not fit next to the H tile otherwise
+                // columns in two halves: the accumulators would not fit next to the H tile otherwise; each half goes
+                // to the exchange as soon as it is complete
                 constexpr int CH = CTL > 4 ? CTL / 2 : CTL;
 #pragma unroll
                 for (int c0 = 0; c0 < CTL; c0 += CH) {
@@ -360,16 +424,17 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                     }
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
-                        float lo, hi;
-                        unpack2(A[c], lo, hi);
-                        cr[c0 + c] = lo + hi;
-                        unpack2(B[c], lo, hi);
-                        ci[c0 + c] = lo + hi;
+                        float alo, ahi, blo, bhi, c0_, c1_;
+                        unpack2(A[c], alo, ahi);
+                        unpack2(B[c], blo, bhi);
+                        unpack2(C[c / 2], c0_, c1_);
+                        const int col = (((c0 + c) / VW) * 8 + lb) * VW + ((c0 + c) % VW);
+                        xslot(col >> 1, (col & 1) * 4 + la) = make_float4((c & 1) ? c1_ : c0_, alo + ahi, blo + bhi, 0.f);
                     }
-#pragma unroll
-                    for (int c = 0; c < CH / 2; ++c) unpack2(C[c], cc[c0 + 2 * c], cc[c0 + 2 * c + 1]);
+                    asm volatile("" ::: "memory");     // keep the halves apart: ptxas otherwise parks the first half's sums on the stack
                 }
             } else {
+                float cc[CTL], cr[CTL], ci[CTL];
 #pragma unroll
                 for (int c = 0; c < CTL; ++c) cc[c] = cr[c] = ci[c] = 0.f;
 #pragma unroll
@@ -384,166 +449,45 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                         ci[c] = fmaf(-Hi[i][c], gv.x, ci[c]);
                     }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < CTL; ++c) {
-                const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
-                const int chunk = ((col & 1) * 4 + la) ^ ((col >> 1) & 7);
-                xch[(col >> 1) * 8 + chunk] = make_float4(cc[c], cr[c], ci[c], 0.f);
+                for (int c = 0; c < CTL; ++c) {
+                    const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
+                    xslot(col >> 1, (col & 1) * 4 + la) = make_float4(cc[c], cr[c], ci[c], 0.f);
+                }
             }
             __syncwarp();
-            float2 xh[CP], xmap[CP];
-            float var[CP], cov[CP];
+            CLK(2);                              // column pass
+            float2 xmap[CP];
+            float var[CP], cov[CP], q_r[CP], q_i[CP];
 #pragma unroll
             for (int t = 0; t < CP; ++t) {
                 const int col = lane + 32 * t;
-                xh[t] = xmap[t] = make_float2(0.f, 0.f);
-                var[t] = cov[t] = 0.f;
+                xmap[t] = make_float2(0.f, 0.f);
+                var[t] = cov[t] = q_r[t] = q_i[t] = 0.f;
                 if (col < N) {
                     float4 p[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) p[q] = xch[(col >> 1) * 8 + (((col & 1) * 4 + q) ^ ((col >> 1) & 7))];
+                    for (int q = 0; q < 4; ++q) p[q] = xslot(col >> 1, (col & 1) * 4 + q);
                     const float sc = (p[0].x + p[1].x) + (p[2].x + p[3].x);
                     const float sr = (p[0].y + p[1].y) + (p[2].y + p[3].y);
                     const float si = (p[0].z + p[1].z) + (p[2].z + p[3].z);
-                    owned(col, xh[t], var[t]);
+                    float2 xh;
+                    owned(col, xh, var[t]);
                     cov[t] = fast_rcp(sc);
-                    xmap[t] = make_float2(fmaf(cov[t], sr, xh[t].x), fmaf(cov[t], si, xh[t].y));
+                    xmap[t] = make_float2(fmaf(cov[t], sr, xh.x), fmaf(cov[t], si, xh.y));
                     xmapvec[col] = xmap[t];
+                    // s / (tau / 2) of the denoiser (bamp.py:68-69) = 2 (xhat sc + sum): the reciprocal stays off the
+                    // critical path (xmap itself is only read by the Loss epilogue)
+                    q_r[t] = 2.0f * fmaf(xh.x, sc, sr);
+                    q_i[t] = 2.0f * fmaf(xh.y, sc, si);
                 }
             }
             __syncwarp();     // everyone is done with the column partials: the region becomes the exp buffer
+            CLK(3);                              // column reduction, xmap
             // ================= denoiser (bamp.py:66-77), tau = cov/2 =================
             float xr_[CP], xi_[CP], vn_[CP];
-            if constexpr (GRID) {
-                // Separable path for the reference's 16-QAM table: e_k = Er[a_k] Ei[b_k] on the 4 x 4 level grid, with the
-                // table's two irregular points hard-wired (config.py:112: (-1,+3) twice -> grid point (1,3) weight +1,
-                // (+1,-3) missing -> grid point (2,0) weight -1; launch_bamp_fast checks the table has this pattern).
-                // Exponents are formed relative to the antenna's own largest level product, i.e. as ONE float product
-                // q * (level - level_max) log2 e -- no cancellation, so float32 is exact enough; only the antenna's
-                // offset to the section maximum (a difference of two large numbers) is taken in float64.
-                const DevGrid& G = a.grid;
-                float q_r[CP], q_i[CP], lmax[CP], smax[CP];
-                double lmd[CP];
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const float rt = fast_rcp(cov[t] * 0.5f);
-                    q_r[t] = xmap[t].x * rt;
-                    q_i[t] = xmap[t].y * rt;
-                    lmd[t] = (double)q_r[t] * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]) + (double)q_i[t] * (q_i[t] >= 0.f ? G.li2[3] : G.li2[0]);
-                    lmax[t] = (lane + 32 * t < N) ? (float)lmd[t] : -INFINITY;
-                }
-                if constexpr (L_ == 1) {           // the section is the whole warp: one CREDUX instead of a shuffle tree
-                    float m = lmax[0];
-#pragma unroll
-                    for (int t = 1; t < CP; ++t) m = fmaxf(m, lmax[t]);
-                    float r;
-                    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(m));
-#pragma unroll
-                    for (int t = 0; t < CP; ++t) smax[t] = r;
-                } else {
-                    section_max<M_, CP>(lmax, smax);
-                }
-                float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], e13[CP], e20[CP];
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const float off = (float)(lmd[t] - (double)smax[t]);       // <= 0 up to rounding
-                    const bool rp = q_r[t] >= 0.f, ip = q_i[t] >= 0.f;
-                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        Er[t][l] = fast_ex2(q_r[t] * (rp ? G.dpos_r[l] : G.dneg_r[l]));
-                        Ei[t][l] = fast_ex2(fmaf(q_i[t], ip ? G.dpos_i[l] : G.dneg_i[l], off));
-                        a0 += Er[t][l];
-                        a1 = fmaf(G.lrf[l], Er[t][l], a1);
-                        b0 += Ei[t][l];
-                        b1 = fmaf(G.lif[l], Ei[t][l], b1);
-                    }
-                    e13[t] = Er[t][1] * Ei[t][3];
-                    e20[t] = Er[t][2] * Ei[t][0];
-                    const float s0 = fmaf(a0, b0, e13[t] - e20[t]);
-                    S0[t] = (lane + 32 * t < N) ? s0 : 0.f;
-                    A0[t] = a0; A1[t] = a1; B0[t] = b0; B1[t] = b1;
-                }
-                float Z[CP], others[CP];
-                section_sum_excl<M_, CP>(S0, Z, others);
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const float rz = fast_rcp(Z[t]);
-                    const float s1r = fmaf(A1[t], B0[t], fmaf(G.lrf[1], e13[t], -G.lrf[2] * e20[t]));
-                    const float s1i = fmaf(A0[t], B1[t], fmaf(G.lif[3], e13[t], -G.lif[0] * e20[t]));
-                    const float xr = s1r * rz, xi = s1i * rz;
-                    // two-term variance (bamp.py:74-76): sum_k |xhat - s_k|^2 e_k factorises the same way
-                    float dr = 0.f, di = 0.f, er2[4], ei2[4];
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        const float er = xr - G.lrf[l], ei = xi - G.lif[l];
-                        er2[l] = er * er;
-                        ei2[l] = ei * ei;
-                        dr = fmaf(er2[l], Er[t][l], dr);
-                        di = fmaf(ei2[l], Ei[t][l], di);
-                    }
-                    float spread = fmaf(dr, B0[t], A0[t] * di);
-                    spread = fmaf(er2[1] + ei2[3], e13[t], spread);
-                    spread = fmaf(-(er2[2] + ei2[0]), e20[t], spread);
-                    xr_[t] = xr;
-                    xi_[t] = xi;
-                    vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
-                }
-            } else {
-                double qr[CP], qi[CP];
-                float lmax[CP], smax[CP];
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const float rt = fast_rcp(cov[t] * 0.5f);
-                    const float q_r = xmap[t].x * rt, q_i = xmap[t].y * rt;
-                    qr[t] = (double)q_r;
-                    qi[t] = (double)q_i;
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int k = 0; k < K_; ++k) m = fmaxf(m, fmaf(q_r, al.ref[k], q_i * al.imf[k]));
-                    lmax[t] = (lane + 32 * t < N) ? m : -INFINITY;
-                }
-                // section maxima (only approximately the true maxima: they are a common shift, nothing else)
-                section_max<M_, CP>(lmax, smax);
-                // exp pass: e = 2^((x - shift) log2 e); per-antenna sums S0 = sum e, S1 = sum sym e
-                float S0[CP], S1r[CP], S1i[CP];
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const double shift = (double)smax[t];
-                    float s0 = 0.f, s1r = 0.f, s1i = 0.f;
-#pragma unroll
-                    for (int k = 0; k < K_; ++k) {
-                        const double x = fma(qr[t], al.re[k], qi[t] * al.im[k]);
-                        const float e = fast_ex2((float)(x - shift) * 1.4426950408889634f);
-                        ebuf[(t * K_ + k) * 32 + lane] = e;
-                        s0 += e;
-                        s1r = fmaf(al.ref[k], e, s1r);
-                        s1i = fmaf(al.imf[k], e, s1i);
-                    }
-                    S0[t] = (lane + 32 * t < N) ? s0 : 0.f;
-                    S1r[t] = s1r;
-                    S1i[t] = s1i;
-                }
-                float Z[CP], others[CP];
-                section_sum_excl<M_, CP>(S0, Z, others);
-                // mean and two-term variance (bamp.py:72-76)
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    const float rz = fast_rcp(Z[t]);
-                    const float xr = S1r[t] * rz, xi = S1i[t] * rz;
-                    float spread = 0.f;
-#pragma unroll
-                    for (int k = 0; k < K_; ++k) {
-                        const float e = ebuf[(t * K_ + k) * 32 + lane];
-                        const float dr = xr - al.ref[k], di = xi - al.imf[k];
-                        spread = fmaf(fmaf(dr, dr, di * di), e, spread);
-                    }
-                    xr_[t] = xr;
-                    xi_[t] = xi;
-                    vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
-                }
-            }
+            fast_denoise<N, M_, K_, GRID, CP>(q_r, q_i, al, a.grid, ebuf, lane, xr_, xi_, vn_);
+            CLK(4);                              // denoiser
             // exit test on var (bamp.py:140), publish the new estimate for the next row pass
             bool close = true;
             float s_tau = 0.f, s_var = 0.f, s_mse = 0.f;
@@ -578,7 +522,12 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 }
             }
             t_done = it + 1;
-            if (g.early_exit && all_close) break;
+            CLK(5);                              // exit test, publish
+            if ((g.early_exit && all_close) || t_done >= g.max_iters) break;
+            // ================= row pass for the next iteration (bamp.py:59-60) =================
+            row_pass();
+            __syncwarp();
+            CLK(0);                              // row pass
         }
 
         if constexpr (DIRECT) {   // the H registers are free: fetch the next frame's tile under the Loss epilogue
@@ -607,134 +556,27 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 for (int q = 0; q < 3; ++q)
                     a.traj[(f * g.max_iters + it) * 3 + q] = a.traj[(f * g.max_iters + t_done - 1) * 3 + q];
         }
-        if (lane == 0 && a.iters) a.iters[f] = t_done;
-        unsigned long long c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0;
         if (lane == 0) {
-            cnt[C_FRAMES] += 1;
-            cnt[C_ITERS] += t_done;
+            if (a.iters) a.iters[f] = t_done;
+            atomicAdd(&cnt32[C_FRAMES], 1u);
+            atomicAdd(&cnt32[C_ITERS], (unsigned)t_done);
         }
-
         // ================= Loss: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1 shapes only ========
         if (a.io.x_true) {
-            bool wrong = false, nan_seen = false;
-            double sq = 0.0;
-            Pick best[CP];
-#pragma unroll
-            for (int t = 0; t < CP; ++t) {
-                const int col = lane + 32 * t;
-                best[t] = Pick{-INFINITY, 0x7fffffff};
-                if (col < N) {
-                    const int m = col % M_;
-                    // in-order scan (flat index increases with k): the first maximum wins, so replace only on
-                    // "strictly greater"; a NaN wins once and then sticks (np.argmax).  Predicated selects, no branches.
-                    const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
-                    double bv = __dadd_rn(__dmul_rn(xr, al.re[0]), __dmul_rn(xi, al.im[0]));
-                    int bk = 0;
-#pragma unroll
-                    for (int k = 1; k < K_; ++k) {
-                        const double v = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
-                        const bool upd = (bv == bv) & ((v > bv) | (v != v));
-                        bv = upd ? v : bv;
-                        bk = upd ? k : bk;
-                    }
-                    best[t] = Pick{bv, m * K_ + bk};
-                    nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
-                }
-            }
-            // reduce the picks inside each section
-            int dec_ant[CP], dec_k[CP];
-            if constexpr (M_ >= 32) {
-                constexpr int TPS = M_ / 32;
-#pragma unroll
-                for (int s0 = 0; s0 < CP; s0 += TPS) {
-                    Pick b = best[s0];
-#pragma unroll
-                    for (int q = 1; q < TPS; ++q)
-                        if (pick_better(best[s0 + q], b)) b = best[s0 + q];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
-                        if (pick_better(other, b)) b = other;
-                    }
-#pragma unroll
-                    for (int q = 0; q < TPS; ++q) {
-                        dec_ant[s0 + q] = b.idx / K_;
-                        dec_k[s0 + q] = b.idx % K_;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < CP; ++t) {
-                    Pick b = best[t];
-#pragma unroll
-                    for (int o = M_ / 2; o > 0; o >>= 1) {
-                        Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
-                        if (pick_better(other, b)) b = other;
-                    }
-                    dec_ant[t] = b.idx / K_;
-                    dec_k[t] = b.idx % K_;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < CP; ++t) {
-                const int col = lane + 32 * t;
-                if (col < N) {
-                    const int sec = col / M_, m = col % M_;
-                    const float2 xt = a.io.x_true[f * N + col];
-                    const int k = dec_k[t];
-                    const float2 h = (m == dec_ant[t]) ? make_float2((float)al.re[k], (float)al.im[k]) : make_float2(0.f, 0.f);
-                    wrong |= (h.x != xt.x) || (h.y != xt.y);
-                    const float dr = xh[t].x - xt.x, di = xh[t].y - xt.y;
-                    sq += (double)dr * dr + (double)di * di;
-                    if (m == 0) {   // one lane per section books the label counters
-                        const long long ih = (g.frame_base + f) * (long long)N + sec * M_ + dec_ant[t];
-                        const long long itrue = a.io.idx_true[f * L_ + sec];
-                        const long long sh = al.gray[k], st = a.io.sym_true[f * L_ + sec];
-                        const unsigned long long imask = g.index_bits_kept >= 64 ? ~0ull : ((1ull << g.index_bits_kept) - 1ull);
-                        c_idx += (ih != itrue);
-                        c_sym += (sh != st);
-                        c_ibit += __popcll((unsigned long long)(ih ^ itrue) & imask);
-                        c_sbit += __popcll((unsigned long long)(sh ^ st) & ((1ull << al.sbits) - 1ull));
-                    }
-                }
-            }
-            // once per frame: fold the lanes' label counters and book everything in the warp's shared counters
-            auto wsum = [](unsigned long long v) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                return v;
-            };
-            const unsigned long long packed = wsum(c_idx | (c_sym << 12) | (c_ibit << 24) | (c_sbit << 44));   // <= 64 sections, 64 bits each
-            sq = warp_sum(sq);
-            const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
-            if (lane == 0) {
-                cnt[C_INDEX_ERR] += packed & 0xfffull;
-                cnt[C_SYMBOL_ERR] += (packed >> 12) & 0xfffull;
-                cnt[C_INDEX_BIT] += (packed >> 24) & 0xfffffull;
-                cnt[C_SYMBOL_BIT] += packed >> 44;
-                cnt[C_FRAME_ERR] += any_wrong;                       // Lin = 1: one time slot per frame
-                cnt[C_NAN_FRAMES] += any_nan;
-                reinterpret_cast<double*>(cnt)[12] += sq;
-            }
+            cp_async_wait_all();
+            __syncwarp();
+            fast_loss2<N, M_, K_, CP>(xmap, xh, al, g, lstage, f, lane, cnt32, sqacc);
         }
         __syncwarp();
+        CLK(6);                                  // tile load issue, outputs, Loss epilogue
     }
+#ifdef AMPSM_CLK
+    __syncwarp();
+    if (lane < 8) atomicAdd(&g_clk[lane], (unsigned long long)clkacc[lane]);
+#endif
 
     // ---- flush the warp's counters
-    __syncwarp();
-    if (a.io.counters && lane == 0) {
-        unsigned long long* out = a.io.counters;
-        const int plain[] = {C_FRAMES, C_INDEX_ERR, C_SYMBOL_ERR, C_INDEX_BIT, C_SYMBOL_BIT, C_ITERS, C_NAN_FRAMES};
-        for (int k : plain)
-            if (cnt[k]) atomicAdd(out + k, cnt[k]);
-        if (cnt[C_FRAME_ERR]) {          // Lin = 1: the frame is its only, first, middle and last time slot
-            const int slots[] = {C_FRAME_ERR, C_SLOT_ERR, C_SLOT_FIRST, C_SLOT_MID, C_SLOT_LAST};
-            for (int k : slots) atomicAdd(out + k, cnt[C_FRAME_ERR]);
-        }
-        const double sq = reinterpret_cast<double*>(cnt)[12];
-        if (sq != 0.0)
-            for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
-    }
+    fast_flush2(cnt32, sqacc, a.io.counters, lane);
 }
 
 template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
@@ -745,7 +587,14 @@ static int launch_shape(const BampArgs& a, cudaStream_t stream) {
     if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID, DIRECT>;
-    const size_t smem = (size_t)S::warp_bytes * kWarpsPerCta;
+    size_t smem = (size_t)S::warp_bytes * kWarpsPerCta;
+    if (const char* cap = getenv("AMPSM_CTAS_PER_SM")) {   // occupancy experiments: pad shared memory so that only `cap` CTAs fit
+        const int k = atoi(cap);
+        if (k >= 1) {
+            const size_t pad = ((size_t)(232448 / k) - 1024) & ~(size_t)127;
+            if (pad > smem) smem = pad;
+        }
+    }
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute(bamp_fast)"))
         return e;
@@ -764,7 +613,8 @@ static int launch_shape(const BampArgs& a, cudaStream_t stream) {
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
     const Geom& g = a.g;
     // the fused Loss epilogue assumes one time slot per frame; the tile loads need 16-byte aligned frames
-    if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0) return AMPSM_ENOFIT;
+    if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0 || g.max_iters < 1) return AMPSM_ENOFIT;
+    if (reinterpret_cast<uintptr_t>(a.io.x_true) % 16) return AMPSM_ENOFIT;     // the Loss inputs are staged by 16-byte cp.async
     if ((reinterpret_cast<uintptr_t>(a.H) % 16) || (reinterpret_cast<uintptr_t>(a.y) % 16) || (((size_t)g.n * 8) % 16) ||
         (a.H_stride != 0 && ((size_t)a.H_stride * 8) % 16))
         return AMPSM_ENOFIT;
@@ -793,3 +643,12 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace ampsm
+
+#ifdef AMPSM_CLK
+extern "C" int ampsm_debug_clocks(unsigned long long* out8, int reset) {
+    unsigned long long z[16] = {};
+    if (out8 && cudaMemcpyFromSymbol(out8, ampsm::g_clk, 8 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset && cudaMemcpyToSymbol(ampsm::g_clk, z, sizeof(z)) != cudaSuccess) return 1;
+    return 0;
+}
+#endif

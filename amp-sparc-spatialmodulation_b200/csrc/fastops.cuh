@@ -87,6 +87,7 @@ inline DevGrid make_grid(const DevAlphabet& al) {
     for (int i = 0; i < kGridMax; ++i) {
         g.lr2[i] = lr[i] * log2e; g.li2[i] = li[i] * log2e;
         g.lr2f[i] = (float)g.lr2[i]; g.li2f[i] = (float)g.li2[i];
+        g.lr2l[i] = (float)(g.lr2[i] - (double)g.lr2f[i]); g.li2l[i] = (float)(g.li2[i] - (double)g.li2f[i]);
         g.lrf[i] = (float)lr[i]; g.lif[i] = (float)li[i];
     }
     for (int i = 0; i < kGridMax; ++i) {
@@ -179,12 +180,23 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
                                              float* ebuf, int lane, float (&xr_)[CP], float (&xi_)[CP], float (&vn_)[CP]) {
     constexpr int L_ = N_ / M_;
     if constexpr (GRID) {
-        float lmax[CP], smax[CP];
-        double lmd[CP];
+        // The antenna's largest level product lm = q_r lr_max + q_i li_max is kept as an unevaluated float32 sum hi + lo
+        // (products split exactly by FMA, the addition by two-sum), so that the offset to the section maximum -- a
+        // difference of two numbers of order |q| -- carries no float32 cancellation error without any float64
+        // instruction on the iteration's critical path (the float64 chain it replaces was ~10 dependent conversions,
+        // multiplies and adds).  The shift is the float `hi` maximum: any common shift of a section is exact.
+        float lmax[CP], smax[CP], lhi[CP], llo[CP];
 #pragma unroll
         for (int t = 0; t < CP; ++t) {
-            lmd[t] = (double)q_r[t] * (q_r[t] >= 0.f ? G.lr2[3] : G.lr2[0]) + (double)q_i[t] * (q_i[t] >= 0.f ? G.li2[3] : G.li2[0]);
-            lmax[t] = (lane + 32 * t < N_) ? (float)lmd[t] : -INFINITY;
+            const float ar = q_r[t] >= 0.f ? G.lr2f[3] : G.lr2f[0], ai = q_i[t] >= 0.f ? G.li2f[3] : G.li2f[0];
+            const float ar_lo = q_r[t] >= 0.f ? G.lr2l[3] : G.lr2l[0], ai_lo = q_i[t] >= 0.f ? G.li2l[3] : G.li2l[0];
+            const float p1 = q_r[t] * ar, p2 = q_i[t] * ai;
+            const float e1 = fmaf(q_r[t], ar, -p1), e2 = fmaf(q_i[t], ai, -p2);
+            const float sm = p1 + p2, bb = sm - p1;
+            const float err = (p1 - (sm - bb)) + (p2 - bb);
+            lhi[t] = sm;
+            llo[t] = (e1 + e2) + (err + fmaf(q_r[t], ar_lo, q_i[t] * ai_lo));     // + the float32 rounding of the level constants
+            lmax[t] = (lane + 32 * t < N_) ? sm : -INFINITY;
         }
         if constexpr (L_ == 1) {           // the section is the whole warp: one CREDUX instead of a shuffle tree
             float m = lmax[0];
@@ -200,18 +212,17 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
         float Er[CP][4], Ei[CP][4], S0[CP], A0[CP], A1[CP], B0[CP], B1[CP], e13[CP], e20[CP];
 #pragma unroll
         for (int t = 0; t < CP; ++t) {
-            const float off = (float)(lmd[t] - (double)smax[t]);       // <= 0 up to rounding
+            const float off = (lhi[t] - smax[t]) + llo[t];              // <= 0 up to rounding
             const bool rp = q_r[t] >= 0.f, ip = q_i[t] >= 0.f;
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 Er[t][l] = fast_ex2(q_r[t] * (rp ? G.dpos_r[l] : G.dneg_r[l]));
                 Ei[t][l] = fast_ex2(fmaf(q_i[t], ip ? G.dpos_i[l] : G.dneg_i[l], off));
-                a0 += Er[t][l];
-                a1 = fmaf(G.lrf[l], Er[t][l], a1);
-                b0 += Ei[t][l];
-                b1 = fmaf(G.lif[l], Ei[t][l], b1);
             }
+            const float a0 = (Er[t][0] + Er[t][1]) + (Er[t][2] + Er[t][3]);
+            const float b0 = (Ei[t][0] + Ei[t][1]) + (Ei[t][2] + Ei[t][3]);
+            const float a1 = fmaf(G.lrf[0], Er[t][0], G.lrf[1] * Er[t][1]) + fmaf(G.lrf[2], Er[t][2], G.lrf[3] * Er[t][3]);
+            const float b1 = fmaf(G.lif[0], Ei[t][0], G.lif[1] * Ei[t][1]) + fmaf(G.lif[2], Ei[t][2], G.lif[3] * Ei[t][3]);
             e13[t] = Er[t][1] * Ei[t][3];
             e20[t] = Er[t][2] * Ei[t][0];
             const float s0 = fmaf(a0, b0, e13[t] - e20[t]);
@@ -226,18 +237,17 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
             const float s1r = fmaf(A1[t], B0[t], fmaf(G.lrf[1], e13[t], -G.lrf[2] * e20[t]));
             const float s1i = fmaf(A0[t], B1[t], fmaf(G.lif[3], e13[t], -G.lif[0] * e20[t]));
             const float xr = s1r * rz, xi = s1i * rz;
-            float dr = 0.f, di = 0.f, er2[4], ei2[4];
+            float er2[4], ei2[4];
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const float er = xr - G.lrf[l], ei = xi - G.lif[l];
                 er2[l] = er * er;
                 ei2[l] = ei * ei;
-                dr = fmaf(er2[l], Er[t][l], dr);
-                di = fmaf(ei2[l], Ei[t][l], di);
             }
+            const float dr = fmaf(er2[0], Er[t][0], er2[1] * Er[t][1]) + fmaf(er2[2], Er[t][2], er2[3] * Er[t][3]);
+            const float di = fmaf(ei2[0], Ei[t][0], ei2[1] * Ei[t][1]) + fmaf(ei2[2], Ei[t][2], ei2[3] * Ei[t][3]);
             float spread = fmaf(dr, B0[t], A0[t] * di);
-            spread = fmaf(er2[1] + ei2[3], e13[t], spread);
-            spread = fmaf(-(er2[2] + ei2[0]), e20[t], spread);
+            spread += fmaf(er2[1] + ei2[3], e13[t], -(er2[2] + ei2[0]) * e20[t]);
             xr_[t] = xr;
             xi_[t] = xi;
             vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
@@ -407,6 +417,180 @@ __device__ __forceinline__ void fast_flush_counters(const unsigned long long* cn
         for (int k : slots) atomicAdd(out + k, cnt[C_FRAME_ERR]);
     }
     const double sq = reinterpret_cast<const double*>(cnt)[12];
+    if (sq != 0.0)
+        for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
+}
+
+// ---- Loss, low-latency version: the per-frame epilogue of the register-resident kernels ---------------------------------
+// The first version cost ~3600 cycles per frame on B200 (phase clocks, scripts/phase_clocks.py) -- more than one whole
+// BAMP iteration -- almost all of it exposed latency: a 15-step float64 compare chain per column, a 5-step shuffle
+// butterfly on (double, int) picks, x_true / label loads from L2 on first use, and two more 5-step butterflies for the
+// counters.  Here (a) the inputs are staged into shared memory by cp.async at the START of the frame, (b) the per-column
+// arg-max is a tournament (depth log2 K), (c) the section arg-max is three REDUX on an order-preserving 64-bit key,
+// (d) counters accumulate per lane / by fire-and-forget shared atomics and are folded once per kernel.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared-memory staging of one frame's Loss inputs: x_true [N] float2 | idx_true [L] int64 | sym_true [L] int64
+template <int N_, int L_>
+struct LossStage {
+    static constexpr int lab_bytes = (L_ * 8 + 15) & ~15;
+    static constexpr int bytes = N_ * 8 + 2 * lab_bytes;
+    __device__ static const float2* xt(const unsigned char* st) { return reinterpret_cast<const float2*>(st); }
+    __device__ static const long long* idx(const unsigned char* st) { return reinterpret_cast<const long long*>(st + N_ * 8); }
+    __device__ static const long long* sym(const unsigned char* st) { return reinterpret_cast<const long long*>(st + N_ * 8 + lab_bytes); }
+    // x_true + f N must be 16-byte aligned (the launchers check the base pointer; N is even for every fast shape)
+    __device__ static void issue(unsigned char* st, const LossIO& io, long long f, int lane) {
+        static_assert(N_ % 2 == 0, "x_true rows are copied in 16-byte pieces");
+        for (int c = lane; c < N_ / 2; c += 32) cp_async16(st + c * 16, io.x_true + f * N_ + 2 * c);
+        if (lane < L_) {
+            cp_async8(st + N_ * 8 + lane * 8, io.idx_true + f * L_ + lane);
+            cp_async8(st + N_ * 8 + lab_bytes + lane * 8, io.sym_true + f * L_ + lane);
+        }
+        cp_async_commit();
+    }
+};
+
+// order-preserving key of np.argmax: NaN beats everything, -0.0 == +0.0
+__device__ __forceinline__ unsigned long long argmax_key(double v) {
+    const long long b = __double_as_longlong(__dadd_rn(v, 0.0));          // -0.0 + 0.0 = +0.0
+    const unsigned long long k = b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+    return (v != v) ? ~0ull : k;
+}
+// first maximum of `key` over the lanes of a section (M_ lanes, or the whole warp), ties to the smallest idx
+template <int M_>
+__device__ __forceinline__ int section_argmax(unsigned long long key, int idx, int lane) {
+    unsigned mask = 0xffffffffu;
+    if constexpr (M_ < 32) mask = ((1u << M_) - 1u) << (lane & ~(M_ - 1));
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(mask, hi);
+    const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
+    return (int)__reduce_min_sync(mask, (hi == mh && lo == ml) ? (unsigned)idx : 0x7fffffffu);
+}
+
+// xmap / xh: the lane's CP columns (column = lane + 32 t) of the decision input and of the MMSE estimate; `st` the staged
+// inputs of this frame (LossStage, complete: cp.async.wait_all + __syncwarp done by the caller).  cnt32: the warp's 16
+// shared counters (Counter enum slots), sqacc: 32 per-lane float64 squared-error sums.
+template <int N_, int M_, int K_, int CP>
+__device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const Geom& g,
+                                           const unsigned char* st, long long f, int lane, unsigned* cnt32, double* sqacc) {
+    constexpr int L_ = N_ / M_;
+    using LS = LossStage<N_, L_>;
+    bool nan_seen = false;
+    unsigned long long key[CP];
+    int kidx[CP];
+#pragma unroll
+    for (int t = 0; t < CP; ++t) {
+        const int col = lane + 32 * t;
+        key[t] = 0ull;
+        kidx[t] = 0x7fffffff;
+        if (col < N_) {
+            // Re(x conj(sym_k)) in complex128 for every k (loss.py:295), then a tournament over ordered neighbours: the
+            // right-hand winner replaces the left-hand one only if it is strictly greater or NaN and the left is not NaN
+            // -- np.argmax's first-maximum / first-NaN rule for any merge of two index-ordered groups.
+            const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
+            double bv[K_];
+            int bk[K_];
+#pragma unroll
+            for (int k = 0; k < K_; ++k) {
+                bv[k] = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
+                bk[k] = k;
+            }
+#pragma unroll
+            for (int s = 1; s < K_; s *= 2) {
+#pragma unroll
+                for (int i = 0; i + s < K_; i += 2 * s) {
+                    const bool upd = (bv[i] == bv[i]) & ((bv[i + s] > bv[i]) | (bv[i + s] != bv[i + s]));
+                    bv[i] = upd ? bv[i + s] : bv[i];
+                    bk[i] = upd ? bk[i + s] : bk[i];
+                }
+            }
+            key[t] = argmax_key(bv[0]);
+            kidx[t] = (col % M_) * K_ + bk[0];
+            nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
+        }
+    }
+    int dec_ant[CP], dec_k[CP];
+    if constexpr (M_ >= 32) {
+        constexpr int TPS = M_ / 32;
+#pragma unroll
+        for (int s0 = 0; s0 < CP; s0 += TPS) {
+            unsigned long long bkey = key[s0];
+            int bidx = kidx[s0];
+#pragma unroll
+            for (int q = 1; q < TPS; ++q) {                       // the lane's later columns have larger flat indices
+                const bool upd = key[s0 + q] > bkey;
+                bkey = upd ? key[s0 + q] : bkey;
+                bidx = upd ? kidx[s0 + q] : bidx;
+            }
+            const int w = section_argmax<32>(bkey, bidx, lane);
+#pragma unroll
+            for (int q = 0; q < TPS; ++q) {
+                dec_ant[s0 + q] = w / K_;
+                dec_k[s0 + q] = w % K_;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < CP; ++t) {
+            const int w = section_argmax<M_>(key[t], kidx[t], lane);
+            dec_ant[t] = w / K_;
+            dec_k[t] = w % K_;
+        }
+    }
+    bool wrong = false;
+    double sq = 0.0;
+#pragma unroll
+    for (int t = 0; t < CP; ++t) {
+        const int col = lane + 32 * t;
+        if (col < N_) {
+            const int sec = col / M_, m = col % M_;
+            const float2 xt = LS::xt(st)[col];
+            const int k = dec_k[t];
+            const float2 h = (m == dec_ant[t]) ? make_float2((float)al.re[k], (float)al.im[k]) : make_float2(0.f, 0.f);
+            wrong |= (h.x != xt.x) || (h.y != xt.y);
+            const float dr = xh[t].x - xt.x, di = xh[t].y - xt.y;
+            sq += (double)dr * dr + (double)di * di;
+            if (m == 0) {   // one lane per section books the label counters
+                const long long ih = (g.frame_base + f) * (long long)N_ + sec * M_ + dec_ant[t];
+                const long long itrue = LS::idx(st)[sec];
+                const long long sh = al.gray[k], strue = LS::sym(st)[sec];
+                const unsigned long long imask = g.index_bits_kept >= 64 ? ~0ull : ((1ull << g.index_bits_kept) - 1ull);
+                const unsigned ib = __popcll((unsigned long long)(ih ^ itrue) & imask);
+                const unsigned sb = __popcll((unsigned long long)(sh ^ strue) & ((1ull << al.sbits) - 1ull));
+                if (ih != itrue) atomicAdd(&cnt32[C_INDEX_ERR], 1u);
+                if (sh != strue) atomicAdd(&cnt32[C_SYMBOL_ERR], 1u);
+                if (ib) atomicAdd(&cnt32[C_INDEX_BIT], ib);
+                if (sb) atomicAdd(&cnt32[C_SYMBOL_BIT], sb);
+            }
+        }
+    }
+    sqacc[lane] += sq;
+    const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
+    if (lane == 0) {
+        if (any_wrong) atomicAdd(&cnt32[C_FRAME_ERR], 1u);             // Lin = 1: one time slot per frame
+        if (any_nan) atomicAdd(&cnt32[C_NAN_FRAMES], 1u);
+    }
+}
+// fold a warp's shared counters into the global block (Lin = 1: the frame is its only, first, middle and last slot).
+// 32-bit per-warp counts: a warp would need > 6e7 frames of 64 label bits in one call to overflow.
+__device__ __forceinline__ void fast_flush2(const unsigned* cnt32, const double* sqacc, unsigned long long* out, int lane) {
+    __syncwarp();
+    const double sq = warp_sum(sqacc[lane]);
+    if (lane != 0 || !out) return;
+    const int plain[] = {C_FRAMES, C_INDEX_ERR, C_SYMBOL_ERR, C_INDEX_BIT, C_SYMBOL_BIT, C_ITERS, C_NAN_FRAMES};
+    for (int k : plain)
+        if (cnt32[k]) atomicAdd(out + k, (unsigned long long)cnt32[k]);
+    if (cnt32[C_FRAME_ERR]) {
+        const int slots[] = {C_FRAME_ERR, C_SLOT_ERR, C_SLOT_FIRST, C_SLOT_MID, C_SLOT_LAST};
+        for (int k : slots) atomicAdd(out + k, (unsigned long long)cnt32[C_FRAME_ERR]);
+    }
     if (sq != 0.0)
         for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
 }

@@ -12,6 +12,7 @@ struct DevGrid {
     int ok, nr, ni, ncorr;
     double lr2[kGridMax], li2[kGridMax];
     float lr2f[kGridMax], li2f[kGridMax], lrf[kGridMax], lif[kGridMax];
+    float lr2l[kGridMax], li2l[kGridMax];    // float32 residuals lr2 - lr2f, li2 - li2f (compensated exponent offset)
     int ca[kGridCorrMax], cb[kGridCorrMax];
     float cw[kGridCorrMax];                  // multiplicity - 1 (0: unused slot)
     float dpos_r[kGridMax], dneg_r[kGridMax], dpos_i[kGridMax], dneg_i[kGridMax];   // (level - top/bottom level) log2 e
