@@ -67,7 +67,9 @@ struct FastShape {
     static constexpr int ctas_per_sm = DIRECT ? 8 : 2;    // two warps per SM sub-partition either way: 255 registers
 };
 
-template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
+// TRAJ: per-iteration (tau, var, MSE) means are written; a separate instantiation, so that the production kernel carries
+// neither the code nor the registers for it.
+template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT, bool TRAJ>
 __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_cta * 32, FastShape<RT, CTL, M_, K_, DIRECT>::ctas_per_sm)
     bamp_fast_kernel(const __grid_constant__ BampArgs a) {
     using S = FastShape<RT, CTL, M_, K_, DIRECT>;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 if (col < N) {
                     close &= fabsf(vn - var[t]) <= __fadd_rn(kAtol, fabsf(__fmul_rn(kRtol, var[t])));
                     publish(col, xr, xi, vn);
-                    if (a.traj) {
+                    if constexpr (TRAJ) {
                         s_tau += cov[t];
                         s_var += vn;
                         if (a.io.x_true) {
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
             }
             const bool all_close = __all_sync(0xffffffffu, close);
             __syncwarp();     // colvec is published, the exp buffer is free: the next row pass may start
-            if (a.traj) {
+            if constexpr (TRAJ) {
                 s_tau = warp_sum(s_tau);
                 s_var = warp_sum(s_var);
                 s_mse = warp_sum(s_mse);
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 if (a.var) a.var[f * N + col] = var[t];
             }
         }
-        if (a.traj) {
+        if constexpr (TRAJ) {
             __syncwarp();
             for (int it = t_done + lane; it < g.max_iters; it += 32)
                 for (int q = 0; q < 3; ++q)
@@ -579,14 +581,14 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     fast_flush2(cnt32, sqacc, a.io.counters, lane);
 }
 
-template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
-static int launch_shape(const BampArgs& a, cudaStream_t stream) {
+template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT, bool TRAJ>
+static int launch_shape_t(const BampArgs& a, cudaStream_t stream) {
     using S = FastShape<RT, CTL, M_, K_, DIRECT>;
     constexpr int kWarpsPerCta = S::warps_per_cta;
     int dev = 0, sms = 0;
     if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID, DIRECT>;
+    auto kern = bamp_fast_kernel<RT, CTL, M_, K_, GRID, DIRECT, TRAJ>;
     size_t smem = (size_t)S::warp_bytes * kWarpsPerCta;
     if (const char* cap = getenv("AMPSM_CTAS_PER_SM")) {   // occupancy experiments: pad shared memory so that only `cap` CTAs fit
         const int k = atoi(cap);
@@ -608,6 +610,11 @@ static int launch_shape(const BampArgs& a, cudaStream_t stream) {
     kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(a);
     count_launch();
     return check_cuda(cudaGetLastError(), "bamp_fast_kernel launch");
+}
+
+template <int RT, int CTL, int M_, int K_, bool GRID, bool DIRECT>
+static int launch_shape(const BampArgs& a, cudaStream_t stream) {
+    return a.traj ? launch_shape_t<RT, CTL, M_, K_, GRID, DIRECT, true>(a, stream) : launch_shape_t<RT, CTL, M_, K_, GRID, DIRECT, false>(a, stream);
 }
 
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {

@@ -95,7 +95,12 @@ inline DevGrid make_grid(const DevAlphabet& al) {
         g.dpos_i[i] = (float)(g.li2[i] - g.li2[kGridMax - 1]); g.dneg_i[i] = (float)(g.li2[i] - g.li2[0]);
     }
     // the device code hard-wires the reference table's two irregular grid points (see the kernel)
-    const bool ref16 = nc == 2 && g.ca[0] == 1 && g.cb[0] == 3 && g.cw[0] == 1.f && g.ca[1] == 2 && g.cb[1] == 0 && g.cw[1] == -1.f;
+    bool uniform = true;                                       // equally spaced levels on both axes (the rho^l exponentials)
+    for (int i = 2; i < kGridMax; ++i) {
+        if (fabs((lr[i] - lr[i - 1]) - (lr[1] - lr[0])) > 1e-12 * fabs(lr[1] - lr[0])) uniform = false;
+        if (fabs((li[i] - li[i - 1]) - (li[1] - li[0])) > 1e-12 * fabs(li[1] - li[0])) uniform = false;
+    }
+    const bool ref16 = uniform && nc == 2 && g.ca[0] == 1 && g.cb[0] == 3 && g.cw[0] == 1.f && g.ca[1] == 2 && g.cb[1] == 0 && g.cw[1] == -1.f;
     g.ok = ref16 ? 1 : 0;
     return g;
 }
@@ -214,11 +219,14 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
         for (int t = 0; t < CP; ++t) {
             const float off = (lhi[t] - smax[t]) + llo[t];              // <= 0 up to rounding
             const bool rp = q_r[t] >= 0.f, ip = q_i[t] >= 0.f;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                Er[t][l] = fast_ex2(q_r[t] * (rp ? G.dpos_r[l] : G.dneg_r[l]));
-                Ei[t][l] = fast_ex2(fmaf(q_i[t], ip ? G.dpos_i[l] : G.dneg_i[l], off));
-            }
+            // equally spaced levels (make_grid checks it): the four exponentials of an axis are 1, rho, rho^2, rho^3 with
+            // rho = 2^(-|q| spacing), counted from the antenna's largest level -- 3 MUFU per antenna instead of 8
+            const float rho_r = fast_ex2(-fabsf(q_r[t]) * G.dneg_r[1]), rho_i = fast_ex2(-fabsf(q_i[t]) * G.dneg_i[1]);
+            const float e0 = fast_ex2(off);
+            const float rr2 = rho_r * rho_r, rr3 = rr2 * rho_r;
+            const float i1 = e0 * rho_i, i2 = i1 * rho_i, i3 = i2 * rho_i;
+            Er[t][0] = rp ? rr3 : 1.0f; Er[t][1] = rp ? rr2 : rho_r; Er[t][2] = rp ? rho_r : rr2; Er[t][3] = rp ? 1.0f : rr3;
+            Ei[t][0] = ip ? i3 : e0;    Ei[t][1] = ip ? i2 : i1;     Ei[t][2] = ip ? i1 : i2;     Ei[t][3] = ip ? e0 : i3;
             const float a0 = (Er[t][0] + Er[t][1]) + (Er[t][2] + Er[t][3]);
             const float b0 = (Ei[t][0] + Ei[t][1]) + (Ei[t][2] + Ei[t][3]);
             const float a1 = fmaf(G.lrf[0], Er[t][0], G.lrf[1] * Er[t][1]) + fmaf(G.lrf[2], Er[t][2], G.lrf[3] * Er[t][3]);
@@ -304,124 +312,6 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
 }
 
 // ---- Loss on the column-owner layout: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1, one warp per frame ----
-// xmap / xh: the lane's CP columns of the decision input and of the MMSE estimate.  Books into the warp's shared
-// counter block `cnt` (slots as the Counter enum, slot 12 = squared-error sum as double); lane 0 writes.
-template <int N_, int M_, int K_, int CP>
-__device__ __forceinline__ void fast_loss(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const Geom& g,
-                                          const LossIO& io, long long f, int lane, unsigned long long* cnt) {
-    constexpr int L_ = N_ / M_;
-    bool wrong = false, nan_seen = false;
-    double sq = 0.0;
-    Pick best[CP];
-#pragma unroll
-    for (int t = 0; t < CP; ++t) {
-        const int col = lane + 32 * t;
-        best[t] = Pick{-INFINITY, 0x7fffffff};
-        if (col < N_) {
-            const int m = col % M_;
-            // in-order scan (flat index increases with k): the first maximum wins, so replace only on "strictly
-            // greater"; a NaN wins once and then sticks (np.argmax).  Predicated selects, no branches.
-            const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
-            double bv = __dadd_rn(__dmul_rn(xr, al.re[0]), __dmul_rn(xi, al.im[0]));
-            int bk = 0;
-#pragma unroll
-            for (int k = 1; k < K_; ++k) {
-                const double v = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
-                const bool upd = (bv == bv) & ((v > bv) | (v != v));
-                bv = upd ? v : bv;
-                bk = upd ? k : bk;
-            }
-            best[t] = Pick{bv, m * K_ + bk};
-            nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
-        }
-    }
-    int dec_ant[CP], dec_k[CP];
-    if constexpr (M_ >= 32) {
-        constexpr int TPS = M_ / 32;
-#pragma unroll
-        for (int s0 = 0; s0 < CP; s0 += TPS) {
-            Pick b = best[s0];
-#pragma unroll
-            for (int q = 1; q < TPS; ++q)
-                if (pick_better(best[s0 + q], b)) b = best[s0 + q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
-                if (pick_better(other, b)) b = other;
-            }
-#pragma unroll
-            for (int q = 0; q < TPS; ++q) {
-                dec_ant[s0 + q] = b.idx / K_;
-                dec_k[s0 + q] = b.idx % K_;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < CP; ++t) {
-            Pick b = best[t];
-#pragma unroll
-            for (int o = M_ / 2; o > 0; o >>= 1) {
-                Pick other{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o)};
-                if (pick_better(other, b)) b = other;
-            }
-            dec_ant[t] = b.idx / K_;
-            dec_k[t] = b.idx % K_;
-        }
-    }
-    unsigned long long c_idx = 0, c_sym = 0, c_ibit = 0, c_sbit = 0;
-#pragma unroll
-    for (int t = 0; t < CP; ++t) {
-        const int col = lane + 32 * t;
-        if (col < N_) {
-            const int sec = col / M_, m = col % M_;
-            const float2 xt = io.x_true[f * N_ + col];
-            const int k = dec_k[t];
-            const float2 h = (m == dec_ant[t]) ? make_float2((float)al.re[k], (float)al.im[k]) : make_float2(0.f, 0.f);
-            wrong |= (h.x != xt.x) || (h.y != xt.y);
-            const float dr = xh[t].x - xt.x, di = xh[t].y - xt.y;
-            sq += (double)dr * dr + (double)di * di;
-            if (m == 0) {   // one lane per section books the label counters
-                const long long ih = (g.frame_base + f) * (long long)N_ + sec * M_ + dec_ant[t];
-                const long long itrue = io.idx_true[f * L_ + sec];
-                const long long sh = al.gray[k], st = io.sym_true[f * L_ + sec];
-                const unsigned long long imask = g.index_bits_kept >= 64 ? ~0ull : ((1ull << g.index_bits_kept) - 1ull);
-                c_idx += (ih != itrue);
-                c_sym += (sh != st);
-                c_ibit += __popcll((unsigned long long)(ih ^ itrue) & imask);
-                c_sbit += __popcll((unsigned long long)(sh ^ st) & ((1ull << al.sbits) - 1ull));
-            }
-        }
-    }
-    unsigned long long packed = c_idx | (c_sym << 12) | (c_ibit << 24) | (c_sbit << 44);   // <= 64 sections, 64 bits each
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
-    sq = warp_sum(sq);
-    const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
-    if (lane == 0) {
-        cnt[C_INDEX_ERR] += packed & 0xfffull;
-        cnt[C_SYMBOL_ERR] += (packed >> 12) & 0xfffull;
-        cnt[C_INDEX_BIT] += (packed >> 24) & 0xfffffull;
-        cnt[C_SYMBOL_BIT] += packed >> 44;
-        cnt[C_FRAME_ERR] += any_wrong;                       // Lin = 1: one time slot per frame
-        cnt[C_NAN_FRAMES] += any_nan;
-        reinterpret_cast<double*>(cnt)[12] += sq;
-    }
-}
-// flush a warp's shared counter block into the global one (Lin = 1: the frame is its only, first, middle and last slot)
-__device__ __forceinline__ void fast_flush_counters(const unsigned long long* cnt, unsigned long long* out) {
-    const int plain[] = {C_FRAMES, C_INDEX_ERR, C_SYMBOL_ERR, C_INDEX_BIT, C_SYMBOL_BIT, C_ITERS, C_NAN_FRAMES};
-    for (int k : plain)
-        if (cnt[k]) atomicAdd(out + k, cnt[k]);
-    if (cnt[C_FRAME_ERR]) {
-        const int slots[] = {C_FRAME_ERR, C_SLOT_ERR, C_SLOT_FIRST, C_SLOT_MID, C_SLOT_LAST};
-        for (int k : slots) atomicAdd(out + k, cnt[C_FRAME_ERR]);
-    }
-    const double sq = reinterpret_cast<const double*>(cnt)[12];
-    if (sq != 0.0)
-        for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<double*>(out) + C_SQERR + k, sq);
-}
-
-// ---- Loss, low-latency version: the per-frame epilogue of the register-resident kernels ---------------------------------
 // The first version cost ~3600 cycles per frame on B200 (phase clocks, scripts/phase_clocks.py) -- more than one whole
 // BAMP iteration -- almost all of it exposed latency: a 15-step float64 compare chain per column, a 5-step shuffle
 // butterfly on (double, int) picks, x_true / label loads from L2 on first use, and two more 5-step butterflies for the
@@ -434,6 +324,11 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 

@@ -42,8 +42,12 @@ struct VFastShape {
     static constexpr int rowstate = rowvec + (R + R / 8) * 16;            // float4 [R] {y~.re, y~.im, s^2, -}
     static constexpr int ystage = rowstate + R * 16;                      // float2 [kMaxRows]
     static constexpr int xmapvec = ystage + kMaxRows * 8;                 // float2 [N]  r (the Loss input)
-    static constexpr int cnt = xmapvec + N * 8;                           // u64 [16]
-    static constexpr int total = cnt + 128;
+    static constexpr int cnt = xmapvec + N * 8;                           // u32 [16] the warp's counters
+    static constexpr int sq = cnt + 64;                                   // double [32] per-lane squared-error sums
+    static constexpr int loss = sq + 256;                                 // x_true, labels of the current frame (LossStage)
+    static constexpr int sstage = (loss + LossStage<N, N / M_>::bytes + 15) & ~15;   // float [R]  singular values of the staged frame
+    static constexpr int ustage = sstage + R * 4;                         // float2 [kMaxRows][R]  U of the staged frame (y: ystage)
+    static constexpr int total = (ustage + kMaxRows * R * 8 + 127) & ~127;
 };
 
 __device__ __forceinline__ float clampF(float v, float lo, float hi) {
@@ -71,7 +75,12 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     float4* rowstate = reinterpret_cast<float4*>(smem + S::rowstate);
     float2* ystage = reinterpret_cast<float2*>(smem + S::ystage);
     float2* xmapvec = reinterpret_cast<float2*>(smem + S::xmapvec);
-    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(smem + S::cnt);
+    unsigned* cnt32 = reinterpret_cast<unsigned*>(smem + S::cnt);
+    double* sqacc = reinterpret_cast<double*>(smem + S::sq);
+    unsigned char* lstage = smem + S::loss;
+    const float* sstage = reinterpret_cast<const float*>(smem + S::sstage);
+    const float2* ustage = reinterpret_cast<const float2*>(smem + S::ustage);
+    using LS = LossStage<N, L_>;
 
     const Geom& g = a.g;
     const DevAlphabet& al = a.al;
@@ -87,7 +96,8 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     const double sp = a.sparsity;
     const double s2t0_d = sp * sp * (1.0 - sp) + (1.0 - sp) * (1.0 - sp) * sp;   // python float (vamp.py:26)
 
-    if (lane < 16) cnt[lane] = 0ull;
+    if (lane < 16) cnt32[lane] = 0u;
+    sqacc[lane] = 0.0;
     __syncwarp();
 
     // column-vector exchange: per column one float4 {x,x,y,y} (the broadcast operand pairs of the row pass), placed so
@@ -111,38 +121,38 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             }
         }
     };
-    auto l2_prefetch = [&](long long ff) {    // one frame ahead, so that the tile loads and the y~ loop hit in L2
-        if (lane == 0) {
-            if (a.Vh_stride) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Vall + ff * a.Vh_stride), "r"(R * N * 8) : "memory");
-            if (a.U_stride) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Uall + ff * a.U_stride), "r"(n * R * 8) : "memory");
-        } else if (lane == 1) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(yall + ff * n));
-            if (n > 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(yall + ff * n + 16));
-            if (a.s_stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(sall + ff * a.s_stride));
-        } else if (a.io.x_true) {
-            if (lane >= 2 && (lane - 2) * 16 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.x_true + ff * N + (lane - 2) * 16));
-            if (lane == 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.idx_true + ff * L_));
-            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.io.sym_true + ff * L_));
+    // One frame ahead: the Vh tile into L2 (load_tile() then hits there), and U, y, s into the warp's shared-memory stage by
+    // cp.async -- y~ = diag(s) U^H y is formed at the start of a frame, and with U read from L2 on first use that loop
+    // alone cost ~3000 cycles per frame (four rounds of eight dependent L2 loads).  The stage is refilled for frame f + 1
+    // as soon as y~ of frame f is formed, so the copy has a whole frame to land.
+    auto stage_factors = [&](long long ff) {
+        if (ff < a.frames) {
+            if (lane == 0 && a.Vh_stride)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Vall + ff * a.Vh_stride), "r"(R * N * 8) : "memory");
+            const float2* Uf = Uall + ff * a.U_stride;
+            for (int c = lane; c < n * (R / 2); c += 32) cp_async16(smem + S::ustage + c * 16, Uf + 2 * c);
+            for (int c = lane; c < n; c += 32) cp_async8(smem + S::ystage + c * 8, yall + ff * n + c);
+            cp_async4(smem + S::sstage + lane * 4, sall + ff * a.s_stride + lane);
         }
+        cp_async_commit();                     // always one group per call: the wait_group counts below rely on it
     };
     long long f = blockIdx.x;
     if (f < a.frames) load_tile(f);
 
+    stage_factors(f);
     for (; f < a.frames; f += gridDim.x) {
-        {
-            const long long nf = f + gridDim.x;
-            if (nf < a.frames) l2_prefetch(nf);
-        }
-        // ---- y~ = (s U^H) y (vamp.py:22): lane k owns singular value k; U column-wise, coalesced over k
-        for (int i = lane; i < n; i += 32) ystage[i] = __ldg(yall + f * n + i);
+        // the Loss inputs of this frame: staged long before the epilogue (one commit group per frame, empty without labels)
+        if (a.io.x_true) LS::issue(lstage, a.io, f, lane);
+        else cp_async_commit();
+        // ---- y~ = (s U^H) y (vamp.py:22): lane k owns singular value k; U column-wise from the stage (conflict-free)
+        cp_async_wait_group<1>();              // pending: {factors of f, Loss inputs of f} -> the factors are complete
         __syncwarp();
         {
-            const float2* Uf = Uall + f * a.U_stride;
-            const float sk = __ldg(sall + f * a.s_stride + lane);
+            const float sk = sstage[lane];
             float ar = 0.f, ai = 0.f;
 #pragma unroll 8
             for (int i = 0; i < n; ++i) {
-                const float2 u = __ldg(Uf + (size_t)i * R + lane);
+                const float2 u = ustage[i * R + lane];
                 const float2 yv = ystage[i];
                 const float wr = sk * u.x, wi = -(sk * u.y);            // s * conj(U)
                 ar += wr * yv.x - wi * yv.y;
@@ -150,6 +160,8 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             }
             rowstate[lane] = make_float4(ar, ai, sk * sk, 0.f);         // vamp.py:17
         }
+        __syncwarp();                          // every lane is done with the stage: refill it for the next frame
+        stage_factors(f + gridDim.x);
         const double noise_var_d = a.sigma2_pf ? (double)a.sigma2_pf[f] : a.sigma2_d;
         const float nv = (float)noise_var_d;
         float s2t = (float)s2t0_d;
@@ -349,14 +361,17 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         }
         if (lane == 0) {
             if (a.iters) a.iters[f] = t_done;
-            cnt[C_FRAMES] += 1;
-            cnt[C_ITERS] += t_done;
+            atomicAdd(&cnt32[C_FRAMES], 1u);
+            atomicAdd(&cnt32[C_ITERS], (unsigned)t_done);
         }
-        if (a.io.x_true) fast_loss<N, M_, K_, CP>(xmap, xh, al, g, a.io, f, lane, cnt);   // Loss is fed T.r as xmap (vamp.py:187)
+        if (a.io.x_true) {                                       // Loss is fed T.r as xmap (vamp.py:187)
+            cp_async_wait_group<1>();          // pending: {Loss inputs of f, factors of the next frame} -> the former are complete
+            __syncwarp();
+            fast_loss2<N, M_, K_, CP>(xmap, xh, al, g, lstage, f, lane, cnt32, sqacc);
+        }
         __syncwarp();
     }
-    __syncwarp();
-    if (a.io.counters && lane == 0) fast_flush_counters(cnt, a.io.counters);
+    fast_flush2(cnt32, sqacc, a.io.counters, lane);
 }
 
 template <int RT, int CTL, int M_, int K_, bool GRID, int WPS>
@@ -394,8 +409,9 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
     const Geom& g = a.g;
     // complex64, one time slot per frame, MAP decision, per-section shift; 16-byte aligned rows for the tile loads
     if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0 || g.R != 32 || g.N != 64 || g.n > 64 || g.n < 1) return AMPSM_ENOFIT;
+    if (reinterpret_cast<uintptr_t>(a.io.x_true) % 16) return AMPSM_ENOFIT;     // the Loss inputs are staged by 16-byte cp.async
     if ((reinterpret_cast<uintptr_t>(a.Vh) % 16) || (a.Vh_stride != 0 && ((size_t)a.Vh_stride * 8) % 16) ||
-        (reinterpret_cast<uintptr_t>(a.U) % 8) || (reinterpret_cast<uintptr_t>(a.y) % 8))
+        (reinterpret_cast<uintptr_t>(a.U) % 16) || (reinterpret_cast<uintptr_t>(a.y) % 8) || (reinterpret_cast<uintptr_t>(a.s) % 4))
         return AMPSM_ENOFIT;
     const int K = a.al.K;
     VampArgs b = a;

@@ -19,15 +19,27 @@ ap.add_argument("--frames", type=int, default=148 * 8 * 128)
 ap.add_argument("--fixed", action="store_true")
 ap.add_argument("--iters", type=int, default=bench.ITERS)
 ap.add_argument("--snr-db", type=float, default=15.0)
+ap.add_argument("--vamp", action="store_true", help="time the VAMP fast kernel (per-frame SVD factors) instead")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = pkg.Config(bench.NT, bench.NA, bench.NR, 1, 1, batch=a.frames, generator_mode='sparc', iterations=a.iters,
                  alphabet=bench.ALPHABET, channel_profile='uniform', device="cuda:0")
 H, y, x, labels, idx = bench.make_gpu_inputs(torch, cfg, a.frames, a.snr_db, dev, 1234)
-amp = pkg.BAMP(cfg, kernel='auto', outputs=False, early_exit=not a.fixed)
 lib = _cabi.lib()
-have_clk = hasattr(lib, "ampsm_debug_clocks")
+have_clk = hasattr(lib, "ampsm_debug_clocks") and not a.vamp
 snr = 10 ** (a.snr_db / 10)
+if a.vamp:
+    vamp = pkg.VAMP(cfg, kernel='auto', outputs=False, early_exit=not a.fixed)
+    from amp_sparc_spatialmodulation_b200.vamp import svd_batched
+    U, sv, Vh = svd_batched(H)                  # the library's Jacobi kernel (cuSOLVER's batched SVD takes minutes here)
+    del H
+
+    class _V:
+        def detect(self, H_, y_, snr_, x_, lab_, idx_):
+            return vamp.detect(U, sv, Vh, y_, snr_, x_, lab_, idx_)
+    amp, H = _V(), None
+else:
+    amp = pkg.BAMP(cfg, kernel='auto', outputs=False, early_exit=not a.fixed)
 for _ in range(2):
     det = amp.detect(H, y, snr, x, labels, idx)
 torch.cuda.synchronize()
@@ -43,7 +55,7 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 c = det.counters_dict()
 fi = c["iters"]
-print(f"ctas/sm={os.environ.get('AMPSM_CTAS_PER_SM', 'default')} fixed={a.fixed} iters={a.iters} frames={a.frames} mean T={fi / a.frames:.3f} "
+print(f"{'VAMP' if a.vamp else 'BAMP'} ctas/sm={os.environ.get('AMPSM_CTAS_PER_SM', 'default')} fixed={a.fixed} iters={a.iters} frames={a.frames} mean T={fi / a.frames:.3f} "
       f"{ms:.3f} ms  {fi / ms * 1e3:.4e} frame-iter/s  {a.frames / ms * 1e3:.4e} frames/s", flush=True)
 if have_clk:
     out = (C.c_ulonglong * 8)()

@@ -271,8 +271,12 @@ def test_vamp_fast_and_generic_kernels_agree(alphabet, Na, snr_db):
     assert (ia == ib).mean() >= (ic == ib).mean() - 0.06, ((ia == ib).mean(), (ic == ib).mean())
     assert (np.abs(ia - ib) <= 1).mean() >= (np.abs(ic - ib) <= 1).mean() - 0.04
     assert abs(ia.mean() - ib.mean()) < 0.02 * ib.mean()
+    # Net error counts: any two float32 evaluation orders of VAMP decide ~0.5 % of the frames differently, in both
+    # directions (scripts/diag_vamp_flip.py on B200, 20k frames at 12 dB: fast vs f64-exp 103-117 frames, generic f32-exp
+    # vs f64-exp 83-94, each split about evenly into better / worse), so the NET difference is a random walk of
+    # ~sqrt(100) = 10 counts per sigma; 2e-3 F = 40 is four sigma.
     for k in INT_KEYS:
-        slack = max(4, 1e-3 * F) * (4 if k.endswith("bit_err") else 1)
+        slack = max(4, 2e-3 * F) * (4 if k.endswith("bit_err") else 1)
         assert abs(ca[k] - cb[k]) <= abs(cc[k] - cb[k]) + slack, (k, ca[k], cb[k], cc[k])
     d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
     d32 = (c.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
