@@ -23,15 +23,8 @@
 
 namespace ampsm {
 
-// Phase timing for development builds (-DAMPSM_CLK, scripts/phase_clocks.py): lane 0 of every warp accumulates the cycles
-// between phase boundaries; ampsm_debug_clocks() returns the sums over all warps.  Compiled out of the shipped library.
 #ifdef AMPSM_CLK
 __device__ unsigned long long g_clk[16];
-#define CLK_INIT() unsigned clk_last_ = clock()
-#define CLK(p) do { const unsigned now_ = clock(); if (lane == 0) atomicAdd(&clkacc[p], now_ - clk_last_); clk_last_ = now_; } while (0)
-#else
-#define CLK_INIT() do {} while (0)
-#define CLK(p) do {} while (0)
 #endif
 
 // DIRECT = false: the frame's H lands in a per-warp staging buffer (bulk TMA) and |H|^2 lives in registers next to H.
@@ -567,7 +560,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
         if (a.io.x_true) {
             cp_async_wait_all();
             __syncwarp();
-            fast_loss2<N, M_, K_, CP>(xmap, xh, al, g, lstage, f, lane, cnt32, sqacc);
+            fast_loss2<N, M_, K_, CP, GRID>(xmap, xh, al, a.grid, g, lstage, f, lane, cnt32, sqacc);
         }
         __syncwarp();
         CLK(6);                                  // tile load issue, outputs, Loss epilogue

@@ -7,6 +7,17 @@
 
 namespace ampsm {
 
+// Phase timing for development builds (-DAMPSM_CLK, scripts/build_clk.sh, scripts/phase_clocks.py): lane 0 of every warp
+// accumulates the cycles between phase boundaries in `clkacc` (16 shared 32-bit slots per warp); the kernels add them to
+// a global array that ampsm_debug_clocks() / ampsm_debug_clocks_vamp() return.  Compiled out of the shipped library.
+#ifdef AMPSM_CLK
+#define CLK_INIT() unsigned clk_last_ = clock()
+#define CLK(p) do { const unsigned now_ = clock(); if (lane == 0) atomicAdd(&clkacc[p], now_ - clk_last_); clk_last_ = now_; } while (0)
+#else
+#define CLK_INIT() do {} while (0)
+#define CLK(p) do {} while (0)
+#endif
+
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -102,6 +113,16 @@ inline DevGrid make_grid(const DevAlphabet& al) {
     }
     const bool ref16 = uniform && nc == 2 && g.ca[0] == 1 && g.cb[0] == 3 && g.cw[0] == 1.f && g.ca[1] == 2 && g.cb[1] == 0 && g.cw[1] == -1.f;
     g.ok = ref16 ? 1 : 0;
+    // corners of the grid in the table (the Loss shortcut of fast_loss2): every corner must be present, with a negative
+    // bottom and a positive top level on both axes
+    g.corner_ok = (lr[0] < 0 && lr[nr - 1] > 0 && li[0] < 0 && li[ni - 1] > 0) ? 1 : 0;
+    for (int sl = 0; sl < 4; ++sl) {
+        const double cr = (sl & 2) ? lr[0] : lr[nr - 1], ci = (sl & 1) ? li[0] : li[ni - 1];
+        g.corner_k[sl] = -1;
+        for (int k = al.K - 1; k >= 0; --k)
+            if (al.re[k] == cr && al.im[k] == ci) g.corner_k[sl] = k;
+        if (g.corner_k[sl] < 0) g.corner_ok = 0;
+    }
     return g;
 }
 
@@ -372,9 +393,16 @@ __device__ __forceinline__ int section_argmax(unsigned long long key, int idx, i
 // xmap / xh: the lane's CP columns (column = lane + 32 t) of the decision input and of the MMSE estimate; `st` the staged
 // inputs of this frame (LossStage, complete: cp.async.wait_all + __syncwarp done by the caller).  cnt32: the warp's 16
 // shared counters (Counter enum slots), sqacc: 32 per-lane float64 squared-error sums.
-template <int N_, int M_, int K_, int CP>
-__device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const Geom& g,
-                                           const unsigned char* st, long long f, int lane, unsigned* cnt32, double* sqacc) {
+// GRID (product-grid alphabets, make_grid): Re(x conj(s)) = x.re s.re + x.im s.im is maximised by the corner of the grid
+// that carries the signs of x, by a margin of (level spacing) x min(|x.re|, |x.im|) before rounding; whenever that margin
+// exceeds the float64 rounding of the two products and the sum by orders of magnitude (min > 1e-12 max, both finite) the
+// corner is the UNIQUE maximum of the rounded values as well, so np.argmax's answer for the column is the corner's first
+// table index and only its metric needs to be evaluated (3 float64 instructions instead of ~50 + a 15-merge tournament).
+// Columns that fail the test (zeros, NaN, Inf, extreme ratios) take the full tournament.
+template <int N_, int M_, int K_, int CP, bool GRID>
+__device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const DevGrid& G,
+                                           const Geom& g, const unsigned char* st, long long f, int lane, unsigned* cnt32,
+                                           double* sqacc) {
     constexpr int L_ = N_ / M_;
     using LS = LossStage<N_, L_>;
     bool nan_seen = false;
@@ -390,24 +418,38 @@ __device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float
             // right-hand winner replaces the left-hand one only if it is strictly greater or NaN and the left is not NaN
             // -- np.argmax's first-maximum / first-NaN rule for any merge of two index-ordered groups.
             const double xr = (double)xmap[t].x, xi = (double)xmap[t].y;
-            double bv[K_];
-            int bk[K_];
-#pragma unroll
-            for (int k = 0; k < K_; ++k) {
-                bv[k] = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
-                bk[k] = k;
+            bool corner = false;
+            if constexpr (GRID) {
+                const float ax = fabsf(xmap[t].x), ay = fabsf(xmap[t].y);
+                corner = G.corner_ok && fminf(ax, ay) > 1e-12f * fmaxf(ax, ay) && fmaxf(ax, ay) < INFINITY;   // false for NaN
             }
+            double wv;
+            int wk;
+            if (corner) {
+                wk = G.corner_k[(xmap[t].x < 0.f ? 2 : 0) + (xmap[t].y < 0.f ? 1 : 0)];
+                wv = __dadd_rn(__dmul_rn(xr, al.re[wk]), __dmul_rn(xi, al.im[wk]));
+            } else {
+                double bv[K_];
+                int bk[K_];
 #pragma unroll
-            for (int s = 1; s < K_; s *= 2) {
-#pragma unroll
-                for (int i = 0; i + s < K_; i += 2 * s) {
-                    const bool upd = (bv[i] == bv[i]) & ((bv[i + s] > bv[i]) | (bv[i + s] != bv[i + s]));
-                    bv[i] = upd ? bv[i + s] : bv[i];
-                    bk[i] = upd ? bk[i + s] : bk[i];
+                for (int k = 0; k < K_; ++k) {
+                    bv[k] = __dadd_rn(__dmul_rn(xr, al.re[k]), __dmul_rn(xi, al.im[k]));
+                    bk[k] = k;
                 }
+#pragma unroll
+                for (int s = 1; s < K_; s *= 2) {
+#pragma unroll
+                    for (int i = 0; i + s < K_; i += 2 * s) {
+                        const bool upd = (bv[i] == bv[i]) & ((bv[i + s] > bv[i]) | (bv[i + s] != bv[i + s]));
+                        bv[i] = upd ? bv[i + s] : bv[i];
+                        bk[i] = upd ? bk[i + s] : bk[i];
+                    }
+                }
+                wv = bv[0];
+                wk = bk[0];
             }
-            key[t] = argmax_key(bv[0]);
-            kidx[t] = (col % M_) * K_ + bk[0];
+            key[t] = argmax_key(wv);
+            kidx[t] = (col % M_) * K_ + wk;
             nan_seen |= (xmap[t].x != xmap[t].x) || (xmap[t].y != xmap[t].y);
         }
     }

@@ -27,6 +27,9 @@ namespace ampsm {
 
 namespace {
 
+#ifdef AMPSM_CLK
+__device__ unsigned long long g_clk_v[16];
+#endif
 
 template <int RT, int CTL, int M_, int K_, bool GRID>
 struct VFastShape {
@@ -46,8 +49,11 @@ struct VFastShape {
     static constexpr int sq = cnt + 64;                                   // double [32] per-lane squared-error sums
     static constexpr int loss = sq + 256;                                 // x_true, labels of the current frame (LossStage)
     static constexpr int sstage = (loss + LossStage<N, N / M_>::bytes + 15) & ~15;   // float [R]  singular values of the staged frame
-    static constexpr int ustage = sstage + R * 4;                         // float2 [kMaxRows][R]  U of the staged frame (y: ystage)
-    static constexpr int total = (ustage + kMaxRows * R * 8 + 127) & ~127;
+    static constexpr int ustage = (sstage + R * 4 + 127) & ~127;          // float2 [kMaxRows][R]  U of the staged frame (y: ystage)
+    static constexpr int ypair = ustage + kMaxRows * R * 8;               // float4 [kMaxRows] {y.re, y.im, y.im, -y.re}
+    static constexpr int ubar = ypair + kMaxRows * 16;                    // mbarrier of the bulk copy of U
+    static constexpr int clk = ubar + 16;                                 // phase clocks (development builds)
+    static constexpr int total = (clk + 64 + 127) & ~127;
 };
 
 __device__ __forceinline__ float clampF(float v, float lo, float hi) {
@@ -80,6 +86,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     unsigned char* lstage = smem + S::loss;
     const float* sstage = reinterpret_cast<const float*>(smem + S::sstage);
     const float2* ustage = reinterpret_cast<const float2*>(smem + S::ustage);
+    float4* ypair = reinterpret_cast<float4*>(smem + S::ypair);
     using LS = LossStage<N, L_>;
 
     const Geom& g = a.g;
@@ -95,9 +102,14 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     const float eta = (float)eta_d, one_m_eta = (float)(1.0 - eta_d);
     const double sp = a.sparsity;
     const double s2t0_d = sp * sp * (1.0 - sp) + (1.0 - sp) * (1.0 - sp) * sp;   // python float (vamp.py:26)
+    const float ratio0_shared = (float)(a.sigma2_d / s2t0_d);                    // one float64 division per kernel, not per frame
 
     if (lane < 16) cnt32[lane] = 0u;
     sqacc[lane] = 0.0;
+#ifdef AMPSM_CLK
+    unsigned* clkacc = reinterpret_cast<unsigned*>(smem + S::clk);
+    if (lane < 16) clkacc[lane] = 0u;
+#endif
     __syncwarp();
 
     // column-vector exchange: per column one float4 {x,x,y,y} (the broadcast operand pairs of the row pass), placed so
@@ -125,12 +137,23 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     // cp.async -- y~ = diag(s) U^H y is formed at the start of a frame, and with U read from L2 on first use that loop
     // alone cost ~3000 cycles per frame (four rounds of eight dependent L2 loads).  The stage is refilled for frame f + 1
     // as soon as y~ of frame f is formed, so the copy has a whole frame to land.
+    uint64_t* ubar = reinterpret_cast<uint64_t*>(smem + S::ubar);
+    if (lane == 0) {
+        mbar_init(ubar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
     auto stage_factors = [&](long long ff) {
         if (ff < a.frames) {
-            if (lane == 0 && a.Vh_stride)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Vall + ff * a.Vh_stride), "r"(R * N * 8) : "memory");
-            const float2* Uf = Uall + ff * a.U_stride;
-            for (int c = lane; c < n * (R / 2); c += 32) cp_async16(smem + S::ustage + c * 16, Uf + 2 * c);
+            if (lane == 0) {
+                if (a.Vh_stride)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Vall + ff * a.Vh_stride), "r"(R * N * 8) : "memory");
+                // U of the frame is one contiguous block: ONE bulk copy (the first version issued 16 cp.async per lane,
+                // ~1000 cycles of LSU issue per frame)
+                fence_proxy_async();           // the generic-proxy reads of the stage are ordered before the async-proxy write
+                mbar_expect_tx(ubar, (uint32_t)(n * R * 8));
+                tma_load_1d(smem + S::ustage, Uall + ff * a.U_stride, (uint32_t)(n * R * 8), ubar);
+            }
             for (int c = lane; c < n; c += 32) cp_async8(smem + S::ystage + c * 8, yall + ff * n + c);
             cp_async4(smem + S::sstage + lane * 4, sall + ff * a.s_stride + lane);
         }
@@ -140,30 +163,58 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     if (f < a.frames) load_tile(f);
 
     stage_factors(f);
+    uint32_t uphase = 0;
+    CLK_INIT();
     for (; f < a.frames; f += gridDim.x) {
         // the Loss inputs of this frame: staged long before the epilogue (one commit group per frame, empty without labels)
         if (a.io.x_true) LS::issue(lstage, a.io, f, lane);
         else cp_async_commit();
         // ---- y~ = (s U^H) y (vamp.py:22): lane k owns singular value k; U column-wise from the stage (conflict-free)
-        cp_async_wait_group<1>();              // pending: {factors of f, Loss inputs of f} -> the factors are complete
+        cp_async_wait_group<1>();              // pending: {y, s of f; Loss inputs of f} -> y and s are complete
+        mbar_wait(ubar, uphase);               // U of f
+        uphase ^= 1u;
+        __syncwarp();
+        // operand pairs of the packed product: conj(u) y = (u.re y.re + u.im y.im) + i (u.re y.im - u.im y.re), so with u as the
+        // natural (re, im) pair  A += u (y.re, y.im),  B += u (y.im, -y.re)  ->  re = A.lo + A.hi, im = B.lo + B.hi
+        for (int i = lane; i < n; i += 32) {
+            const float2 yv = ystage[i];
+            ypair[i] = make_float4(yv.x, yv.y, yv.y, -yv.x);
+        }
         __syncwarp();
         {
             const float sk = sstage[lane];
-            float ar = 0.f, ai = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < n; ++i) {
-                const float2 u = ustage[i * R + lane];
-                const float2 yv = ystage[i];
-                const float wr = sk * u.x, wi = -(sk * u.y);            // s * conj(U)
-                ar += wr * yv.x - wi * yv.y;
-                ai += wr * yv.y + wi * yv.x;
+            const pair_t* up = reinterpret_cast<const pair_t*>(ustage) + lane;
+            pair_t A0 = 0ull, B0 = 0ull, A1 = 0ull, B1 = 0ull;   // two interleaved chains per component
+            int i = 0;
+#pragma unroll 4
+            for (; i + 2 <= n; i += 2) {
+                const ulonglong2 y0 = *reinterpret_cast<const ulonglong2*>(&ypair[i]);
+                const ulonglong2 y1 = *reinterpret_cast<const ulonglong2*>(&ypair[i + 1]);
+                const pair_t u0 = up[i * R], u1 = up[(i + 1) * R];
+                A0 = ffma2(u0, y0.x, A0);
+                B0 = ffma2(u0, y0.y, B0);
+                A1 = ffma2(u1, y1.x, A1);
+                B1 = ffma2(u1, y1.y, B1);
             }
-            rowstate[lane] = make_float4(ar, ai, sk * sk, 0.f);         // vamp.py:17
+            if (i < n) {
+                const ulonglong2 y0 = *reinterpret_cast<const ulonglong2*>(&ypair[i]);
+                A0 = ffma2(up[i * R], y0.x, A0);
+                B0 = ffma2(up[i * R], y0.y, B0);
+            }
+            float a0l, a0h, a1l, a1h, b0l, b0h, b1l, b1h;
+            unpack2(A0, a0l, a0h);
+            unpack2(A1, a1l, a1h);
+            unpack2(B0, b0l, b0h);
+            unpack2(B1, b1l, b1h);
+            // y~ = (s U^H) y (vamp.py:17, 22); the scaling by s is applied to the sum (rounding only)
+            rowstate[lane] = make_float4(sk * ((a0l + a0h) + (a1l + a1h)), sk * ((b0l + b0h) + (b1l + b1h)), sk * sk, 0.f);
         }
         __syncwarp();                          // every lane is done with the stage: refill it for the next frame
+        CLK(6);                                // Loss-input issue, wait for the stage, y~
         stage_factors(f + gridDim.x);
         const double noise_var_d = a.sigma2_pf ? (double)a.sigma2_pf[f] : a.sigma2_d;
         const float nv = (float)noise_var_d;
+        const float ratio0 = a.sigma2_pf ? (float)(noise_var_d / s2t0_d) : ratio0_shared;   // python-float division (vamp.py:66)
         float s2t = (float)s2t0_d;
         // state (vamp.py:23-26): r~ = sparsity, var = 1; the column owner (column = lane + 32 t) publishes them
 #pragma unroll
@@ -179,12 +230,13 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         __syncwarp();
 
         int t_done = 0;
+        CLK(7);                                // stage refill issue, state init
         for (int it = 0; it < g.max_iters; ++it) {
             // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66).  The scalar
             // divisions of the bookkeeping are MUFU reciprocals (2^-23 relative): an IEEE division is a ~15-instruction
             // dependent sequence, eight of them per iteration sat on the critical path of the first version.
             const float rs2t = fast_rcp(s2t);
-            const float ratio = (it == 0) ? (float)(noise_var_d / s2t0_d) : nv * rs2t;
+            const float ratio = (it == 0) ? ratio0 : nv * rs2t;
             // ================= row pass: q = Vh r~ (vamp.py:67) =================
             {
                 constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
@@ -222,6 +274,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 }
             }
             __syncwarp();
+            CLK(0);                            // row pass
             // ================= LMMSE in the SVD basis: d = scale (y~ + ratio q) - q (vamp.py:68-72) =================
             float scale;
             {
@@ -236,6 +289,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 rowvec[lane + (lane >> 3)] = make_float4(dx, dy, dy, -dx);      // operand pairs (dx,dy), (dy,-dx)
             }
             __syncwarp();
+            CLK(1);                            // row reduction, LMMSE
             // ================= column pass: V d (vamp.py:72) =================
             {
                 constexpr int CH = CTL > 4 ? CTL / 2 : CTL;
@@ -277,6 +331,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             const float sig2 = clampF(alpha * inv_1ma * s2t, var_min, var_max);
             const float rsig = __frcp_rn(sig2);                                // the one accurate reciprocal: it scales every exponent
             __syncwarp();
+            CLK(2);                            // column pass, scalars
             // ================= r = (x~ - alpha r~)/(1 - alpha), denoiser with the scalar variance (vamp.py:79-84) ==========
             float2 r[CP];
             float q_r[CP], q_i[CP], var_old[CP];
@@ -297,8 +352,10 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 var_old[t] = varvec[col];
             }
             __syncwarp();     // everyone has read r~ and the partials
+            CLK(3);                            // column reduction, r
             float xr_[CP], xi_[CP], vn_[CP];
             fast_denoise<N, M_, K_, GRID, CP>(q_r, q_i, al, a.grid, ebuf, lane, xr_, xi_, vn_);
+            CLK(4);                            // denoiser
             // ================= Onsager bookkeeping (vamp.py:85-94), exit test on var (vamp.py:185) =================
             float vs = 0.f;
             bool close = true;
@@ -337,6 +394,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 }
             }
             t_done = it + 1;
+            CLK(5);                            // Onsager scalars, publish
             if (g.early_exit && all_close) break;
         }
         {   // the tile registers are free: fetch the next frame's tile under the Loss epilogue
@@ -367,10 +425,15 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         if (a.io.x_true) {                                       // Loss is fed T.r as xmap (vamp.py:187)
             cp_async_wait_group<1>();          // pending: {Loss inputs of f, factors of the next frame} -> the former are complete
             __syncwarp();
-            fast_loss2<N, M_, K_, CP>(xmap, xh, al, g, lstage, f, lane, cnt32, sqacc);
+            fast_loss2<N, M_, K_, CP, GRID>(xmap, xh, al, a.grid, g, lstage, f, lane, cnt32, sqacc);
         }
         __syncwarp();
+        CLK(8);                                // tile load issue, outputs, Loss epilogue
     }
+#ifdef AMPSM_CLK
+    __syncwarp();
+    if (lane < 16) atomicAdd(&g_clk_v[lane], (unsigned long long)clkacc[lane]);
+#endif
     fast_flush2(cnt32, sqacc, a.io.counters, lane);
 }
 
@@ -427,3 +490,12 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace ampsm
+
+#ifdef AMPSM_CLK
+extern "C" int ampsm_debug_clocks_vamp(unsigned long long* out16, int reset) {
+    unsigned long long z[16] = {};
+    if (out16 && cudaMemcpyFromSymbol(out16, ampsm::g_clk_v, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset && cudaMemcpyToSymbol(ampsm::g_clk_v, z, sizeof(z)) != cudaSuccess) return 1;
+    return 0;
+}
+#endif

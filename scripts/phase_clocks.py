@@ -26,7 +26,8 @@ cfg = pkg.Config(bench.NT, bench.NA, bench.NR, 1, 1, batch=a.frames, generator_m
                  alphabet=bench.ALPHABET, channel_profile='uniform', device="cuda:0")
 H, y, x, labels, idx = bench.make_gpu_inputs(torch, cfg, a.frames, a.snr_db, dev, 1234)
 lib = _cabi.lib()
-have_clk = hasattr(lib, "ampsm_debug_clocks") and not a.vamp
+have_clk = hasattr(lib, "ampsm_debug_clocks")
+clk_fn = getattr(lib, "ampsm_debug_clocks_vamp" if a.vamp else "ampsm_debug_clocks", None)
 snr = 10 ** (a.snr_db / 10)
 if a.vamp:
     vamp = pkg.VAMP(cfg, kernel='auto', outputs=False, early_exit=not a.fixed)
@@ -44,7 +45,7 @@ for _ in range(2):
     det = amp.detect(H, y, snr, x, labels, idx)
 torch.cuda.synchronize()
 if have_clk:
-    lib.ampsm_debug_clocks(None, 1)
+    clk_fn(None, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 reps = 3
 e0.record()
@@ -58,10 +59,14 @@ fi = c["iters"]
 print(f"{'VAMP' if a.vamp else 'BAMP'} ctas/sm={os.environ.get('AMPSM_CTAS_PER_SM', 'default')} fixed={a.fixed} iters={a.iters} frames={a.frames} mean T={fi / a.frames:.3f} "
       f"{ms:.3f} ms  {fi / ms * 1e3:.4e} frame-iter/s  {a.frames / ms * 1e3:.4e} frames/s", flush=True)
 if have_clk:
-    out = (C.c_ulonglong * 8)()
-    lib.ampsm_debug_clocks(out, 1)
-    names = ["row pass", "row reduce+publish", "col pass", "col reduce+xmap", "denoiser", "exit+publish", "epilogue(per frame)",
-             "prologue(per frame)"]
+    out = (C.c_ulonglong * 16)()
+    clk_fn(out, 1)
+    if a.vamp:
+        names = ["row pass", "row reduce + LMMSE", "col pass + scalars", "col reduce + r", "denoiser", "Onsager + publish"]
+        frame_phases = {6: "stage wait + y~", 7: "stage refill + init", 8: "epilogue"}
+    else:
+        names = ["row pass", "row reduce+publish", "col pass", "col reduce+xmap", "denoiser", "exit+publish"]
+        frame_phases = {6: "epilogue", 7: "prologue"}
     tot_it = fi * reps
     tot_fr = a.frames * reps
     s = 0.0
@@ -70,5 +75,5 @@ if have_clk:
         s += v
         print(f"  {names[p]:>22s}: {v:8.1f} cycles / warp-iteration")
     print(f"  {'iteration total':>22s}: {s:8.1f}")
-    for p in (6, 7):
-        print(f"  {names[p]:>22s}: {out[p] / tot_fr:8.1f} cycles / frame")
+    for p, nm in frame_phases.items():
+        print(f"  {nm:>22s}: {out[p] / tot_fr:8.1f} cycles / frame")
