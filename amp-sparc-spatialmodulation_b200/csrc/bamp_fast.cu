@@ -525,10 +525,14 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
             CLK(0);                              // row pass
         }
 
+        // the staged Loss inputs were requested at the start of the frame: complete by now.  (Waiting AFTER the tile loads
+        // below costs ~570 cycles: the wait's dependency barrier queues behind the 32 LDG.128 in the load/store unit.)
+        cp_async_wait_group<0>();
         if constexpr (DIRECT) {   // the H registers are free: fetch the next frame's tile under the Loss epilogue
             const long long nf = f + warps_total;
             if (nf < a.frames) load_tile(nf);
         }
+        CLK(8);                                  // tile load issue
         // ================= outputs =================
         float2 xh[CP], xmap[CP];
         float var[CP];
@@ -557,9 +561,10 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
             atomicAdd(&cnt32[C_ITERS], (unsigned)t_done);
         }
         // ================= Loss: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1 shapes only ========
+        CLK(9);                                  // outputs, frame counters
         if (a.io.x_true) {
-            cp_async_wait_all();
             __syncwarp();
+            CLK(10);                             // (the staged Loss inputs are visible to every lane)
             fast_loss2<N, M_, K_, CP, GRID>(xmap, xh, al, a.grid, g, lstage, f, lane, cnt32, sqacc);
         }
         __syncwarp();
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     }
 #ifdef AMPSM_CLK
     __syncwarp();
-    if (lane < 8) atomicAdd(&g_clk[lane], (unsigned long long)clkacc[lane]);
+    if (lane < 16) atomicAdd(&g_clk[lane], (unsigned long long)clkacc[lane]);
 #endif
 
     // ---- flush the warp's counters
@@ -647,7 +652,7 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
 #ifdef AMPSM_CLK
 extern "C" int ampsm_debug_clocks(unsigned long long* out8, int reset) {
     unsigned long long z[16] = {};
-    if (out8 && cudaMemcpyFromSymbol(out8, ampsm::g_clk, 8 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (out8 && cudaMemcpyFromSymbol(out8, ampsm::g_clk, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
     if (reset && cudaMemcpyToSymbol(ampsm::g_clk, z, sizeof(z)) != cudaSuccess) return 1;
     return 0;
 }

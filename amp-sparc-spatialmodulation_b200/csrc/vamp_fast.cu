@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             CLK(5);                            // Onsager scalars, publish
             if (g.early_exit && all_close) break;
         }
+        // pending cp.async groups: {Loss inputs of f, y / s of the next frame} -> the former are complete; waited for BEFORE
+        // the tile loads, behind which the wait's dependency barrier would queue in the load/store unit
+        cp_async_wait_group<1>();
         {   // the tile registers are free: fetch the next frame's tile under the Loss epilogue
             const long long nf = f + gridDim.x;
             if (nf < a.frames) load_tile(nf);
@@ -423,7 +426,6 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             atomicAdd(&cnt32[C_ITERS], (unsigned)t_done);
         }
         if (a.io.x_true) {                                       // Loss is fed T.r as xmap (vamp.py:187)
-            cp_async_wait_group<1>();          // pending: {Loss inputs of f, factors of the next frame} -> the former are complete
             __syncwarp();
             fast_loss2<N, M_, K_, CP, GRID>(xmap, xh, al, a.grid, g, lstage, f, lane, cnt32, sqacc);
         }

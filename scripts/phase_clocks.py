@@ -66,7 +66,7 @@ if have_clk:
         frame_phases = {6: "stage wait + y~", 7: "stage refill + init", 8: "epilogue"}
     else:
         names = ["row pass", "row reduce+publish", "col pass", "col reduce+xmap", "denoiser", "exit+publish"]
-        frame_phases = {6: "epilogue", 7: "prologue"}
+        frame_phases = {8: "tile load issue", 9: "outputs, counters", 10: "Loss input wait", 6: "Loss", 7: "prologue"}
     tot_it = fi * reps
     tot_fr = a.frames * reps
     s = 0.0
