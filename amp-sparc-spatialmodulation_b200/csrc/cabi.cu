@@ -332,7 +332,8 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     k.io.counters = (unsigned long long*)counters;
     k.xmap = xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
     if (p->kernel != 1 && !is_double && !p->exp_f64 && p->shift_mode == 0) {
-        const int rc = launch_vamp_fast(k, (cudaStream_t)stream);
+        int rc = launch_vamp_fast(k, (cudaStream_t)stream);                         // 32 x 64 factors, one warp per frame
+        if (rc == AMPSM_ENOFIT) rc = launch_vamp_quad(k, (cudaStream_t)stream);     // 64 x 128 factors, four warps per frame
         if (rc != AMPSM_ENOFIT || p->kernel == 2) return rc;
     } else if (p->kernel == 2) {
         set_error("VAMP register-resident kernel supports complex64, exp_f64=0, shift_mode=0 only");

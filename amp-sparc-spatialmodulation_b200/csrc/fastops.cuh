@@ -18,6 +18,11 @@ namespace ampsm {
 #define CLK(p) do {} while (0)
 #endif
 
+// torch.max / torch.min propagate NaN (vamp.py:76-77)
+__device__ __forceinline__ float clampF(float v, float lo, float hi) {
+    if (v != v) return v;
+    return fminf(fmaxf(v, lo), hi);
+}
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -362,9 +367,11 @@ struct LossStage {
     __device__ static const long long* idx(const unsigned char* st) { return reinterpret_cast<const long long*>(st + N_ * 8); }
     __device__ static const long long* sym(const unsigned char* st) { return reinterpret_cast<const long long*>(st + N_ * 8 + lab_bytes); }
     // x_true + f N must be 16-byte aligned (the launchers check the base pointer; N is even for every fast shape)
-    __device__ static void issue(unsigned char* st, const LossIO& io, long long f, int lane) {
+    // `lane` = index of the calling thread among the `nthreads` that share the stage (one warp, or the CTA of the
+    // four-warps-per-frame kernel); every one of them commits exactly one cp.async group
+    __device__ static void issue(unsigned char* st, const LossIO& io, long long f, int lane, int nthreads = 32) {
         static_assert(N_ % 2 == 0, "x_true rows are copied in 16-byte pieces");
-        for (int c = lane; c < N_ / 2; c += 32) cp_async16(st + c * 16, io.x_true + f * N_ + 2 * c);
+        for (int c = lane; c < N_ / 2; c += nthreads) cp_async16(st + c * 16, io.x_true + f * N_ + 2 * c);
         if (lane < L_) {
             cp_async8(st + N_ * 8 + lane * 8, io.idx_true + f * L_ + lane);
             cp_async8(st + N_ * 8 + lab_bytes + lane * 8, io.sym_true + f * L_ + lane);
@@ -399,10 +406,13 @@ __device__ __forceinline__ int section_argmax(unsigned long long key, int idx, i
 // corner is the UNIQUE maximum of the rounded values as well, so np.argmax's answer for the column is the corner's first
 // table index and only its metric needs to be evaluated (3 float64 instructions instead of ~50 + a 15-merge tournament).
 // Columns that fail the test (zeros, NaN, Inf, extreme ratios) take the full tournament.
+// col_base: the frame column of lane 0's first column (0 for the one-warp-per-frame kernels; 32 w for warp w of the
+// four-warps-per-frame kernel, whose sections must then lie inside one warp).  Returns bit 0: some decided value of this
+// warp's columns differs from x_true, bit 1: NaN input; with book_frame the frame-level counters are booked here.
 template <int N_, int M_, int K_, int CP, bool GRID>
-__device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const DevGrid& G,
-                                           const Geom& g, const unsigned char* st, long long f, int lane, unsigned* cnt32,
-                                           double* sqacc) {
+__device__ __forceinline__ unsigned fast_loss2(const float2 (&xmap)[CP], const float2 (&xh)[CP], const DevAlphabet& al, const DevGrid& G,
+                                               const Geom& g, const unsigned char* st, long long f, int lane, unsigned* cnt32,
+                                               double* sqacc, int col_base = 0, bool book_frame = true) {
     constexpr int L_ = N_ / M_;
     using LS = LossStage<N_, L_>;
     bool nan_seen = false;
@@ -410,7 +420,7 @@ __device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float
     int kidx[CP];
 #pragma unroll
     for (int t = 0; t < CP; ++t) {
-        const int col = lane + 32 * t;
+        const int col = col_base + lane + 32 * t;
         key[t] = 0ull;
         kidx[t] = 0x7fffffff;
         if (col < N_) {
@@ -485,7 +495,7 @@ __device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float
     double sq = 0.0;
 #pragma unroll
     for (int t = 0; t < CP; ++t) {
-        const int col = lane + 32 * t;
+        const int col = col_base + lane + 32 * t;
         if (col < N_) {
             const int sec = col / M_, m = col % M_;
             const float2 xt = LS::xt(st)[col];
@@ -510,10 +520,11 @@ __device__ __forceinline__ void fast_loss2(const float2 (&xmap)[CP], const float
     }
     sqacc[lane] += sq;
     const bool any_wrong = __any_sync(0xffffffffu, wrong), any_nan = __any_sync(0xffffffffu, nan_seen);
-    if (lane == 0) {
+    if (book_frame && lane == 0) {
         if (any_wrong) atomicAdd(&cnt32[C_FRAME_ERR], 1u);             // Lin = 1: one time slot per frame
         if (any_nan) atomicAdd(&cnt32[C_NAN_FRAMES], 1u);
     }
+    return (any_wrong ? 1u : 0u) | (any_nan ? 2u : 0u);
 }
 // fold a warp's shared counters into the global block (Lin = 1: the frame is its only, first, middle and last slot).
 // 32-bit per-warp counts: a warp would need > 6e7 frames of 64 label bits in one call to overflow.

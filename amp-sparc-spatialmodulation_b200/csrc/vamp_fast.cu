@@ -56,12 +56,6 @@ struct VFastShape {
     static constexpr int total = (clk + 64 + 127) & ~127;
 };
 
-__device__ __forceinline__ float clampF(float v, float lo, float hi) {
-    // torch.max / torch.min propagate NaN (vamp.py:76-77)
-    if (v != v) return v;
-    return fminf(fmaxf(v, lo), hi);
-}
-
 // WPS = warps (frames) per SM: 12 = three per sub-partition at 168 registers, 8 = two at 255 registers (A/B switch)
 template <int RT, int CTL, int M_, int K_, bool GRID, int WPS>
 __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constant__ VampArgs a) {
