@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast", "pair"])
     ap.add_argument("--vamp-frames", type=int, default=1 << 18, help="frames per GPU of the VAMP leg (0 = skip it)")
+    ap.add_argument("--c3-frames", type=int, default=1 << 14, help="frames per GPU of the config-3 VAMP leg (128 x 64; 0 = skip it)")
+    ap.add_argument("--c3-snr-db", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed-t", action="store_true")
     return ap.parse_args()
@@ -438,6 +440,10 @@ def main():
         vbytes = 8 * NR * NT + 8 * NR * NR + 4 * NR + 8 * NR + 8 * NT            # Vh, U, s, y, x_true: 25 472 B
         vflop = 16 * NR * NT + 18 * NT * 16 + 40 * NT + 10 * NR                  # 54 080 flop per frame-iteration
         gbs = (cv["frames"] / world) * vbytes / (msv * 1e-3) / 1e9
+        try:        # ncu dram bytes per frame (profiles/) x frames of one launch
+            vtraffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("vamp_c2_bytes_per_frame") * fv
+        except Exception:
+            vtraffic = None
         tfl = (cf["iters"] / world) * vflop / (msf * 1e-3) / 1e12
         tf32 = out.get("fixed_T", {}).get("roofline_fp32", {}).get("peak") or 0.0
         out["vamp"] = {
@@ -448,7 +454,7 @@ def main():
             "config": {"workload": f"VAMP Nt={NT} Nr={NR} Na={NA} 16-QAM SM, per-frame thin SVD factors (U, s, Vh) resident in HBM, "
                                    f"iterations={ITERS}, early exit as reference, SNR {args.snr_db} dB"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_frame": vbytes, "traffic": None},
+                         "algorithmic_bytes_per_frame": vbytes, "traffic": vtraffic},
             "fixed_T": {"value": cf["iters"] / (msf * 1e-3), "unit": "frame-iter/s", "iterations": ITERS,
                         "roofline_fp32": {"bound": "fp32", "achieved": tfl, "peak": tf32, "unit": "TFLOP/s",
                                           "frac": (tfl / tf32) if tf32 else None, "algorithmic_flop_per_frame_iter": vflop}},
@@ -457,6 +463,56 @@ def main():
                              "what": "ampsm_vamp_detect_from_h: one-sided Jacobi SVD of every frame's H (one warp per matrix) "
                                      "+ the iterations; per-rank time, not reduced over ranks"},
         }
+    # ---- BASELINE config 3: VAMP Nt=128 Nr=64 Na=4 QPSK (vamp.py:159-191), per-frame SVD factors resident in HBM, through the
+    # four-warps-per-frame register-resident kernel (csrc/vamp_quad.cu); per-rank device time
+    if args.c3_frames > 0:
+        f3 = args.c3_frames
+        cfg3 = pkg.Config(128, 4, 64, 1, 1, batch=f3, generator_mode='sparc', iterations=ITERS, alphabet='QPSK',
+                          channel_profile='uniform', device=str(dev))
+        snr3 = 10 ** (args.c3_snr_db / 10)
+        g3 = torch.Generator(device=dev).manual_seed(4321 + rank)
+        from amp_sparc_spatialmodulation_b200.simulate import device_frames
+        H3, y3, x3, l3, i3 = device_frames(cfg3, f3, snr3, g3)
+        Us, ss, Vs = [], [], []
+        for H1 in H3.split(4096):                           # thin SVD through the Hermitian eigenproblem of H H^H (float64)
+            Hd = H1.to(torch.complex128)
+            wv, V = torch.linalg.eigh(Hd @ Hd.mH)
+            wv, V = wv.flip(-1), V.flip(-1)
+            sv3 = wv.clamp_min(0).sqrt()
+            Us.append(V.to(torch.complex64)), ss.append(sv3.to(torch.float32))
+            Vs.append(((V.mH @ Hd) / sv3.unsqueeze(-1)).to(torch.complex64))
+            del Hd, wv, V, sv3
+        U3, s3, V3 = torch.cat(Us).contiguous(), torch.cat(ss).contiguous(), torch.cat(Vs).contiguous()
+        del Us, ss, Vs, H3
+        flop3 = 16 * 64 * 128 + 18 * 128 * 4 + 40 * 128 + 10 * 64               # 146 048 flop per frame-iteration
+        c3out = {}
+        for tag, ee in (("exit", True), ("fixed_T", False)):
+            v3 = pkg.VAMP(cfg3, outputs=False, early_exit=ee)
+            for _ in range(2):
+                v3.detect(U3, s3, V3, y3, snr3, x3, l3, i3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                det = v3.detect(U3, s3, V3, y3, snr3, x3, l3, i3)
+            e1.record()
+            torch.cuda.synchronize()
+            c3out[tag] = (det.counters_dict(), e0.elapsed_time(e1) / 3)
+        (ce, mse), (cf3, msf3) = c3out["exit"], c3out["fixed_T"]
+        tf32 = out.get("fixed_T", {}).get("roofline_fp32", {}).get("peak") or 0.0
+        out["vamp_c3"] = {
+            "metric": "VAMP frame-iterations/s", "value": ce["iters"] / (mse * 1e-3), "unit": "frame-iter/s",
+            "frames_per_gpu": f3, "mean_iterations_per_frame": ce["iters"] / f3, "ier": ce["index_err"] / (4 * f3),
+            "nan_frames": ce["nan_frames"],
+            "config": {"workload": f"VAMP Nt=128 Nr=64 Na=4 QPSK generalized SM, per-frame thin SVD factors resident in HBM, "
+                                   f"iterations={ITERS}, early exit as reference, SNR {args.c3_snr_db} dB, complex64; per-rank time"},
+            "roofline_fp32": {"bound": "fp32", "achieved": ce["iters"] * flop3 / (mse * 1e-3) / 1e12, "peak": tf32, "unit": "TFLOP/s",
+                              "frac": (ce["iters"] * flop3 / (mse * 1e-3) / 1e12 / tf32) if tf32 else None,
+                              "algorithmic_flop_per_frame_iter": flop3},
+            "fixed_T": {"value": cf3["iters"] / (msf3 * 1e-3), "unit": "frame-iter/s",
+                        "tflops": cf3["iters"] * flop3 / (msf3 * 1e-3) / 1e12},
+        }
+        del U3, s3, V3
     if cpu_base:
         out["cpu_baseline"] = cpu_base
     if rank == 0:
