@@ -30,6 +30,27 @@ FLOP_PER_FRAME_ITER = 20 * NR * NT + 18 * NT * 16 + 30 * NR + 20 * NT      # SUR
 BYTES_PER_FRAME = 8 * NR * NT + 8 * NR + 8 * NT                             # H, y, x_true: 17 152
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The driver reads ONE JSON line from stdout: everything else that lands there (NCCL prints its version banner to
+    stdout under torchrun, libraries may print too) is sent to stderr; emit() writes the result line to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_RESULT_FD, (line + "\n").encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -121,7 +142,7 @@ def run_reference(args):
     pool.close()
     v = float(np.mean(rates))
     sample = f"{used} frames/step of BAMP 64x32 16-QAM at {args.snr_db} dB, numpy oracle port, {cores} processes"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "BAMP frame-iterations/s", "value": v, "unit": "frame-iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex64 (denoiser float64)", "data": "synthetic",
@@ -205,6 +226,7 @@ def make_gpu_inputs(torch, cfg, frames, snr_db, dev, seed):
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -516,7 +538,7 @@ def main():
     if cpu_base:
         out["cpu_baseline"] = cpu_base
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
