@@ -425,7 +425,9 @@ def main():
             vamp = pkg.VAMP(cfgv, kernel=args.kernel if args.kernel in ("auto", "generic", "fast") else "auto", outputs=False,
                             early_exit=ee)
             for _ in range(max(1, args.warmup)):
-                vamp.detect(U, sv, Vh, yv, snr, xv, lv, iv)
+                det = vamp.detect(U, sv, Vh, yv, snr, xv, lv, iv)
+                if world > 1:
+                    allreduce_counters(det.counters)      # as in the timed loop (the first collective after a pause is slow)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
