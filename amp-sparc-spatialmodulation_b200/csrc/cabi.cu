@@ -389,15 +389,17 @@ int ampsm_svd_batched(int64_t frames, int32_t n, int32_t N, const void* H, void*
                       void* stream) {
     if (frames < 0 || (frames > 0 && (!H || !U || !s || !Vh))) { set_error("SVD: NULL pointer or frames < 0"); return AMPSM_EINVAL; }
     if (frames == 0) return 0;
-    return launch_svd_jacobi((const float2*)H, frames, n, N, (float2*)U, s, (float2*)Vh, sweeps, (cudaStream_t)stream);
+    return launch_svd_jacobi((const float2*)H, frames, n, N, (float2*)U, s, (float2*)Vh, sweeps, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// workspace: U^H y [frames][n] | s [frames][n] | Vh [frames][n][N] | one n x n identity (the `U` the detector is handed)
 int64_t ampsm_vamp_from_h_workspace_bytes(const ampsm_problem* p, int64_t frames) {
     if (!p || frames < 0) return -1;
     const size_t n = p->n, N = p->N;
-    return (int64_t)(align256((size_t)frames * n * n * 8) + align256((size_t)frames * n * 4) + align256((size_t)frames * n * N * 8));
+    return (int64_t)(align256((size_t)frames * n * 8) + align256((size_t)frames * n * 4) + align256((size_t)frames * n * N * 8) +
+                     align256(n * n * 8));
 }
 
 int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H, const void* y,
@@ -410,11 +412,17 @@ int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, in
     if (frames == 0) return 0;
     const size_t n = p->n, N = p->N;
     unsigned char* w = (unsigned char*)workspace;
-    void* U = w;
-    float* s = (float*)(w + align256((size_t)frames * n * n * 8));
-    void* Vh = w + align256((size_t)frames * n * n * 8) + align256((size_t)frames * n * 4);
-    if (int e = ampsm_svd_batched(frames, p->n, p->N, H, U, s, Vh, nullptr, stream)) return e;
-    return ampsm_vamp_detect(p, a, frames, 0, U, (int64_t)(n * n), s, (int64_t)n, Vh, (int64_t)(n * N), y, sigma2, sigma2_per_frame,
+    float2* yrot = (float2*)w;
+    float* s = (float*)(w + align256((size_t)frames * n * 8));
+    void* Vh = w + align256((size_t)frames * n * 8) + align256((size_t)frames * n * 4);
+    float2* eye = (float2*)((unsigned char*)Vh + align256((size_t)frames * n * N * 8));
+    // VAMP needs U only in y~ = diag(s) U^H y (vamp.py:22): the Jacobi kernel rotates y along with the rows of H, and the
+    // detector is handed U = I (shared by all frames) with U^H y in place of y
+    if (int e = launch_svd_jacobi((const float2*)H, frames, p->n, p->N, nullptr, s, (float2*)Vh, nullptr, (const float2*)y, yrot,
+                                  (cudaStream_t)stream))
+        return e;
+    if (int e = launch_identity(eye, p->n, (cudaStream_t)stream)) return e;
+    return ampsm_vamp_detect(p, a, frames, 0, eye, 0, s, (int64_t)n, Vh, (int64_t)(n * N), yrot, sigma2, sigma2_per_frame,
                              sparsity, x_true, sym_true, idx_true, xmap, xmmse, var, iters, traj, counters, stream);
 }
 

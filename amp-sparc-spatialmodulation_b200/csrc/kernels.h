@@ -119,7 +119,9 @@ long long scamp_workspace_bytes(const Geom& g, long long frames);
 int launch_loss(const LossArgs& a, cudaStream_t stream);
 int launch_shrink(const ShrinkArgs& a, int kind, cudaStream_t stream);   // kind 0 bayes, 1 shrinkOOK, 2 sw_shrinkOOK
 // batched thin SVD H = U diag(s) Vh of dense [frames][n][N] complex64 matrices, n <= 32 (svd_jacobi.cu); sweeps optional
-int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, cudaStream_t stream);
+int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, const float2* y,
+                      float2* yrot, cudaStream_t stream);      // y != nullptr: yrot = U^H y instead of U
+int launch_identity(float2* I, int n, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);
 int probe_fp32x2(int device, double* tflops);
 

@@ -12,6 +12,8 @@
 // rows: it loads them once into registers (conflict-free 8-byte accesses, padded rows), forms the three inner products,
 // combines them with its partner by one shuffle round, rotates in registers and stores back.  A pair whose rows are
 // already orthogonal to 4e-7 (relative) is skipped; the sweep loop ends when a whole sweep rotated nothing.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ampsm {
@@ -23,11 +25,12 @@ constexpr int kSvdWarps = 3;              // warps (matrices) per CTA
 constexpr int kSvdMaxSweeps = 16;
 constexpr float kSvdTol = 4.0e-7f;
 
-template <int NC>
+template <int NC, bool WITHY = false>
 struct SvdShape {
     static constexpr int wstride = NC + 1;                    // complex elements per row of W (odd: conflict-free columns)
     static constexpr int qstride = kSvdRows + 1;
-    static constexpr int warp_bytes = (kSvdRows * wstride + kSvdRows * qstride) * 8 + 2 * kSvdRows * 4;   // + perm, 1/s
+    static constexpr int q_elems = WITHY ? kSvdRows : kSvdRows * qstride;      // WITHY: the vector z = Q y instead of Q
+    static constexpr int warp_bytes = (kSvdRows * wstride + q_elems) * 8 + 2 * kSvdRows * 4;   // + perm, 1/s
 };
 // column k of a lane's share: lane half h takes the columns whose index mod 16 lies in [8h, 8h+8), so that the 16 lanes
 // of a half-warp (8 consecutive rows x 2 halves, row stride = 1 mod 16 in 8-byte units) hit 16 distinct bank pairs
@@ -36,17 +39,74 @@ __device__ __forceinline__ constexpr int svd_col(int c, int h) {
     return NC >= 16 ? ((c >> 3) * 16 + 8 * h + (c & 7)) : (2 * c + h);
 }
 
-// NC = number of columns (compile time), n = number of rows (run time, <= 32)
+
+// ---- block variant: four rows (two "super-rows") per group of four lanes -------------------------------------------------
+// A step of the pairwise tournament loads and stores the whole matrix for 16 rotations; the kernel is bound by exactly that
+// shared-memory traffic (ncu: data pipe 79 % busy).  The block variant runs the tournament over 16 super-rows of two rows:
+// a group of four lanes loads the four rows of its super-row pair once (each lane a quarter of the columns, 128 registers
+// at 64 columns), forms their 4 x 4 Gram matrix (two shuffle rounds), and works through the four cross pairs -- plus the two
+// inner pairs once per sweep -- on the GRAM matrix alone, accumulating the plane rotations in a 4 x 4 matrix T that is then
+// applied to the rows in one pass.  15 steps per sweep instead of 31: half the shared-memory traffic per sweep.
+// (Correct -- the SVD tests pass with AMPSM_SVD_BLOCK=1 -- but slower on B200, see launch_svd_nc: an experiment kept as evidence.)
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 conjf2(float2 a) { return make_float2(a.x, -a.y); }
+// columns of lane h (0..3): inside every block of 16 columns the offsets {0,1,8,9}[h] + {0,2,4,6} -- with rows two apart in
+// neighbouring groups (row stride = 1 mod 16 in 8-byte units) the 16 lanes of a half-warp hit 16 distinct bank pairs
 template <int NC>
+__device__ __forceinline__ constexpr int svd_bcol(int c, int h) {
+    return NC >= 16 ? (16 * (c >> 2) + ((h & 1) + 8 * (h >> 1)) + 2 * (c & 3)) : (4 * c + h);
+}
+// one Jacobi rotation of rows (A, B) of the group, on the Gram matrix G (gd: diagonal, go[i][j] = <a_i, a_j> = sum conj(a_i) a_j)
+// and on the accumulated transformation T (rows' = T rows); same formulas as the pairwise kernel
+template <int A, int B>
+__device__ __forceinline__ bool svd_grot(float (&gd)[4], float2 (&go)[4][4], float2 (&T)[4][4]) {
+    const float alpha = gd[A], beta = gd[B];
+    const float2 gm = go[A][B];
+    const float g2 = gm.x * gm.x + gm.y * gm.y;
+    if (!(g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f)) return false;
+    const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
+    const float pr = gm.x * ginv, pi = -gm.y * ginv;                                 // e^{-i phi} = conj(gamma) / |gamma|
+    const float zeta = (beta - alpha) * (0.5f * ginv);
+    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
+    const float2 sp = make_float2(sn * pr, sn * pi), cp = make_float2(cs * pr, cs * pi);
+    // a' = c a - (s p) b ; b' = s a + (c p) b
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 ta = T[A][k], tb = T[B][k], u = cmulf(sp, tb), v = cmulf(cp, tb);
+        T[A][k] = make_float2(cs * ta.x - u.x, cs * ta.y - u.y);
+        T[B][k] = make_float2(sn * ta.x + v.x, sn * ta.y + v.y);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k == A || k == B) continue;
+        const float2 x = go[k][A], y = go[k][B], u = cmulf(sp, y), v = cmulf(cp, y);   // <a_k, .> is linear in its second argument
+        go[k][A] = make_float2(cs * x.x - u.x, cs * x.y - u.y);
+        go[k][B] = make_float2(sn * x.x + v.x, sn * x.y + v.y);
+        go[A][k] = conjf2(go[k][A]);
+        go[B][k] = conjf2(go[k][B]);
+    }
+    gd[A] = alpha - t * gabs;
+    gd[B] = beta + t * gabs;
+    go[A][B] = go[B][A] = make_float2(0.f, 0.f);
+    return true;
+}
+
+// NC = number of columns (compile time), n = number of rows (run time, <= 32).
+// WITHY: the caller only needs U^H y (VAMP's y~ = diag(s) U^H y, vamp.py:22): the rotations are applied to the vector y
+// instead of the n x n matrix Q = U^H -- a third less shared-memory traffic per rotation, no U written or read later.
+// BLOCK: the four-rows-per-group sweep above instead of the pairwise one.
+template <int NC, bool WITHY, bool BLOCK>
 __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2* __restrict__ H, long long frames, int n, float2* __restrict__ U,
-                                                                   float* __restrict__ S, float2* __restrict__ Vh, int* __restrict__ sweeps_out) {
-    using Sh = SvdShape<NC>;
+                                                                   float* __restrict__ S, float2* __restrict__ Vh, int* __restrict__ sweeps_out,
+                                                                   const float2* __restrict__ yin, float2* __restrict__ yrot) {
+    using Sh = SvdShape<NC, WITHY>;
     constexpr int HC = NC / 2, HQ = kSvdRows / 2;             // columns of W / Q per lane
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     float2* W = reinterpret_cast<float2*>(smem + (size_t)wic * Sh::warp_bytes);
     float2* Q = W + kSvdRows * Sh::wstride;
-    int* perm = reinterpret_cast<int*>(Q + kSvdRows * Sh::qstride);
+    int* perm = reinterpret_cast<int*>(Q + Sh::q_elems);
     float* sinv = reinterpret_cast<float*>(perm + kSvdRows);
     const int j = lane >> 1, h = lane & 1;
 
@@ -57,15 +117,126 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
             const int r = e / NC, c = e - r * NC;
             W[r * Sh::wstride + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
         }
-        for (int e = lane; e < kSvdRows * kSvdRows; e += 32) {
-            const int r = e >> 5, c = e & 31;
-            Q[r * Sh::qstride + c] = make_float2(r == c ? 1.f : 0.f, 0.f);
+        if constexpr (WITHY) {
+            Q[lane] = lane < n ? __ldg(yin + f * n + lane) : make_float2(0.f, 0.f);      // z = y (rows >= n are zero)
+        } else {
+            for (int e = lane; e < kSvdRows * kSvdRows; e += 32) {
+                const int r = e >> 5, c = e & 31;
+                Q[r * Sh::qstride + c] = make_float2(r == c ? 1.f : 0.f, 0.f);
+            }
         }
         __syncwarp();
 
         int sweeps = 0;
         for (; sweeps < kSvdMaxSweeps; ++sweeps) {
             bool rotated = false;
+            if constexpr (BLOCK) {
+                constexpr int QC = NC / 4, kSuper = kSvdRows / 2;        // columns per lane, super-rows
+                const int g = lane >> 2, hb = lane & 3;
+                for (int step = 0; step < kSuper - 1; ++step) {
+                    int P, Qs;
+                    if (g == 0) {
+                        P = kSuper - 1;
+                        Qs = step;
+                    } else {
+                        P = step + g;
+                        if (P >= kSuper - 1) P -= kSuper - 1;
+                        Qs = step - g;
+                        if (Qs < 0) Qs += kSuper - 1;
+                    }
+                    const int rows[4] = {2 * P, 2 * P + 1, 2 * Qs, 2 * Qs + 1};
+                    float2 a[4][QC];
+                    float gd[4] = {0.f, 0.f, 0.f, 0.f};
+                    float2 go[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) go[i][k] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < QC; ++c) a[i][c] = W[rows[i] * Sh::wstride + svd_bcol<NC>(c, hb)];
+#pragma unroll
+                    for (int c = 0; c < QC; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            gd[i] = fmaf(a[i][c].x, a[i][c].x, fmaf(a[i][c].y, a[i][c].y, gd[i]));
+#pragma unroll
+                            for (int k = i + 1; k < 4; ++k) {
+                                go[i][k].x = fmaf(a[i][c].x, a[k][c].x, fmaf(a[i][c].y, a[k][c].y, go[i][k].x));      // sum conj(a_i) a_k
+                                go[i][k].y = fmaf(a[i][c].x, a[k][c].y, fmaf(-a[i][c].y, a[k][c].x, go[i][k].y));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            gd[i] += __shfl_xor_sync(0xffffffffu, gd[i], o);
+#pragma unroll
+                            for (int k = i + 1; k < 4; ++k) {
+                                go[i][k].x += __shfl_xor_sync(0xffffffffu, go[i][k].x, o);
+                                go[i][k].y += __shfl_xor_sync(0xffffffffu, go[i][k].y, o);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = i + 1; k < 4; ++k) go[k][i] = conjf2(go[i][k]);
+                    float2 T[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) T[i][k] = make_float2(i == k ? 1.f : 0.f, 0.f);
+                    bool any = false;
+                    any |= svd_grot<0, 2>(gd, go, T);
+                    any |= svd_grot<1, 3>(gd, go, T);
+                    any |= svd_grot<0, 3>(gd, go, T);
+                    any |= svd_grot<1, 2>(gd, go, T);
+                    if (step == 0) {            // the pairs inside a super-row: once per sweep
+                        any |= svd_grot<0, 1>(gd, go, T);
+                        any |= svd_grot<2, 3>(gd, go, T);
+                    }
+                    if (any) {                  // uniform over the four lanes of the group (they hold the same Gram matrix)
+#pragma unroll
+                        for (int c = 0; c < QC; ++c) {
+                            const float2 x0 = a[0][c], x1 = a[1][c], x2 = a[2][c], x3 = a[3][c];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float2 r = cmulf(T[i][0], x0);
+                                const float2 r1 = cmulf(T[i][1], x1), r2 = cmulf(T[i][2], x2), r3 = cmulf(T[i][3], x3);
+                                r = make_float2((r.x + r1.x) + (r2.x + r3.x), (r.y + r1.y) + (r2.y + r3.y));
+                                W[rows[i] * Sh::wstride + svd_bcol<NC>(c, hb)] = r;
+                            }
+                        }
+                        if constexpr (WITHY) {
+                            if (hb == 0) {
+                                const float2 z0 = Q[rows[0]], z1 = Q[rows[1]], z2 = Q[rows[2]], z3 = Q[rows[3]];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 r0 = cmulf(T[i][0], z0), r1 = cmulf(T[i][1], z1), r2 = cmulf(T[i][2], z2), r3 = cmulf(T[i][3], z3);
+                                    Q[rows[i]] = make_float2((r0.x + r1.x) + (r2.x + r3.x), (r0.y + r1.y) + (r2.y + r3.y));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kSvdRows / 4; ++c) {
+                                const int cq = svd_bcol<kSvdRows>(c, hb);
+                                const float2 x0 = Q[rows[0] * Sh::qstride + cq], x1 = Q[rows[1] * Sh::qstride + cq],
+                                             x2 = Q[rows[2] * Sh::qstride + cq], x3 = Q[rows[3] * Sh::qstride + cq];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 r0 = cmulf(T[i][0], x0), r1 = cmulf(T[i][1], x1), r2 = cmulf(T[i][2], x2), r3 = cmulf(T[i][3], x3);
+                                    Q[rows[i] * Sh::qstride + cq] = make_float2((r0.x + r1.x) + (r2.x + r3.x), (r0.y + r1.y) + (r2.y + r3.y));
+                                }
+                            }
+                        }
+                        rotated = true;
+                    }
+                    __syncwarp();
+                }
+            } else {
             for (int step = 0; step < kSvdRows - 1; ++step) {
                 // tournament pairing: position 31 stays, the others rotate
                 int p, q;
@@ -113,18 +284,27 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                         wa[svd_col<NC>(c, h)] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
                         wb[svd_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
                     }
-                    float2* qa = Q + p * Sh::qstride;
-                    float2* qb = Q + q * Sh::qstride;
+                    if constexpr (WITHY) {
+                        if (h == 0) {           // the same rotation on the two entries of z = Q y
+                            const float2 x = Q[p], y = Q[q];
+                            Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        }
+                    } else {
+                        float2* qa = Q + p * Sh::qstride;
+                        float2* qb = Q + q * Sh::qstride;
 #pragma unroll
-                    for (int c = 0; c < HQ; ++c) {
-                        const int cq = svd_col<kSvdRows>(c, h);
-                        const float2 x = qa[cq], y = qb[cq];
-                        qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                        qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        for (int c = 0; c < HQ; ++c) {
+                            const int cq = svd_col<kSvdRows>(c, h);
+                            const float2 x = qa[cq], y = qb[cq];
+                            qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        }
                     }
                     rotated = true;
                 }
                 __syncwarp();
+            }
             }
             if (!__any_sync(0xffffffffu, rotated)) {
                 ++sweeps;
@@ -161,7 +341,9 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                 out[c] = make_float2(w.x * sc, w.y * sc);
             }
         }
-        if (lane < n) {
+        if constexpr (WITHY) {
+            if (lane < n) yrot[f * n + lane] = Q[perm[lane]];                   // (U^H y)_k, k in singular-value order
+        } else if (lane < n) {
             const int row = perm[lane];
             for (int i = 0; i < n; ++i) {
                 const float2 qv = Q[row * Sh::qstride + i];
@@ -173,13 +355,14 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
     }
 }
 
-template <int NC>
-int launch_svd_nc(const float2* H, long long frames, int n, float2* U, float* S, float2* Vh, int* sweeps, cudaStream_t stream) {
+template <int NC, bool WITHY, bool BLOCK>
+int launch_svd_nc_b(const float2* H, long long frames, int n, float2* U, float* S, float2* Vh, int* sweeps, const float2* y, float2* yrot,
+                  cudaStream_t stream) {
     int dev = 0, sms = 0;
     if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = svd_jacobi_kernel<NC>;
-    const size_t smem = (size_t)SvdShape<NC>::warp_bytes * kSvdWarps;
+    auto kern = svd_jacobi_kernel<NC, WITHY, BLOCK>;
+    const size_t smem = (size_t)SvdShape<NC, WITHY>::warp_bytes * kSvdWarps;
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(svd)"))
         return e;
     int per_sm = 1;
@@ -189,27 +372,54 @@ int launch_svd_nc(const float2* H, long long frames, int n, float2* U, float* S,
     const long long need = (frames + kSvdWarps - 1) / kSvdWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(H, frames, n, U, S, Vh, sweeps);
+    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(H, frames, n, U, S, Vh, sweeps, y, yrot);
     count_launch();
     return check_cuda(cudaGetLastError(), "svd_jacobi_kernel launch");
 }
 
+template <int NC, bool WITHY>
+int launch_svd_nc(const float2* H, long long frames, int n, float2* U, float* S, float2* Vh, int* sweeps, const float2* y, float2* yrot,
+                  cudaStream_t stream) {
+    // measured on B200 (262 144 matrices 32 x 64, from-H path): pairwise 3.59e6 frames/s, block 1.82e6 -- the block sweep halves
+    // the shared-memory traffic but needs 255 registers (6 warps per SM instead of 12) and ~6x the serial scalar work per
+    // step; it stays selectable for A/B runs
+    static const bool block = getenv("AMPSM_SVD_BLOCK") != nullptr;
+    return block ? launch_svd_nc_b<NC, WITHY, true>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream)
+                 : launch_svd_nc_b<NC, WITHY, false>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream);
+}
+
+__global__ void identity_kernel(float2* I, int n) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) I[e] = make_float2((e / n) == (e % n) ? 1.f : 0.f, 0.f);
+}
+
 }  // namespace
 
-int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, cudaStream_t stream) {
+// y == nullptr: U, s, Vh.  y != nullptr: s, Vh and yrot = U^H y (U is not formed; see WITHY).
+int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, const float2* y,
+                      float2* yrot, cudaStream_t stream) {
     if (n < 1 || n > kSvdRows || N < n) {
         set_error("batched SVD: needs 1 <= n <= 32 rows and n <= N columns (got %d x %d)", n, N);
         return AMPSM_ENOFIT;
     }
+#define AMPSM_SVD_NC(NCC) \
+    case NCC: return y ? launch_svd_nc<NCC, true>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream) \
+                       : launch_svd_nc<NCC, false>(H, frames, n, U, S, Vh, sweeps, nullptr, nullptr, stream);
     switch (N) {
-        case 8: return launch_svd_nc<8>(H, frames, n, U, S, Vh, sweeps, stream);
-        case 16: return launch_svd_nc<16>(H, frames, n, U, S, Vh, sweeps, stream);
-        case 32: return launch_svd_nc<32>(H, frames, n, U, S, Vh, sweeps, stream);
-        case 64: return launch_svd_nc<64>(H, frames, n, U, S, Vh, sweeps, stream);
+        AMPSM_SVD_NC(8)
+        AMPSM_SVD_NC(16)
+        AMPSM_SVD_NC(32)
+        AMPSM_SVD_NC(64)
         default:
             set_error("batched SVD: column counts 8, 16, 32, 64 are instantiated (got %d)", N);
             return AMPSM_ENOFIT;
     }
+#undef AMPSM_SVD_NC
+}
+
+int launch_identity(float2* I, int n, cudaStream_t stream) {
+    identity_kernel<<<1, 256, 0, stream>>>(I, n);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "identity_kernel launch");
 }
 
 }  // namespace ampsm
