@@ -457,3 +457,64 @@ def test_vamp_quad_and_generic_kernels_agree(alphabet, Na, snr_db):
     pf = pkg.VAMP(cfg, kernel='fast', outputs=True).detect(U[:1].expand(64, -1, -1).contiguous(), s[:1].expand(64, -1).contiguous(),
                                                            Vh[:1].expand(64, -1, -1).contiguous(), y[:64], snr, x[:64], lab[:64], idx[:64])
     assert torch.equal(sh.xmmse, pf.xmmse)
+
+
+@pytest.mark.parametrize("alphabet", ["16QAM", "QPSK"])
+def test_fast_loss_degenerate_frames_match_generic(alphabet):
+    """The fused Loss of the register-resident kernels (fast_loss2: corner shortcut for product-grid alphabets, tournament
+    for everything else, REDUX arg-max on an order-preserving key) on inputs that defeat the shortcut: all-zero channels
+    (xmap == 0 exactly: every metric is +-0, np.argmax takes flat index 0), NaN and Inf observations (first NaN wins),
+    frames whose xmap has an exactly-zero real or imaginary part, mixed with ordinary frames.  Every integer count and the
+    per-frame decisions must equal the generic kernel's (block_loss, the np.argmax restatement pinned by the Loss goldens)."""
+    F = 4096
+    cfg = c2(F, alphabet=alphabet)
+    H, y, x, lab, idx = make_frames(cfg, F, 12.0, seed=77)
+    H = H.clone()
+    y = y.clone()
+    H[0:64] = 0                                       # xmap = 0 exactly
+    y[64:96] = float('nan')                           # NaN everywhere
+    y[96:128, 0] = float('inf')                       # Inf -> NaN after the first products
+    H[128:192] = H[128:192].real.to(torch.complex64)  # real channel ...
+    y[128:192] = y[128:192].real.to(torch.complex64)  # ... and real observation: xmap.imag == 0 exactly
+    snr = 10 ** 1.2
+    res = {}
+    for kernel in ('fast', 'generic'):
+        d = pkg.BAMP(cfg, kernel=kernel, outputs=True).detect(H, y, snr, x, lab, idx)
+        res[kernel] = (d.counters_dict(), d.xmap.reshape(F, -1).clone(), d.iters.clone())
+    cf, cg = res['fast'][0], res['generic'][0]
+    assert cf["nan_frames"] == cg["nan_frames"] >= 64
+    # degenerate frames: identical counts frame group by frame group (run the groups alone)
+    for lo, hi in ((0, 64), (64, 128), (128, 192)):
+        sl = slice(lo, hi)
+        n = hi - lo
+        sub = c2(n, alphabet=alphabet)
+        idx_s = idx[sl] - lo * cfg.N
+        a = pkg.BAMP(sub, kernel='fast', outputs=False).detect(H[sl], y[sl], snr, x[sl], lab[sl], idx_s).counters_dict()
+        b = pkg.BAMP(sub, kernel='generic', outputs=False).detect(H[sl], y[sl], snr, x[sl], lab[sl], idx_s).counters_dict()
+        if lo < 128:
+            assert ints(a) == ints(b), (lo, hi, ints(a), ints(b))
+        else:
+            # real channel and observation: the imaginary part of xmap is pure rounding (or exactly zero), so the metrics of
+            # conjugate symbols nearly tie and two float32 evaluation orders may pick different ones in a few frames
+            assert all(abs(a[k] - b[k]) <= 3 * (4 if k.endswith("bit_err") else 1) for k in INT_KEYS), (ints(a), ints(b))
+    # the whole call: ordinary frames may differ by float32 near-ties only
+    diff = {k: (cf[k], cg[k]) for k in INT_KEYS if cf[k] != cg[k]}
+    assert all(abs(u - v) <= 3 * (4 if k.endswith("bit_err") else 1) for k, (u, v) in diff.items()), diff
+
+
+def test_fast_kernel_falls_back_on_misaligned_loss_inputs():
+    """The register-resident kernels stage x_true with 16-byte cp.async; an x_true that is only 8-byte aligned must take the
+    generic kernel ('auto') with the same result, and be refused by kernel='fast'."""
+    F = 2048
+    cfg = c2(F)
+    H, y, x, lab, idx = make_frames(cfg, F, 15.0, seed=9)
+    buf = torch.zeros(F * cfg.N + 1, dtype=torch.complex64, device=DEV)
+    xm = buf[1:].view(F, cfg.N)                       # data_ptr() % 16 == 8
+    xm.copy_(x)
+    assert xm.data_ptr() % 16 == 8
+    ref = pkg.BAMP(cfg, outputs=False).detect(H, y, 10 ** 1.5, x, lab, idx).counters_dict()
+    got = pkg.BAMP(cfg, outputs=False).detect(H, y, 10 ** 1.5, xm, lab, idx).counters_dict()
+    diff = {k: (got[k], ref[k]) for k in INT_KEYS if got[k] != ref[k]}
+    assert all(abs(u - v) <= 2 for u, v in diff.values()), diff     # generic vs fast kernel: near-ties only
+    with pytest.raises(Exception):
+        pkg.BAMP(cfg, kernel='fast', outputs=False).detect(H, y, 10 ** 1.5, xm, lab, idx)
