@@ -49,7 +49,7 @@ struct FastShape {
     static constexpr int xch_bytes = ((xch_bytes_a > ebuf_bytes ? xch_bytes_a : ebuf_bytes) + 127) & ~127;
     static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // padded slots (see the kernel)
     static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 20 + 127) & ~127;     // float4 per column + the variance array
-    static constexpr int wvec_bytes = ((n > 32 ? n : 32) * 8 + 127) & ~127;
+    static constexpr int wvec_bytes = 0;
     // per-lane state that is only touched in one phase: z/u, y, xmap | 16 counters | 32 squared-error sums | Loss inputs
     static constexpr int o_ystate = 32 * 16, o_xmap = o_ystate + 32 * 8, o_cnt = o_xmap + (N > 32 ? N : 32) * 8;
     static constexpr int o_sq = o_cnt + 64, o_loss = o_sq + 256;
@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     float* ebuf = reinterpret_cast<float*>(ws + S::stage_bytes);
     float4* rowvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes);
     float4* colvec = reinterpret_cast<float4*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes);
-    float2* wvec = reinterpret_cast<float2*>(ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes);
     // per-lane state that is only touched in one phase lives in shared memory, not in registers: the H tile needs them
     unsigned char* st = ws + S::stage_bytes + S::xch_bytes + S::rowvec_bytes + S::colvec_bytes + S::wvec_bytes;
     float4* rowstate = reinterpret_cast<float4*>(st);                       // {z.re, z.im, u, -} of row `lane`
@@ -132,8 +131,11 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     // H and |H|^2 tiles.  PAIR: every element stays the natural (re, im) register pair it is loaded as, and |H|^2 is
     // paired over the lane's adjacent columns, so that all mat-vec FMAs are packed FFMA2 (fma.rn.f32x2, sm_100: half
     // the issue slots for the same FMA-pipe work) with no register re-packing inside the iteration loop:
-    //   H x    : A += h (xx,xx), B += h (xy,xy)   ->  re = A.lo - B.hi, im = B.lo + A.hi
-    //   H^H g  : A += h (gx,gy), B += h (gy,-gx)  ->  re = A.lo + A.hi, im = B.lo + B.hi
+    //   H x    : A += h x.re, B += h x.im   ->  re = A.lo - B.hi, im = B.lo + A.hi
+    //   H^H g  : A += h g.re, B += h g.im   ->  re = A.lo + B.hi, im = B.lo - A.hi
+    // with the scalar broadcast to both halves by the instruction itself (a 32-bit operand register; found in round 1h --
+    // the first versions published pre-duplicated pairs {x,x,y,y}, {gx,gy,gy,-gx}, {w,w} and paid for them in shared-memory
+    // wavefronts: +5 % from dropping them).
     // (B200 register file: one 64-bit operand per lane and cycle -- an FFMA2 whose three operands are all new takes 3
     // cycles, with one of them in the operand-reuse cache 2, which is the FMA pipe's own rate; scripts/exp/ffma2_issue.cu.
     // The loops below keep the broadcast operand fixed over consecutive instructions for that reason.)
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     };
     auto publish = [&](int col, float xr, float xi, float v) {
         if constexpr (PAIR) {
-            colvec[colslot(col)] = make_float4(xr, xr, xi, xi);
+            reinterpret_cast<float2*>(colvec)[col] = make_float2(xr, xi);
             varvec[col] = v;
         } else {
             colvec[colslot(col)] = make_float4(xr, xi, v, 0.f);
@@ -189,11 +191,11 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     };
     // read back the estimate a column owner published (xhat, var)
     auto owned = [&](int col, float2& x, float& v) {
-        const float4 q = colvec[colslot(col)];
         if constexpr (PAIR) {
-            x = make_float2(q.x, q.z);
+            x = reinterpret_cast<const float2*>(colvec)[col];
             v = varvec[col];
         } else {
+            const float4 q = colvec[colslot(col)];
             x = make_float2(q.x, q.y);
             v = q.z;
         }
@@ -210,8 +212,14 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
                 for (int t = 0; t < NV; ++t) {
                     const int col = (t * 8 + lb) * 2;
-                    const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {xx,xx | xy,xy}
-                    const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
+                    // plain {x0.re, x0.im, x1.re, x1.im}: one LDS.128 brings the lane's two adjacent columns; the scalars are
+                    // broadcast to both halves by the FFMA2 itself (32-bit operand register)
+                    const float4 xq = reinterpret_cast<const float4*>(colvec)[t * 8 + lb];
+                    ulonglong2 x0, x1;
+                    x0.x = pack2(xq.x, xq.x);
+                    x0.y = pack2(xq.y, xq.y);
+                    x1.x = pack2(xq.z, xq.z);
+                    x1.y = pack2(xq.w, xq.w);
                     const pair_t vp = *reinterpret_cast<const pair_t*>(&varvec[col]);                       // {var_c, var_c+1}
 #pragma unroll
                     for (int i = 0; i < RH; ++i) {
@@ -383,12 +391,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 const float rn = fast_rcp(un);
                 rowstate[lane] = make_float4(zn.x, zn.y, un, 0.f);
                 const float gx = (yv.x - zn.x) * rn, gy = (yv.y - zn.y) * rn;
-                if constexpr (PAIR) {
-                    rowvec[lane + (lane >> 3)] = make_float4(gx, gy, gy, -gx);     // operand pairs (gx,gy), (gy,-gx)
-                    wvec[lane] = make_float2(rn, rn);
-                } else {
-                    rowvec[lane + (lane >> 3)] = make_float4(gx, gy, rn, 0.f);
-                }
+                rowvec[lane + (lane >> 3)] = make_float4(gx, gy, rn, 0.f);       // one load brings all three scalars of a row
             }
             __syncwarp();
             CLK(1);                              // row reduction, z / u update, operand publish
@@ -407,12 +410,15 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
                     for (int i = 0; i < RT; ++i) {
                         const int row = la * RT + i;
-                        const ulonglong2 gq = *reinterpret_cast<const ulonglong2*>(&rowvec[row + (row >> 3)]);   // {gx,gy | gy,-gx}
-                        const pair_t wp = *reinterpret_cast<const pair_t*>(&wvec[row]);                          // {1/u, 1/u}
+                        // broadcast scalar operands (FFMA2 takes a 32-bit register for both halves: no duplicated pairs in shared
+                        // memory, half the register-file traffic of a 64-bit operand):
+                        //   A += h gx = (hr gx, hi gx),  B += h gy = (hr gy, hi gy)  ->  re = A.lo + B.hi,  im = B.lo - A.hi
+                        const float4 gv = rowvec[row + (row >> 3)];                                              // {g.re, g.im, 1/u, -}
+                        const pair_t gxp = pack2(gv.x, gv.x), gyp = pack2(gv.y, gv.y), wp = pack2(gv.z, gv.z);
 #pragma unroll
                         for (int c = 0; c < CH; ++c) {
-                            A[c] = ffma2(Hp[i][c0 + c], gq.x, A[c]);
-                            B[c] = ffma2(Hp[i][c0 + c], gq.y, B[c]);
+                            A[c] = ffma2(Hp[i][c0 + c], gxp, A[c]);
+                            B[c] = ffma2(Hp[i][c0 + c], gyp, B[c]);
                         }
 #pragma unroll
                         for (int c = 0; c < CH / 2; ++c) C[c] = ffma2(Pp[i][c0 / 2 + c], wp, C[c]);
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                         unpack2(B[c], blo, bhi);
                         unpack2(C[c / 2], c0_, c1_);
                         const int col = (((c0 + c) / VW) * 8 + lb) * VW + ((c0 + c) % VW);
-                        xslot(col >> 1, (col & 1) * 4 + la) = make_float4((c & 1) ? c1_ : c0_, alo + ahi, blo + bhi, 0.f);
+                        xslot(col >> 1, (col & 1) * 4 + la) = make_float4((c & 1) ? c1_ : c0_, alo + bhi, blo - ahi, 0.f);
                     }
                     asm volatile("" ::: "memory");     // keep the halves apart: ptxas otherwise parks the first half's sums on the stack
                 }

@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
     float2* rowp = reinterpret_cast<float2*>(smem + S::rowp);
     float2* colp = reinterpret_cast<float2*>(smem + S::colp);
     float* ebuf = reinterpret_cast<float*>(smem + S::ebuf);
-    float4* colvec = reinterpret_cast<float4*>(smem + S::colvec);
+    float2* colvec = reinterpret_cast<float2*>(smem + S::colvec);        // r~ of every column, plain (re, im)
     float* varvec = reinterpret_cast<float*>(smem + S::varvec);
-    float4* rowvec = reinterpret_cast<float4*>(smem + S::rowvec);
+    float2* rowvec = reinterpret_cast<float2*>(smem + S::rowvec);        // d of every row, plain (re, im)
     float4* rowstate = reinterpret_cast<float4*>(smem + S::rowstate);
     float2* ystage = reinterpret_cast<float2*>(smem + S::ystage);
     float2* xmapvec = reinterpret_cast<float2*>(smem + S::xmapvec);
@@ -106,12 +106,10 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
 #endif
     __syncwarp();
 
-    // column-vector exchange: per column one float4 {x,x,y,y} (the broadcast operand pairs of the row pass), placed so
-    // that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without conflicts
-    auto colslot = [&](int col) {
-        const int t = col >> 4, b = (col >> 1) & 7, e = col & 1;
-        return (t * 2 + e) * 8 + (b ^ (e << 2));
-    };
+    // Operand vectors are plain complex arrays: the FFMA2 broadcasts a 32-bit operand register to both halves, so
+    //   plain product   : A += h x.re, B += h x.im  ->  re = A.lo - B.hi, im = B.lo + A.hi
+    //   adjoint product : A += h d.re, B += h d.im  ->  re = A.lo + B.hi, im = B.lo - A.hi
+    // (the first versions published pre-duplicated pairs {x,x,y,y}, {dx,dy,dy,-dx}: twice the shared-memory wavefronts).
 
     pair_t Hp[RT][CTL];
     // global memory -> registers: per (i, t) the warp reads 4 rows x one full 128-byte line
@@ -214,7 +212,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
 #pragma unroll
         for (int t = 0; t < CP; ++t) {
             const int col = lane + 32 * t;
-            colvec[colslot(col)] = make_float4((float)sp, (float)sp, 0.f, 0.f);
+            colvec[col] = make_float2((float)sp, 0.f);
             varvec[col] = 1.0f;
             xmapvec[col] = make_float2(0.f, 0.f);
         }
@@ -240,8 +238,12 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
 #pragma unroll
                     for (int t = 0; t < NV; ++t) {
                         const int col = (t * 8 + lb) * 2;
-                        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col)]);       // {x,x | y,y}
-                        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&colvec[colslot(col + 1)]);
+                        const float4 xq = *reinterpret_cast<const float4*>(&colvec[col]);        // the lane's two adjacent columns
+                        ulonglong2 x0, x1;
+                        x0.x = pack2(xq.x, xq.x);
+                        x0.y = pack2(xq.y, xq.y);
+                        x1.x = pack2(xq.z, xq.z);
+                        x1.y = pack2(xq.w, xq.w);
                         if (t == 0) {
 #pragma unroll
                             for (int i = 0; i < RH; ++i) A[i] = fmul2(Hp[i0 + i][0], x0.x);
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 const float4 rs = rowstate[lane];
                 scale = fast_rcp(rs.z + ratio);
                 const float dx = scale * (rs.x + ratio * qx) - qx, dy = scale * (rs.y + ratio * qy) - qy;
-                rowvec[lane + (lane >> 3)] = make_float4(dx, dy, dy, -dx);      // operand pairs (dx,dy), (dy,-dx)
+                rowvec[lane] = make_float2(dx, dy);
             }
             __syncwarp();
             CLK(1);                            // row reduction, LMMSE
@@ -293,7 +295,10 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
 #pragma unroll
                     for (int i = 0; i < RT; ++i) {
                         const int row = la * RT + i;
-                        const ulonglong2 gq = *reinterpret_cast<const ulonglong2*>(&rowvec[row + (row >> 3)]);   // {dx,dy | dy,-dx}
+                        const float2 dv = rowvec[row];
+                        ulonglong2 gq;
+                        gq.x = pack2(dv.x, dv.x);
+                        gq.y = pack2(dv.y, dv.y);
                         if (i == 0) {
 #pragma unroll
                             for (int c = 0; c < CH; ++c) A[c] = fmul2(Hp[0][c0 + c], gq.x);
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                         float lo, hi, lo2, hi2;
                         unpack2(A[c], lo, hi);
                         unpack2(B[c], lo2, hi2);
-                        colp[la * (N + 1) + col] = make_float2(lo + hi, lo2 + hi2);
+                        colp[la * (N + 1) + col] = make_float2(lo + hi2, lo2 - hi);
                     }
                 }
             }
@@ -337,9 +342,9 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 for (int q = 0; q < 4; ++q) p[q] = colp[q * (N + 1) + col];
                 const float sx = (p[0].x + p[1].x) + (p[2].x + p[3].x);
                 const float sy = (p[0].y + p[1].y) + (p[2].y + p[3].y);
-                const float4 cv = colvec[colslot(col)];                        // r~ of this column
-                const float xtx = sx + cv.x, xty = sy + cv.z;
-                r[t] = make_float2((xtx - alpha * cv.x) * inv_1ma, (xty - alpha * cv.z) * inv_1ma);
+                const float2 cv = colvec[col];                                 // r~ of this column
+                const float xtx = sx + cv.x, xty = sy + cv.y;
+                r[t] = make_float2((xtx - alpha * cv.x) * inv_1ma, (xty - alpha * cv.y) * inv_1ma);
                 xmapvec[col] = r[t];
                 q_r[t] = __fmul_rn(r[t].x, rsig);                              // s / tau in complex64 (vamp.py:111)
                 q_i[t] = __fmul_rn(r[t].y, rsig);
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 const int col = lane + 32 * t;
                 xh[t] = make_float2(xr_[t], xi_[t]);
                 const float rx = (xr_[t] - dxdr * r[t].x) * norm, ry = (xi_[t] - dxdr * r[t].y) * norm;
-                colvec[colslot(col)] = make_float4(rx, rx, ry, ry);
+                colvec[col] = make_float2(rx, ry);
                 varvec[col] = vn_[t];
                 if (a.traj && a.io.x_true) {
                     const float2 xt = a.io.x_true[f * N + col];
