@@ -16,6 +16,7 @@ struct DevGrid {
     int ca[kGridCorrMax], cb[kGridCorrMax];
     float cw[kGridCorrMax];                  // multiplicity - 1 (0: unused slot)
     float dpos_r[kGridMax], dneg_r[kGridMax], dpos_i[kGridMax], dneg_i[kGridMax];   // (level - top/bottom level) log2 e
+    float cmag[4];                           // |corner level|: re < 0, re >= 0, im < 0, im >= 0
     int corner_ok, corner_k[4];              // first table index of the corner (re < 0 ? min : max, im < 0 ? min : max), slot 2 (re < 0) + (im < 0)
 };
 
