@@ -171,6 +171,13 @@ class Clocks:
     def __init__(self, index):
         self.rows, self.proc, self.index, self.nvml, self.stop = [], None, index, None, False
         self.sm, self.mx, self.reasons, self.source = [], [], set(), None
+        self.t0 = self.t1 = None                       # the timed region (time.perf_counter), set by mark_start / mark_end
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -216,10 +223,9 @@ class Clocks:
             pass
         while not self.stop:
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                if get_reasons:
-                    r = int(get_reasons(self.handle))
-                    self.reasons.update(k for k, b in bits.items() if r & b)
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(self.handle)) if get_reasons else 0
+                self.sm.append((time.perf_counter(), mhz, frozenset(k for k, b in bits.items() if r & b)))
             except Exception:
                 break
             time.sleep(0.002)
@@ -242,15 +248,22 @@ class Clocks:
             self.thread.join(timeout=2)
 
     def summary(self):
+        window = "timed"
         if self.nvml:
-            sm, mx, reasons = self.sm, self.mx, sorted(self.reasons)
+            # the sampler runs from before the warm-up: keep the samples taken inside the timed region; if the region was
+            # shorter than one polling period, the samples of the warm-up steps (the same workload) stand in and say so
+            inside = [x for x in self.sm if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or x[0])]
+            if not inside:
+                inside, window = [x for x in self.sm if self.t0 is None or x[0] <= (self.t1 or x[0])][-8:], "warmup+timed"
+            sm, mx = [x[1] for x in inside], self.mx
+            reasons = sorted(set().union(*[x[2] for x in inside])) if inside else []
         else:
             sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '', 1).isdigit()]
             mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm), "source": self.source}
+                "samples": len(sm), "source": self.source, "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ GPU side
@@ -331,16 +344,18 @@ def main():
         return allreduce_counters(det.counters) if world > 1 else det.counters
 
     def timed(module, steps, warmup):
-        for _ in range(warmup):
-            step(module)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        lib.ampsm_launch_count(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        totals = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
-        kernel_ms = []
-        with Clocks(local) as clk:
+        clk = Clocks(local)
+        with clk:                                       # started before the warm-up: NVML start-up stays out of the timed region
+            for _ in range(warmup):
+                step(module)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            lib.ampsm_launch_count(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            totals = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+            kernel_ms = []
+            clk.mark_start()
             e0.record()
             for _ in range(steps):
                 k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,6 +369,7 @@ def main():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
+            clk.mark_end()
         ms = e0.elapsed_time(e1)
         launches = int(lib.ampsm_launch_count(0))
         if world > 1:
