@@ -47,7 +47,7 @@ struct FastShape {
     static constexpr int ebuf_bytes = 32 * CP * K_ * 4;
     static constexpr int xch_bytes_a = rowpart_bytes > colpart_bytes ? rowpart_bytes : colpart_bytes;
     static constexpr int xch_bytes = ((xch_bytes_a > ebuf_bytes ? xch_bytes_a : ebuf_bytes) + 127) & ~127;
-    static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // padded slots (see the kernel)
+    static constexpr int rowvec_bytes = ((n > 32 ? n : 32) * 20 + 127) & ~127;     // g [32] float2 | 1/u [32] float (PAIR), padded float4 slots otherwise
     static constexpr int colvec_bytes = ((N > 32 ? N : 32) * 20 + 127) & ~127;     // float4 per column + the variance array
     static constexpr int wvec_bytes = 0;
     // per-lane state that is only touched in one phase: z/u, y, xmap | 16 counters | 32 squared-error sums | Loss inputs
@@ -391,7 +391,13 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 const float rn = fast_rcp(un);
                 rowstate[lane] = make_float4(zn.x, zn.y, un, 0.f);
                 const float gx = (yv.x - zn.x) * rn, gy = (yv.y - zn.y) * rn;
-                rowvec[lane + (lane >> 3)] = make_float4(gx, gy, rn, 0.f);       // one load brings all three scalars of a row
+                if constexpr (PAIR) {
+                    // plain arrays g[row] (float2) and 1/u[row] (float): the column pass reads them two rows at a time
+                    reinterpret_cast<float2*>(rowvec)[lane] = make_float2(gx, gy);
+                    reinterpret_cast<float*>(rowvec + 32)[lane] = rn;
+                } else {
+                    rowvec[lane + (lane >> 3)] = make_float4(gx, gy, rn, 0.f);
+                }
             }
             __syncwarp();
             CLK(1);                              // row reduction, z / u update, operand publish
@@ -407,21 +413,29 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                     for (int c = 0; c < CH; ++c) A[c] = B[c] = 0ull;
 #pragma unroll
                     for (int c = 0; c < CH / 2; ++c) C[c] = 0ull;
+                    // broadcast scalar operands (FFMA2 takes a 32-bit register for both halves: no duplicated pairs in shared
+                    // memory, half the register-file traffic of a 64-bit operand):
+                    //   A += h gx = (hr gx, hi gx),  B += h gy = (hr gy, hi gy)  ->  re = A.lo + B.hi,  im = B.lo - A.hi
+                    // The scalars of TWO rows arrive per load pair (LDS.128 {g_a, g_b} + LDS.64 {1/u_a, 1/u_b}): half the loads whose
+                    // latency the mat-vec stream has to cover.
+                    static_assert(RT % 2 == 0, "the packed column pass takes the rows in pairs");
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) {
+                    for (int i = 0; i < RT; i += 2) {
                         const int row = la * RT + i;
-                        // broadcast scalar operands (FFMA2 takes a 32-bit register for both halves: no duplicated pairs in shared
-                        // memory, half the register-file traffic of a 64-bit operand):
-                        //   A += h gx = (hr gx, hi gx),  B += h gy = (hr gy, hi gy)  ->  re = A.lo + B.hi,  im = B.lo - A.hi
-                        const float4 gv = rowvec[row + (row >> 3)];                                              // {g.re, g.im, 1/u, -}
-                        const pair_t gxp = pack2(gv.x, gv.x), gyp = pack2(gv.y, gv.y), wp = pack2(gv.z, gv.z);
+                        const float4 gv = *reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(rowvec) + row);
+                        const float2 wv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(rowvec + 32) + row);
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) {
-                            A[c] = ffma2(Hp[i][c0 + c], gxp, A[c]);
-                            B[c] = ffma2(Hp[i][c0 + c], gyp, B[c]);
+                        for (int e = 0; e < 2; ++e) {
+                            const float gx1 = e ? gv.z : gv.x, gy1 = e ? gv.w : gv.y, w1 = e ? wv.y : wv.x;
+                            const pair_t gxp = pack2(gx1, gx1), gyp = pack2(gy1, gy1), wp = pack2(w1, w1);
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) {
+                                A[c] = ffma2(Hp[i + e][c0 + c], gxp, A[c]);
+                                B[c] = ffma2(Hp[i + e][c0 + c], gyp, B[c]);
+                            }
+#pragma unroll
+                            for (int c = 0; c < CH / 2; ++c) C[c] = ffma2(Pp[i + e][c0 / 2 + c], wp, C[c]);
                         }
-#pragma unroll
-                        for (int c = 0; c < CH / 2; ++c) C[c] = ffma2(Pp[i][c0 / 2 + c], wp, C[c]);
                     }
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
