@@ -41,9 +41,8 @@ struct FastShape {
     static constexpr int NV = CTL / VW;
     static constexpr int CP = (N + 31) / 32;               // owned columns per lane in the denoiser
     static constexpr int stage_bytes = DIRECT ? 0 : ((n * N * 8 + n * 8 + 127) & ~127);   // H, y
-    static constexpr int xrow_bytes = 8 * 16 + 16;           // 8 chunks + pad (see xslot in the kernel)
-    static constexpr int rowpart_bytes = n * xrow_bytes;
-    static constexpr int colpart_bytes = (N / 2) * xrow_bytes;
+    static constexpr int rowpart_bytes = n * 9 * 12;         // float2 + float planes of the row-pass partials (see xrow_put)
+    static constexpr int colpart_bytes = 260 * 8 + 280 * 4;  // float2 + float planes of the column-pass partials (see xcol_put)
     static constexpr int ebuf_bytes = 32 * CP * K_ * 4;
     static constexpr int xch_bytes_a = rowpart_bytes > colpart_bytes ? rowpart_bytes : colpart_bytes;
     static constexpr int xch_bytes = ((xch_bytes_a > ebuf_bytes ? xch_bytes_a : ebuf_bytes) + 127) & ~127;
@@ -165,13 +164,29 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
     // pass), placed so that the 8 column groups read 8 consecutive 16-byte chunks and the 32 owners write without
     // conflicts, plus the variances as a plain float array (adjacent columns = one operand pair).
     float* varvec = reinterpret_cast<float*>(colvec + N);
-    // Partial-sum exchange: 8 float4 chunks per row (row pass: one per column group) or per column pair (column pass: 2
-    // columns x 4 row groups), rows 144 bytes apart.  The 16-byte pad puts consecutive rows 4 banks apart, so the eight
-    // lanes of a quarter-warp that write one row (contiguous 128 bytes) and the eight that read one chunk of eight
-    // consecutive rows are both conflict-free -- and every address is one per-lane base plus an immediate (the XOR swizzle
-    // this replaces cost ~20 address registers, which the compiler spilled).
-    auto xslot = [&](int row, int chunk) -> float4& {
-        return *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(xch) + row * S::xrow_bytes + chunk * 16);
+    // Row-pass partials travel as a float2 plane (H xhat) and a float plane (|H|^2 var), rows 9 entries apart (odd stride:
+    // conflict-free 8-byte and 4-byte accesses on both sides): 3 wavefronts per chunk instead of the 4 of a padded float4
+    auto xrow_put = [&](int row, int chunk, float v, float re, float im) {
+        reinterpret_cast<float2*>(xch)[row * 9 + chunk] = make_float2(re, im);
+        reinterpret_cast<float*>(reinterpret_cast<float2*>(xch) + n * 9)[row * 9 + chunk] = v;
+    };
+    auto xrow_get = [&](int row, int chunk) {
+        const float2 c = reinterpret_cast<const float2*>(xch)[row * 9 + chunk];
+        const float v = reinterpret_cast<const float*>(reinterpret_cast<const float2*>(xch) + n * 9)[row * 9 + chunk];
+        return make_float4(v, c.x, c.y, 0.f);
+    };
+    // Column-pass partials: one float2 plane (H^H g) and one float plane (|H|^2^T 1/u) per row group, columns consecutive inside a
+    // plane.  Plane offsets 0, 65, 130, 195 (float2) and 0, 65, 144, 209 (float: = 0, 1, 16, 17 mod 32) keep the strided writes of
+    // the column pass (column = 2 lb + const) and the consecutive reads of the column owners conflict-free.
+    static_assert(N <= 64, "the column-partial planes are laid out for at most 64 columns");
+    auto xcol_put = [&](int col, int q, float c, float re, float im) {
+        reinterpret_cast<float2*>(xch)[q * 65 + col] = make_float2(re, im);
+        reinterpret_cast<float*>(reinterpret_cast<float2*>(xch) + 260)[(q & 1) * 65 + (q >> 1) * 144 + col] = c;
+    };
+    auto xcol_get = [&](int col, int q) {
+        const float2 v = reinterpret_cast<const float2*>(xch)[q * 65 + col];
+        const float c = reinterpret_cast<const float*>(reinterpret_cast<const float2*>(xch) + 260)[(q & 1) * 65 + (q >> 1) * 144 + col];
+        return make_float4(c, v.x, v.y, 0.f);
     };
     auto colslot = [&](int col) {
         if constexpr (PAIR) {
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                     unpack2(A[i], al_, ah_);
                     unpack2(B[i], bl_, bh_);
                     unpack2(V[i], vl_, vh_);
-                    xslot(row, lb) = make_float4(vl_ + vh_, al_ - bh_, bl_ + ah_, 0.f);
+                    xrow_put(row, lb, vl_ + vh_, al_ - bh_, bl_ + ah_);
                 }
                 asm volatile("" ::: "memory");
             }
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 const int row = la * RT + i;
-                xslot(row, lb) = make_float4(av[i], ar[i], ai[i], 0.f);
+                xrow_put(row, lb, av[i], ar[i], ai[i]);
             }
         }
     };
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
                 for (int c = 0; c < CTL; ++c) v += P[i][c];
             }
-            xslot(row, lb) = make_float4(v, 0.f, 0.f, 0.f);
+            xrow_put(row, lb, v, 0.f, 0.f);
         }
     };
 
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
             if (lane < n) {
                 float4 p[8];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) p[b] = xslot(lane, b);
+                for (int b = 0; b < 8; ++b) p[b] = xrow_get(lane, b);
                 // tree, not a chain: this sits on the iteration's critical path
                 const float sv = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
                 const float sr = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                         unpack2(B[c], blo, bhi);
                         unpack2(C[c / 2], c0_, c1_);
                         const int col = (((c0 + c) / VW) * 8 + lb) * VW + ((c0 + c) % VW);
-                        xslot(col >> 1, (col & 1) * 4 + la) = make_float4((c & 1) ? c1_ : c0_, alo + bhi, blo - ahi, 0.f);
+                        xcol_put(col, la, (c & 1) ? c1_ : c0_, alo + bhi, blo - ahi);
                     }
                     asm volatile("" ::: "memory");     // keep the halves apart: ptxas otherwise parks the first half's sums on the stack
                 }
@@ -467,7 +482,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
 #pragma unroll
                 for (int c = 0; c < CTL; ++c) {
                     const int col = ((c / VW) * 8 + lb) * VW + (c % VW);
-                    xslot(col >> 1, (col & 1) * 4 + la) = make_float4(cc[c], cr[c], ci[c], 0.f);
+                    xcol_put(col, la, cc[c], cr[c], ci[c]);
                 }
             }
             __syncwarp();
@@ -482,7 +497,7 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
                 if (col < N) {
                     float4 p[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) p[q] = xslot(col >> 1, (col & 1) * 4 + q);
+                    for (int q = 0; q < 4; ++q) p[q] = xcol_get(col, q);
                     const float sc = (p[0].x + p[1].x) + (p[2].x + p[3].x);
                     const float sr = (p[0].y + p[1].y) + (p[2].y + p[3].y);
                     const float si = (p[0].z + p[1].z) + (p[2].z + p[3].z);
