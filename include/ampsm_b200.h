@@ -96,6 +96,9 @@ int ampsm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, i
  *   xmap, xmmse : complex64 [frames][N];  var : float [frames][N];  iters : int32 [frames]
  *   traj   : float [frames][max_iters][3] = {mean tau, mean var, mean |xmmse-x|^2} per executed iteration
  *   counters : uint64 [AMPSM_NUM_COUNTERS] (see above)
+ * Alignment: the register-resident kernels (p->kernel = 0 'auto' or 2 'fast') need H, y and x_true 16-byte aligned (as every
+ * cudaMalloc / torch allocation is); with kernel = 0 anything else silently takes the generic kernel, with kernel = 2 the call
+ * returns AMPSM_ENOFIT.
  */
 int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
                       const void* H, int64_t H_frame_stride, const void* y,
