@@ -408,7 +408,7 @@ def main():
     out = {
         "metric": "BAMP frame-iterations/s", "value": value, "unit": "frame-iter/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "complex64 (f32 mat-vecs, f64 exponent differences, f32 exp)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "complex64 (f32 mat-vecs, compensated-f32 exponent offsets, f32 exp; f64 only in the decision fallback)", "data": "synthetic",
         "config": workload_config(args, frames, world), "mean_iterations_per_frame": mean_T,
         "frames_per_s": frames_done / (ms * 1e-3), "fer": c["frame_err"] / max(frames_done, 1),
         "ier": c["index_err"] / max(frames_done * NA * LIN, 1), "nan_frames": c["nan_frames"],
