@@ -151,6 +151,46 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         }
         cp_async_commit();                     // always one group per call: the wait_group counts below rely on it
     };
+    // row pass q = Vh r~ (vamp.py:67): partial sums over the lane's columns into the float2 planes
+    auto row_pass = [&]() {
+        constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
+#pragma unroll
+        for (int i0 = 0; i0 < RT; i0 += RH) {
+            pair_t A[RH], B[RH];
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                const int col = (t * 8 + lb) * 2;
+                const float4 xq = *reinterpret_cast<const float4*>(&colvec[col]);        // the lane's two adjacent columns
+                ulonglong2 x0, x1;
+                x0.x = pack2(xq.x, xq.x);
+                x0.y = pack2(xq.y, xq.y);
+                x1.x = pack2(xq.z, xq.z);
+                x1.y = pack2(xq.w, xq.w);
+                if (t == 0) {
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) A[i] = fmul2(Hp[i0 + i][0], x0.x);
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) B[i] = fmul2(Hp[i0 + i][0], x0.y);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
+#pragma unroll
+                for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < RH; ++i) {
+                float al_, ah_, bl_, bh_;
+                unpack2(A[i], al_, ah_);
+                unpack2(B[i], bl_, bh_);
+                rowp[lb * (R + 1) + la * RT + i0 + i] = make_float2(al_ - bh_, bl_ + ah_);
+            }
+        }
+    };
     long long f = blockIdx.x;
     if (f < a.frames) load_tile(f);
 
@@ -221,56 +261,18 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         for (int t = 0; t < CP; ++t) xh[t] = make_float2(0.f, 0.f);
         __syncwarp();
 
+        // The loop is rotated (as in bamp_fast.cu): an iteration starts at the LMMSE step and ends with the row pass that feeds
+        // the next one, which is skipped when the frame is done -- one row pass less per frame.
+        row_pass();
         int t_done = 0;
-        CLK(7);                                // stage refill issue, state init
-        for (int it = 0; it < g.max_iters; ++it) {
+        CLK(7);                                // stage refill issue, state init, first row pass
+        for (int it = 0;; ++it) {
             // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66).  The scalar
             // divisions of the bookkeeping are MUFU reciprocals (2^-23 relative): an IEEE division is a ~15-instruction
             // dependent sequence, eight of them per iteration sat on the critical path of the first version.
             const float rs2t = fast_rcp(s2t);
             const float ratio = (it == 0) ? ratio0 : nv * rs2t;
-            // ================= row pass: q = Vh r~ (vamp.py:67) =================
-            {
-                constexpr int RH = RT > 4 ? RT / 2 : RT;          // rows in two halves: keeps the accumulators small
-#pragma unroll
-                for (int i0 = 0; i0 < RT; i0 += RH) {
-                    pair_t A[RH], B[RH];
-#pragma unroll
-                    for (int t = 0; t < NV; ++t) {
-                        const int col = (t * 8 + lb) * 2;
-                        const float4 xq = *reinterpret_cast<const float4*>(&colvec[col]);        // the lane's two adjacent columns
-                        ulonglong2 x0, x1;
-                        x0.x = pack2(xq.x, xq.x);
-                        x0.y = pack2(xq.y, xq.y);
-                        x1.x = pack2(xq.z, xq.z);
-                        x1.y = pack2(xq.w, xq.w);
-                        if (t == 0) {
-#pragma unroll
-                            for (int i = 0; i < RH; ++i) A[i] = fmul2(Hp[i0 + i][0], x0.x);
-#pragma unroll
-                            for (int i = 0; i < RH; ++i) B[i] = fmul2(Hp[i0 + i][0], x0.y);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t], x0.x, A[i]);
-#pragma unroll
-                            for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t], x0.y, B[i]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < RH; ++i) A[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.x, A[i]);
-#pragma unroll
-                        for (int i = 0; i < RH; ++i) B[i] = ffma2(Hp[i0 + i][2 * t + 1], x1.y, B[i]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < RH; ++i) {
-                        float al_, ah_, bl_, bh_;
-                        unpack2(A[i], al_, ah_);
-                        unpack2(B[i], bl_, bh_);
-                        rowp[lb * (R + 1) + la * RT + i0 + i] = make_float2(al_ - bh_, bl_ + ah_);
-                    }
-                }
-            }
             __syncwarp();
-            CLK(0);                            // row pass
             // ================= LMMSE in the SVD basis: d = scale (y~ + ratio q) - q (vamp.py:68-72) =================
             float scale;
             {
@@ -397,7 +399,9 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             }
             t_done = it + 1;
             CLK(5);                            // Onsager scalars, publish
-            if (g.early_exit && all_close) break;
+            if ((g.early_exit && all_close) || t_done >= g.max_iters) break;
+            row_pass();
+            CLK(0);                            // row pass
         }
         // pending cp.async groups: {Loss inputs of f, y / s of the next frame} -> the former are complete; waited for BEFORE
         // the tile loads, behind which the wait's dependency barrier would queue in the load/store unit
@@ -475,7 +479,8 @@ int launch_vshape(const VampArgs& a, cudaStream_t stream) {
 int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
     const Geom& g = a.g;
     // complex64, one time slot per frame, MAP decision, per-section shift; 16-byte aligned rows for the tile loads
-    if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0 || g.R != 32 || g.N != 64 || g.n > 64 || g.n < 1) return AMPSM_ENOFIT;
+    if (g.Lin != 1 || g.decision != 0 || g.shift_mode != 0 || g.R != 32 || g.N != 64 || g.n > 64 || g.n < 1 || g.max_iters < 1)
+        return AMPSM_ENOFIT;
     if (reinterpret_cast<uintptr_t>(a.io.x_true) % 16) return AMPSM_ENOFIT;     // the Loss inputs are staged by 16-byte cp.async
     if ((reinterpret_cast<uintptr_t>(a.Vh) % 16) || (a.Vh_stride != 0 && ((size_t)a.Vh_stride * 8) % 16) ||
         (reinterpret_cast<uintptr_t>(a.U) % 16) || (reinterpret_cast<uintptr_t>(a.y) % 8) || (reinterpret_cast<uintptr_t>(a.s) % 4))
