@@ -672,6 +672,8 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream) {
         AMPSM_SHAPE(8, 8, 64, 16, true)     // C2 with the table-driven denoiser
         AMPSM_SHAPE(8, 8, 64, 4, true)      // 64 x 32, QPSK
         AMPSM_SHAPE(8, 8, 16, 4, true)      // 64 x 32, QPSK, Na = 4
+        AMPSM_SHAPE(8, 8, 32, 4, true)      // 64 x 32, QPSK, Na = 2
+        AMPSM_SHAPE(8, 8, 16, 16, true)     // 64 x 32, 16-QAM, Na = 4 (table-driven denoiser)
     }
     AMPSM_SHAPE(8, 8, 64, 16, false)
     AMPSM_SHAPE(1, 1, 8, 4, false)       // C1:  8 x  4, QPSK

@@ -494,6 +494,7 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
     AMPSM_VSHAPE(64, 16)    // 64 x 32, 16-QAM, table-driven denoiser
     AMPSM_VSHAPE(64, 4)     // 64 x 32, QPSK
     AMPSM_VSHAPE(16, 4)     // 64 x 32, QPSK, Na = 4
+    AMPSM_VSHAPE(32, 4)     // 64 x 32, QPSK, Na = 2
 #undef AMPSM_VSHAPE
     return AMPSM_ENOFIT;
 }

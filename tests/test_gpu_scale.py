@@ -107,17 +107,28 @@ def test_high_snr_qpsk_decodes_every_frame():
         assert c["frame_err"] == 0 and c["index_bit_err"] == 0 and c["symbol_bit_err"] == 0 and c["nan_frames"] == 0
 
 
-@pytest.mark.parametrize("fast,Na", [("pair", 4), ("fast", 4), ("pair", 2)])
-def test_multi_section_fast_shape_matches_generic(fast, Na):
+@pytest.mark.parametrize("fast,Na,alphabet", [("pair", 4, "QPSK"), ("fast", 4, "QPSK"), ("pair", 2, "QPSK"), ("fast", 2, "QPSK"),
+                                              ("fast", 4, "16QAM")])
+def test_multi_section_fast_shape_matches_generic(fast, Na, alphabet):
     """64 x 32, QPSK, Na = 4 / 2 (sections of 16 / 32 antennas: sub-warp and whole-warp section reductions)."""
     F = 20000
-    cfg = c2(F, alphabet='QPSK', Na=Na)
-    H, y, x, lab, idx = make_frames(cfg, F, 6.0, seed=8)
-    a = pkg.BAMP(cfg, kernel=fast).detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
-    b = pkg.BAMP(cfg, kernel='generic', exp='f64').detect(H, y, 10 ** 0.6, x, lab, idx).counters_dict()
+    cfg = c2(F, alphabet=alphabet, Na=Na)
+    snr_db = 6.0 if alphabet == 'QPSK' else 18.0          # a regime where the frames converge (else the counts are chaotic)
+    H, y, x, lab, idx = make_frames(cfg, F, snr_db, seed=8)
+    a = pkg.BAMP(cfg, kernel=fast).detect(H, y, 10 ** (snr_db / 10), x, lab, idx).counters_dict()
+    b = pkg.BAMP(cfg, kernel='generic', exp='f64').detect(H, y, 10 ** (snr_db / 10), x, lab, idx).counters_dict()
     diff = {k: (a[k], b[k]) for k in INT_KEYS if a[k] != b[k]}
-    # at most two frames may decide differently (near-ties in float32); a frame carries up to 4 sections of bit errors
-    assert all(abs(u - v) <= (8 if k.endswith("bit_err") else 2) for k, (u, v) in diff.items()), diff
+    if alphabet == 'QPSK':
+        # at most two frames may decide differently (near-ties in float32); a frame carries up to 4 sections of bit errors
+        assert all(abs(u - v) <= (8 if k.endswith("bit_err") else 2) for k, (u, v) in diff.items()), diff
+    else:
+        # 16-QAM with several sections never converges for ~15 % of the sections at any SNR (the reference's decision metric
+        # lacks the |s|^2 term, SURVEY.md App. B.5): those frames wander chaotically in float32, so -- as for VAMP -- the
+        # acceptance is two-sided: as close to the float64-exponent kernel as the generic kernel's own float32-exp mode
+        c = pkg.BAMP(cfg, kernel='generic', exp='f32').detect(H, y, 10 ** (snr_db / 10), x, lab, idx).counters_dict()
+        for k in INT_KEYS:
+            slack = 2e-3 * F * cfg.L * (4 if k.endswith("bit_err") else 1)
+            assert abs(a[k] - b[k]) <= abs(c[k] - b[k]) + slack, (k, a[k], b[k], c[k])
 
 
 def test_shared_matrix_and_edge_frame_counts():
@@ -255,7 +266,7 @@ def svd_factors(H):
     return torch.cat(Us).contiguous(), torch.cat(ss).contiguous(), torch.cat(Vs).contiguous()
 
 
-@pytest.mark.parametrize("alphabet,Na,snr_db", [("16QAM", 1, 12.0), ("QPSK", 1, 8.0), ("QPSK", 4, 6.0)])
+@pytest.mark.parametrize("alphabet,Na,snr_db", [("16QAM", 1, 12.0), ("QPSK", 1, 8.0), ("QPSK", 4, 6.0), ("QPSK", 2, 7.0)])
 def test_vamp_fast_and_generic_kernels_agree(alphabet, Na, snr_db):
     """Register-resident VAMP kernel (one warp per frame, FFMA2, separable / table denoiser) against the generic
     shared-memory kernel with float64 exponents on 20k frames with per-frame SVD factors."""
