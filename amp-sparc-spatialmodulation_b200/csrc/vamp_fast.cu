@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
         __syncwarp();
 
         // The loop is rotated (as in bamp_fast.cu): an iteration starts at the LMMSE step and ends with the row pass that feeds
-        // the next one, which is skipped when the frame is done -- one row pass less per frame.
+        // the next one.  The number of row passes per frame is unchanged (the first one runs here, none after the last
+        // iteration); the order just schedules better (+1.3 % at the early exit, measured).
         row_pass();
         int t_done = 0;
         CLK(7);                                // stage refill issue, state init, first row pass
