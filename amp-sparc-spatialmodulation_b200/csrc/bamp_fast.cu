@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(FastShape<RT, CTL, M_, K_, DIRECT>::warps_per_
         __syncwarp();
 
         // The loop is rotated: an iteration starts at the row REDUCTION and ends with the row pass that feeds the next
-        // one, which is skipped when the frame is done (bamp.py:140) -- one row pass less per frame.
+        // one; the frame's FIRST row pass is row_pass_first() above (row sums of |H|^2, no products with xhat = 0), so a frame of T
+        // iterations runs T - 1 full row passes instead of T.
         int t_done = 0;
         CLK(7);                                  // prologue
         for (int it = 0;; ++it) {
