@@ -19,7 +19,7 @@ constexpr int BK = 32;   // reduction chunk
 
 __host__ __device__ inline size_t up256(size_t v) { return (v + 255) & ~size_t(255); }
 
-static bool scamp_use_tc(long long F) { return F >= 128 && !getenv("AMPSM_SCAMP_SIMT"); }
+static bool scamp_use_tc(const Geom& g, long long F) { return F >= 128 && !getenv("AMPSM_SCAMP_SIMT") && scamp_tc_fits(g.n, g.N, F); }
 
 static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, ScampWs* ws, unsigned char* base) {
     size_t o = 0;
@@ -42,7 +42,7 @@ static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, S
     w.scr = take((size_t)F * g.N * 3 * (exp64 ? 8 : 4));
     w.nzc = (g.N + TILE - 1) / TILE;
     w.nz = take((size_t)((g.n + TILE - 1) / TILE) * w.nzc);
-    w.At = (float2*)take(scamp_use_tc(F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
+    w.At = (float2*)take(scamp_use_tc(g, F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
     w.notclose = (int*)take((size_t)F * 4);
     if (ws) *ws = w;
     return o;
@@ -390,14 +390,18 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
     const dim3 grid_res((g.n + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
     const dim3 grid_est((g.N + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
     // batches of >= 128 frames: both GEMMs on the tensor cores (tcgen05, 3xTF32, scamp_tc.cu); smaller ones on the SIMT tiles
-    const bool use_tc = scamp_use_tc(F);
+    const bool use_tc = scamp_use_tc(g, F);
+    auto fail = [&](int e) {                               // every exit path returns the workspace it allocated
+        if (own_ws) cudaFreeAsync(base, stream);
+        return e;
+    };
     if (use_tc)
-        if (int e = scamp_tc_prepare(a.A, w.At, g.n, g.N, stream)) return e;
+        if (int e = scamp_tc_prepare(a.A, w.At, g.n, g.N, stream)) return fail(e);
     for (int t = 0; t < g.max_iters; ++t) {
         scamp_scalars_kernel<<<(unsigned)F, 64, 0, stream>>>(w, g, a.W, a.sigma2, a.sigma2_pf, F);
         if (use_tc) {
-            if (int e = scamp_tc_gemm(0, w, g, a.A, a.y, F, stream)) return e;
-            if (int e = scamp_tc_gemm(1, w, g, w.At, a.y, F, stream)) return e;
+            if (int e = scamp_tc_gemm(0, w, g, a.A, a.y, F, stream)) return fail(e);
+            if (int e = scamp_tc_gemm(1, w, g, w.At, a.y, F, stream)) return fail(e);
         } else {
             scamp_gemm_kernel<0><<<grid_res, 256, 0, stream>>>(w, g, a.A, a.y, F);
             scamp_gemm_kernel<1><<<grid_est, 256, 0, stream>>>(w, g, a.A, a.y, F);

@@ -580,6 +580,11 @@ __global__ void transpose_c64_kernel(const float2* __restrict__ A, float2* __res
 
 }  // namespace
 
+bool scamp_tc_fits(int n, int N, long long F) {
+    // both reductions must fit the non-zero bitmap, and the frame tiles the grid's y dimension
+    return (n + TK - 1) / TK <= kMaxKBlocks && (N + TK - 1) / TK <= kMaxKBlocks && (F + TM - 1) / TM <= 65535;
+}
+
 int scamp_tc_prepare(const float2* A, float2* At, int n, int N, cudaStream_t stream) {
     transpose_c64_kernel<<<dim3((N + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, stream>>>(A, At, n, N);
     count_launch();
@@ -589,16 +594,13 @@ int scamp_tc_prepare(const float2* A, float2* At, int n, int N, cudaStream_t str
 int scamp_tc_gemm(int mode, const ScampWs& w, const Geom& g, const float2* Bm, const float2* y, long long F, cudaStream_t stream) {
     // the residual GEMM has few outputs (n): 32-wide tiles give it twice the CTAs (two per SM overlap staging and MMAs)
     constexpr int TN0 = 32, TN1 = 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<0, TN0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN0>::total),
-                               "cudaFuncSetAttribute(scamp_tc<0>)"))
-            return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<1, TN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN1>::total),
-                               "cudaFuncSetAttribute(scamp_tc<1>)"))
-            return e;
-        attr_set = true;
-    }
+    // function attributes are per device: set on every launch (cheap), as the other launchers do
+    if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<0, TN0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN0>::total),
+                           "cudaFuncSetAttribute(scamp_tc<0>)"))
+        return e;
+    if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_gemm_kernel<1, TN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<TN1>::total),
+                           "cudaFuncSetAttribute(scamp_tc<1>)"))
+        return e;
     const int Kdim = mode == 0 ? g.N : g.n;
     if ((Kdim + TK - 1) / TK > kMaxKBlocks) {
         set_error("SCAMP tensor-core GEMM: reduction length %d exceeds %d", Kdim, kMaxKBlocks * TK);
@@ -608,13 +610,9 @@ int scamp_tc_gemm(int mode, const ScampWs& w, const Geom& g, const float2* Bm, c
     const int TNm = mode == 0 ? TN0 : TN1;
     const dim3 grid((Odim + TNm - 1) / TNm, (unsigned)((F + TM - 1) / TM));
     if (mode == 0 && (Kdim & 1) == 0 && reinterpret_cast<uintptr_t>(Bm) % 16 == 0 && !getenv("AMPSM_SCAMP_NORING")) {
-        static bool ring_attr = false;
-        if (!ring_attr) {
-            if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_ring_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                        RingSmem<64>::total), "cudaFuncSetAttribute(scamp_tc_ring)"))
-                return e;
-            ring_attr = true;
-        }
+        if (int e = check_cuda(cudaFuncSetAttribute(scamp_tc_ring_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    RingSmem<64>::total), "cudaFuncSetAttribute(scamp_tc_ring)"))
+            return e;
         const dim3 grid_r((Odim + 63) / 64, (unsigned)((F + TM - 1) / TM));     // 64-wide tiles: one wave of CTAs at 1024 frames
         scamp_tc_ring_kernel<0, 64><<<grid_r, kTcThreads, RingSmem<64>::total, stream>>>(w, g, Bm, y, F);
     } else if (mode == 0)

@@ -25,6 +25,7 @@ struct ScampWs {
 };
 
 // tensor-core GEMMs (scamp_tc.cu): mode 0 = residual with Bm = A, mode 1 = estimate with Bm = A^T
+bool scamp_tc_fits(int n, int N, long long F);
 int scamp_tc_prepare(const float2* A, float2* At, int n, int N, cudaStream_t stream);
 int scamp_tc_gemm(int mode, const ScampWs& w, const Geom& g, const float2* Bm, const float2* y, long long F, cudaStream_t stream);
 

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) shrink_ook_kernel(const __grid_constant__
         const float eta = expf(regularize_exp(theta + (1.0f - 2.0f * a.r[i].x) / c));
         const float e = 1.0f / (1.0f + eta + 1.0e-9f);
         float der = 2.0f * eta * e * e / c;
-        if (der != der) der = 0.f;
+        if (der != der) der = 0.f;                        // torch.nan_to_num(der, nan=0.0) also maps +-inf to +-FLT_MAX
+        der = fminf(fmaxf(der, -3.402823466e+38f), 3.402823466e+38f);
         a.out_f[i] = e;
         acc += (double)der;
     }

@@ -499,7 +499,8 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream) {
         return AMPSM_ENOFIT;
     if (reinterpret_cast<uintptr_t>(a.io.x_true) % 16) return AMPSM_ENOFIT;     // the Loss inputs are staged by 16-byte cp.async
     if ((reinterpret_cast<uintptr_t>(a.Vh) % 16) || (a.Vh_stride != 0 && ((size_t)a.Vh_stride * 8) % 16) ||
-        (reinterpret_cast<uintptr_t>(a.U) % 16) || (reinterpret_cast<uintptr_t>(a.y) % 8) || (reinterpret_cast<uintptr_t>(a.s) % 4))
+        (reinterpret_cast<uintptr_t>(a.U) % 16) || (a.U_stride != 0 && ((size_t)a.U_stride * 8) % 16) ||
+        (reinterpret_cast<uintptr_t>(a.y) % 8) || (reinterpret_cast<uintptr_t>(a.s) % 4))
         return AMPSM_ENOFIT;
     const int K = a.al.K;
     VampArgs b = a;
