@@ -17,11 +17,11 @@ COUNTER_NAMES = ['frames', 'frame_err', 'slot_err', 'slot_err_first', 'slot_err_
                  'index_err', 'symbol_err', 'index_bit_err', 'symbol_bit_err', 'iters', 'nan_frames']
 SQERR_NAMES = ['sqerr', 'sqerr_first', 'sqerr_mid', 'sqerr_last']
 
-# every symbol include/ampsm_b200.h declares (checked by tests/test_cabi_symbols.py)
+# every symbol include/ampsm_b200.h declares (checked by tests/test_host_api.py::test_cabi_library_exports_every_declared_symbol)
 EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_taps", "ampsm_bamp_detect_host",
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
            "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
-           "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops",
+           "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops", "ampsm_probe_fp64_tflops",
            "ampsm_launch_count"]
 
 
@@ -78,6 +78,7 @@ def lib():
     L.ampsm_shrink.argtypes = [i32, AP, dbl, dbl, i64, i32, vp, vp, i64, vp, vp, vp, vp]
     L.ampsm_probe_fp32_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ampsm_probe_fp32x2_tflops.argtypes = [i32, C.POINTER(dbl)]
+    L.ampsm_probe_fp64_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ampsm_launch_count.argtypes = [i32]
     L.ampsm_launch_count.restype = i64
     for name in EXPORTS:

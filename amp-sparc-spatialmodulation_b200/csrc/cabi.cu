@@ -223,6 +223,7 @@ int64_t ampsm_launch_count(int reset) {
 
 int ampsm_probe_fp32_tflops(int device, double* tflops) { return probe_fp32(device, tflops); }
 int ampsm_probe_fp32x2_tflops(int device, double* tflops) { return probe_fp32x2(device, tflops); }
+int ampsm_probe_fp64_tflops(int device, double* tflops) { return probe_fp64(device, tflops); }
 
 // ---------------------------------------------------------------- BAMP
 int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* H,

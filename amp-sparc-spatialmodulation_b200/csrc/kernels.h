@@ -125,5 +125,6 @@ int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U
 int launch_identity(float2* I, int n, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);
 int probe_fp32x2(int device, double* tflops);
+int probe_fp64(int device, double* tflops);
 
 }  // namespace ampsm

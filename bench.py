@@ -9,8 +9,10 @@ A step = one SNR point: every frame of the per-GPU pool is detected once (per-fr
 the reference, fused hard decision + error counters), followed by the NCCL all-reduce of the counter block.
 `value` = frame-iterations executed by all ranks / device time (CUDA events, max over ranks), inputs resident
 in HBM.  `e2e` = the same metric through the C-ABI host entry point (ampsm_bamp_detect_host) with pinned host
-buffers, host<->device copies inside the timed region.  `cpu_baseline` / `--impl reference` time the numpy oracle
-port of the reference's path on the host cores (the reference is Python and cannot travel to the GPU box).
+buffers, host<->device copies inside the timed region.  `cpu_baseline` / `--impl reference` time the reference's OWN torch
+CPU path (bamp.py:116-143 with batch=1, one call per frame, Loss included) on all host cores when the unmodified reference is
+importable -- /root/reference in the build container, baseline/_ref (git-ignored, placed by scripts/install_reference.py)
+on the GPU box -- and the numpy oracle port beside it (kind "reference" / "port"); the port alone when it is not.
 """
 import argparse
 import json
@@ -65,6 +67,10 @@ def parse():
     ap.add_argument("--vamp-frames", type=int, default=1 << 18, help="frames per GPU of the VAMP leg (0 = skip it)")
     ap.add_argument("--c3-frames", type=int, default=1 << 14, help="frames per GPU of the config-3 VAMP leg (128 x 64; 0 = skip it)")
     ap.add_argument("--c3-snr-db", type=float, default=2.0)
+    ap.add_argument("--scamp-frames", type=int, default=1024, help="frames of the config-4 SCAMP leg (A 1088 x 16384 shared; 0 = skip it)")
+    ap.add_argument("--scamp-ebn0-db", type=float, default=6.0)
+    ap.add_argument("--c1-frames", type=int, default=1 << 20, help="frames per GPU of the config-1 BAMP leg (8 x 4 QPSK; 0 = skip it)")
+    ap.add_argument("--c128-frames", type=int, default=1 << 12, help="frames of the config-3 complex128 VAMP leg (0 = skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed-t", action="store_true")
     return ap.parse_args()
@@ -102,6 +108,46 @@ def _cpu_worker(args):
     return int(r["iters"].sum()), time.perf_counter() - t0
 
 
+def reference_dir():
+    """Where the unmodified reference can be imported from (None: only the oracle port is available)."""
+    for d in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.exists(os.path.join(d, "bamp.py")) and os.path.exists(os.path.join(d, "loss.py")):
+            return d
+    return None
+
+
+def _ref_worker(args):
+    """The reference's torch CPU path as its drivers run it (bamp_model.py:44-67): batch=1, one BAMP.forward (= all
+    iterations + Loss) per frame, per-frame channel; one torch thread per process, one process per core.  Only the
+    detector call is timed (input generation excluded).  Returns (frame-iterations, detector seconds, frames)."""
+    frames, snr_db, seed, refdir = args
+    import torch
+    torch.set_num_threads(1)
+    if refdir not in sys.path:
+        sys.path.insert(0, refdir)
+    import config as rconfig
+    import channel as rchannel
+    import data as rdata
+    import bamp as rbamp
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    cfg = rconfig.Config(NT, NA, NR, LIN, LH, batch=1, generator_mode='sparc', iterations=ITERS, alphabet=ALPHABET,
+                         channel_profile='uniform', device='cpu')
+    ch, da, amp = rchannel.Channel(cfg), rdata.Data(cfg), rbamp.BAMP(cfg)
+    snr = 10 ** (snr_db / 10)
+    iters, secs = 0, 0.0
+    with torch.no_grad():
+        for _ in range(frames):
+            H = ch.generate_channel()
+            x, sym, idx = da.generate_message()
+            y = H @ x + ch.awgn(snr)
+            t0 = time.perf_counter()
+            loss = amp(H, y, snr, x, sym, idx)
+            secs += time.perf_counter() - t0
+            iters += int(loss.loss['T'])
+    return iters, secs, frames
+
+
 class CpuPool:
     """Process pool over the host cores running the numpy oracle port; one slice of frames per process."""
 
@@ -118,36 +164,63 @@ class CpuPool:
         wall = time.perf_counter() - t0
         return sum(r[0] for r in res) / wall, per * self.workers, wall
 
+    def ref_rate(self, frames_total, snr_db, refdir, seed=7):
+        """All cores run the reference concurrently; the rate is the sum of the per-core detector rates."""
+        per = max(1, frames_total // self.workers)
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_worker, [(per, snr_db, seed + w, refdir) for w in range(self.workers)])
+        wall = time.perf_counter() - t0
+        return sum(r[0] / r[1] for r in res), per * self.workers, wall, sum(r[0] for r in res) / max(sum(r[2] for r in res), 1)
+
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
 def run_reference(args):
-    """--impl reference: the oracle port of the reference's CPU path, all host cores, bounded sample per step."""
+    """--impl reference: the reference's own torch CPU path (batch=1 per frame, all host cores) when the unmodified reference
+    is importable, else the numpy oracle port; a bounded sample of the arm's workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = args.cpu_frames or 4096 * cores
+    refdir = reference_dir()
     pool = CpuPool(cores)
-    for _ in range(args.warmup):
-        pool.rate(max(cores * 16, frames // 8), args.snr_db)
+    port_frames = 2048 * cores
+    port_rate, port_used, port_wall = pool.rate(port_frames, args.snr_db)            # the port beside it, one sample
+    if refdir:
+        pool.ref_rate(4 * cores, args.snr_db, refdir)                               # imports + first calls, untimed
+        probe, _, wall, _ = pool.ref_rate(16 * cores, args.snr_db, refdir)
+        per_core = max(8, min(2048, int(16 * 2.5 / max(wall, 1e-3))))               # ~2.5 s per step
+        frames = args.cpu_frames or per_core * cores
+        run = lambda n, seed: pool.ref_rate(n, args.snr_db, refdir, seed=seed)[:3]
+        kind = "reference"
+        what = (f"the reference's own torch CPU path ({os.path.relpath(refdir, ROOT) if refdir.startswith(ROOT) else refdir}: "
+                f"bamp.py BAMP.forward incl. Loss, batch=1 per frame, {cores} processes x 1 torch thread, detector time only)")
+    else:
+        frames = args.cpu_frames or 4096 * cores
+        run = lambda n, seed: pool.rate(n, args.snr_db, seed=seed)
+        kind = "port"
+        what = f"numpy oracle port (oracle/amp_oracle.py), {cores} processes (the reference itself is not importable here)"
+    for w in range(args.warmup):
+        run(max(cores * 4, frames // 4), 50 + w)
     rates = []
     t_all = time.perf_counter()
     for s in range(args.steps):
-        rate, used, wall = pool.rate(frames, args.snr_db, seed=100 + s)
+        rate, used, wall = run(frames, 100 + s)
         rates.append(rate)
     ms = (time.perf_counter() - t_all) / max(args.steps, 1) * 1e3
     pool.close()
     v = float(np.mean(rates))
-    sample = f"{used} frames/step of BAMP 64x32 16-QAM at {args.snr_db} dB, numpy oracle port, {cores} processes"
+    sample = f"{used} frames/step of BAMP 64x32 16-QAM at {args.snr_db} dB through {what}"
     emit(json.dumps({
         "impl": "reference", "metric": "BAMP frame-iterations/s", "value": v, "unit": "frame-iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex64 (denoiser float64)", "data": "synthetic",
-        "config": workload_config(args, frames, 1),
-        "cpu_baseline": {"value": v, "unit": "frame-iter/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.frames, max(1, args.gpus)),
+        "cpu_baseline": {"value": v, "unit": "frame-iter/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_port": {"value": port_rate, "unit": "frame-iter/s", "cores": cores, "kind": "port",
+                     "sample": f"{port_used} frames in {port_wall:.1f} s, numpy oracle port (vectorised over frames), {cores} processes"},
         "e2e": {"value": v, "unit": "frame-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -305,16 +378,28 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
-    cpu_base = None
+    cpu_base = cpu_port = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:       # before CUDA is touched in this process
         cores = os.cpu_count() or 1
-        frames_cpu = args.cpu_frames or 32768 * cores      # ~10-15 s of host work
         pool = CpuPool(cores)
+        frames_cpu = args.cpu_frames or 16384 * cores      # ~5 s of host work for the port
         rate, used, wall = pool.rate(frames_cpu, args.snr_db)
+        cpu_port = {"value": rate, "unit": "frame-iter/s", "cores": cores, "kind": "port",
+                    "sample": f"{used} frames of the same workload in {wall:.1f} s, numpy oracle port (oracle/amp_oracle.py, vectorised "
+                              f"over frames), {cores} processes"}
+        refdir = reference_dir()
+        if refdir:
+            pool.ref_rate(4 * cores, args.snr_db, refdir)
+            _, _, w0, _ = pool.ref_rate(16 * cores, args.snr_db, refdir)
+            per_core = max(16, min(8192, int(16 * 15.0 / max(w0, 1e-3))))            # ~15 s of host work
+            rrate, rused, rwall, rT = pool.ref_rate(per_core * cores, args.snr_db, refdir)
+            cpu_base = {"value": rrate, "unit": "frame-iter/s", "cores": cores, "kind": "reference",
+                        "sample": f"{rused} frames of the same workload in {rwall:.1f} s through the reference's own torch CPU path "
+                                  f"(bamp.py BAMP.forward incl. Loss, batch=1 per frame, mean T = {rT:.2f}; {cores} processes x 1 torch "
+                                  f"thread; detector time only, input generation excluded)"}
+        else:
+            cpu_base = dict(cpu_port)
         pool.close()
-        cpu_base = {"value": rate, "unit": "frame-iter/s", "cores": cores, "kind": "port",
-                    "sample": f"{used} frames of the same workload in {wall:.1f} s, numpy oracle port (oracle/amp_oracle.py), "
-                              f"{cores} processes"}
 
     import torch
     import torch.distributed as dist
@@ -393,17 +478,32 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    import ctypes
+    tfp = ctypes.c_double(0.0)
+    lib.ampsm_probe_fp32_tflops(local, ctypes.byref(tfp))
+    fp32_peak = tfp.value                                # FFMA probe kernel of the library, run in this process
+    fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12        # 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4
     traffic = None
     try:
         per_frame = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bamp_c2_bytes_per_frame")
         traffic = per_frame * frames if per_frame else None       # ncu dram bytes per frame x frames of this launch
     except OSError:
         pass
-    per_gpu_frames_per_launch = frames
-    achieved_gbs = per_gpu_frames_per_launch * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "bamp (per-GPU launch)", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "kernel_ms": kernel_ms}
+    per_gpu_iters_per_launch = frame_iters / max(world, 1) / max(args.steps, 1)
+    achieved_gbs = frames * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    achieved_tf = per_gpu_iters_per_launch * FLOP_PER_FRAME_ITER / (kernel_ms * 1e-3) / 1e12
+    r_hbm = {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "peak_source": peak_src,
+             "algorithmic_bytes_per_frame": BYTES_PER_FRAME}
+    r_fp32 = {"achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
+              "peak_source": "FFMA probe kernel run in this process (ampsm_probe_fp32_tflops)", "peak_nominal": fp32_nominal,
+              "frac_of_nominal": achieved_tf / fp32_nominal, "algorithmic_flop_per_frame_iter": FLOP_PER_FRAME_ITER}
+    binding = "fp32" if (r_fp32["frac"] or 0.0) >= r_hbm["frac"] else "hbm"
+    top = r_fp32 if binding == "fp32" else r_hbm
+    roofline = {"bound": binding, "binding": binding, "kernel": "bamp_fast_kernel (one launch per step and GPU)", "achieved": top["achieved"],
+                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "hbm": r_hbm, "fp32": r_fp32, "kernel_ms": kernel_ms,
+                "traffic": traffic,
+                "traffic_source": "profiles/roofline_traffic.json (dram__bytes_read+write per frame from the committed ncu --set full "
+                                  "capture of this kernel) x frames of one launch; a stored constant, not measured in this run"}
 
     out = {
         "metric": "BAMP frame-iterations/s", "value": value, "unit": "frame-iter/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -420,23 +520,18 @@ def main():
     # fixed-T mode (exit disabled: exactly 20 iterations per frame) against the FP32 pipe
     if not args.no_fixed_t:
         ms2, kms2, c2, _, _ = timed(amp_fixed, max(2, args.steps // 2), 1)
-        tf = 0.0
-        if rank == 0:
-            import ctypes
-            t = ctypes.c_double(0.0)
-            lib.ampsm_probe_fp32_tflops(local, ctypes.byref(t))
-            tf = t.value
+        tf = fp32_peak
         v2 = c2["iters"] / (ms2 * 1e-3)
         ach = (frames * ITERS * FLOP_PER_FRAME_ITER) / (kms2 * 1e-3) / 1e12
         out["fixed_T"] = {"value": v2, "unit": "frame-iter/s", "iterations": ITERS, "kernel_ms": kms2,
                           "roofline_fp32": {"bound": "fp32", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
                                             "frac": (ach / tf) if tf else None,
                                             "peak_source": "FFMA probe kernel run in this process (ampsm_probe_fp32_tflops)",
+                                            "peak_nominal": fp32_nominal, "frac_of_nominal": ach / fp32_nominal,
                                             "algorithmic_flop_per_frame_iter": FLOP_PER_FRAME_ITER}}
 
     # end to end through the C-ABI host entry point: pinned host buffers, H2D/D2H inside the timed region
     fe = min(args.e2e_frames, frames)
-    import ctypes
     hH = H[:fe].cpu().pin_memory()
     hy = y[:fe].cpu().pin_memory()
     hx = x[:fe].cpu().pin_memory()
@@ -609,8 +704,147 @@ def main():
                         "tflops": cf3["iters"] * flop3 / (msf3 * 1e-3) / 1e12},
         }
         del U3, s3, V3
+    # ---- BASELINE config 1: BAMP 8 x 4 QPSK (the reference's own CPU-runnable case) through the same entry point
+    if args.c1_frames > 0:
+        f1 = args.c1_frames
+        cfg1 = pkg.Config(8, 1, 4, 1, 1, batch=f1, generator_mode='sparc', iterations=ITERS, alphabet='QPSK',
+                          channel_profile='uniform', device=str(dev))
+        from amp_sparc_spatialmodulation_b200.simulate import device_frames
+        snr1 = 10 ** (10.0 / 10)
+        H1, y1, x1, l1, i1 = device_frames(cfg1, f1, snr1, torch.Generator(device=dev).manual_seed(77 + rank))
+        amp1 = pkg.BAMP(cfg1, outputs=False)
+        for _ in range(2):
+            amp1.detect(H1, y1, snr1, x1, l1, i1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            det = amp1.detect(H1, y1, snr1, x1, l1, i1)
+        e1.record()
+        torch.cuda.synchronize()
+        c1d, ms1 = det.counters_dict(), e0.elapsed_time(e1) / 3
+        b1 = 8 * 4 * 8 + 8 * 4 + 8 * 8                       # H, y, x_true: 352 B per frame
+        fl1 = 20 * 4 * 8 + 18 * 8 * 4 + 30 * 4 + 20 * 8      # 1 496 flop per frame-iteration
+        out["bamp_c1"] = {
+            "metric": "BAMP frame-iterations/s", "value": c1d["iters"] / (ms1 * 1e-3), "unit": "frame-iter/s", "frames_per_gpu": f1,
+            "mean_iterations_per_frame": c1d["iters"] / f1, "fer": c1d["frame_err"] / f1, "nan_frames": c1d["nan_frames"],
+            "config": {"workload": "BAMP Nt=8 Nr=4 Na=1 QPSK SM, per-frame i.i.d. Rayleigh H, iterations=20, early exit, SNR 10 dB; per-rank time"},
+            "roofline": {"hbm": {"achieved": f1 * b1 / (ms1 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": f1 * b1 / (ms1 * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_frame": b1},
+                         "fp32": {"achieved": c1d["iters"] * fl1 / (ms1 * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                  "frac": c1d["iters"] * fl1 / (ms1 * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                                  "algorithmic_flop_per_frame_iter": fl1}}}
+        del H1, y1, x1
+    # ---- BASELINE config 4: SCAMP, L = 256 sections x M = 64, design matrix shared by the frame batch (scamp.py:77-108):
+    # Config(512, 8, 32, 32, 3, 'tail', QPSK) -> A 1088 x 16384 (8.8 % non-zero: band of Lh = 3 blocks), W 34 x 32
+    if args.scamp_frames > 0 and rank == 0:
+        fs = args.scamp_frames
+        cfg4 = pkg.Config(512, 8, 32, 32, 3, batch=fs, generator_mode='sparc', iterations=ITERS, alphabet='QPSK',
+                          channel_profile='uniform', channel_truncation='tail', device=str(dev))
+        np.random.seed(0)
+        W4, A4 = pkg.Channel(pkg.Config(512, 8, 32, 32, 3, batch=1, generator_mode='sparc', iterations=ITERS, alphabet='QPSK',
+                                        channel_profile='uniform', channel_truncation='tail', device='cpu')).generate_as_sparc()
+        W4, A4 = W4.to(dev), A4.to(dev)
+        g4 = torch.Generator(device=dev).manual_seed(99)
+        M4, L4, N4, n4 = cfg4.M, cfg4.L, cfg4.N, cfg4.n
+        ant = torch.randint(0, M4, (fs, L4), device=dev, generator=g4)
+        k4 = torch.randint(0, cfg4.K, (fs, L4), device=dev, generator=g4)
+        sym4 = torch.as_tensor(np.asarray(cfg4.symbols)).to(dev, torch.complex64)
+        gray4 = torch.as_tensor(np.asarray(cfg4.gray)).to(dev, torch.int64)
+        pos4 = ant + torch.arange(L4, device=dev) * M4
+        x4 = torch.zeros(fs, N4, dtype=torch.complex64, device=dev)
+        x4.scatter_(1, pos4, sym4[k4])
+        snr4 = 10 ** ((args.scamp_ebn0_db + 10 * np.log10(cfg4.code_rate)) / 10)
+        s24 = (cfg4.Na / cfg4.Nr) / snr4
+        y4 = x4 @ A4.T + torch.view_as_complex(torch.randn(fs, n4, 2, device=dev, generator=g4) * float(np.sqrt(s24 / 2)))
+        lab4 = gray4[k4].reshape(-1).contiguous()
+        idx4 = (pos4 + torch.arange(fs, device=dev)[:, None] * N4).reshape(-1).contiguous()
+        # TF32 tensor peak: cuBLAS TF32 GEMM 8192^3 (library call used as the probe only), best of 5
+        a32 = torch.randn(8192, 8192, device=dev)
+        b32 = torch.randn(8192, 8192, device=dev)
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        best = 0.0
+        for rep in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a32 @ b32
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        del a32, b32
+        nnz = int((A4 != 0).sum())
+        sout = {}
+        for tag, ee in (("exit", True), ("fixed_T", False)):
+            sc = pkg.SCAMP(cfg4, outputs=False, early_exit=ee)
+            for _ in range(2):
+                sc.detect(W4, A4, y4, snr4, x4, lab4, idx4)
+            torch.cuda.synchronize()
+            lib.ampsm_launch_count(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                det = sc.detect(W4, A4, y4, snr4, x4, lab4, idx4)
+            e1.record()
+            torch.cuda.synchronize()
+            sout[tag] = (det.counters_dict(), e0.elapsed_time(e1) / 3, int(lib.ampsm_launch_count(0)) // 3)
+        (cs, mss, ls), (cf4, msf4, _) = sout["exit"], sout["fixed_T"]
+        flop_nz = 16 * nnz + 18 * N4 * cfg4.K                # per frame-iteration: two complex mat-vecs over the non-zero entries + denoiser
+        tf_alg = cf4["iters"] * flop_nz / (msf4 * 1e-3) / 1e12
+        tf_mma = cf4["iters"] * 3 * 16 * nnz / (msf4 * 1e-3) / 1e12     # 3xTF32: three tensor-core products per algorithmic one
+        out["scamp_c4"] = {
+            "metric": "SCAMP frame-iterations/s", "value": cs["iters"] / (mss * 1e-3), "unit": "frame-iter/s", "frames": fs,
+            "ms_per_call": mss, "mean_iterations_per_frame": cs["iters"] / fs, "fer": cs["frame_err"] / fs,
+            "ver": cs["slot_err"] / (fs * cfg4.Lin), "nan_frames": cs["nan_frames"], "gpu_launches_per_call": ls,
+            "config": {"workload": f"SCAMP Config(512, 8, 32, 32, 3, 'tail', QPSK): L=256 sections x M=64, A {n4} x {N4} shared by "
+                                   f"{fs} frames ({nnz / A4.numel():.3f} non-zero), iterations={ITERS}, early exit, Eb/N0 "
+                                   f"{args.scamp_ebn0_db} dB; one GPU (rank 0)"},
+            "fixed_T": {"value": cf4["iters"] / (msf4 * 1e-3), "unit": "frame-iter/s", "ms_per_call": msf4},
+            "roofline_tensor": {"bound": "tensor", "achieved": tf_mma, "peak": best, "unit": "TFLOP/s (TF32)", "frac": tf_mma / best if best else None,
+                                "algorithmic_tflops": tf_alg, "algorithmic_flop_per_frame_iter": flop_nz,
+                                "what": "fixed-T run; achieved = 3 x 16 x nnz(A) tensor-core flop per frame-iteration (3xTF32 split of the two "
+                                        "complex mat-vecs over the non-zero blocks) / time; peak = cuBLAS TF32 GEMM 8192^3 measured in this process"}}
+        del W4, A4, x4, y4
+    # ---- BASELINE config 3 in complex128 (the reference fed with upcast factors, vamp.py:12-28,119): FP64 pipe
+    if args.c128_frames > 0 and rank == 0:
+        f5 = args.c128_frames
+        cfg5 = pkg.Config(128, 4, 64, 1, 1, batch=f5, generator_mode='sparc', iterations=ITERS, alphabet='QPSK',
+                          channel_profile='uniform', device=str(dev))
+        snr5 = 10 ** (args.c3_snr_db / 10)
+        from amp_sparc_spatialmodulation_b200.simulate import device_frames
+        H5, y5, x5, l5, i5 = device_frames(cfg5, f5, snr5, torch.Generator(device=dev).manual_seed(555))
+        U5, s5, V5 = torch.linalg.svd(H5.to(torch.complex128), full_matrices=False)
+        U5, s5, V5, y5d = U5.contiguous(), s5.contiguous(), V5.contiguous(), y5.to(torch.complex128)
+        v5 = pkg.VAMP(cfg5, outputs=False)
+        for _ in range(2):
+            v5.detect(U5, s5, V5, y5d, snr5, x5, l5, i5)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            det = v5.detect(U5, s5, V5, y5d, snr5, x5, l5, i5)
+        e1.record()
+        torch.cuda.synchronize()
+        c5d, ms5 = det.counters_dict(), e0.elapsed_time(e1) / 3
+        flop3 = 16 * 64 * 128 + 18 * 128 * 4 + 40 * 128 + 10 * 64
+        t64 = ctypes.c_double(0.0)
+        if hasattr(lib, "ampsm_probe_fp64_tflops"):
+            lib.ampsm_probe_fp64_tflops(local, ctypes.byref(t64))
+        ach5 = c5d["iters"] * flop3 / (ms5 * 1e-3) / 1e12
+        out["vamp_c3_c128"] = {
+            "metric": "VAMP frame-iterations/s", "value": c5d["iters"] / (ms5 * 1e-3), "unit": "frame-iter/s", "frames": f5,
+            "mean_iterations_per_frame": c5d["iters"] / f5, "nan_frames": c5d["nan_frames"],
+            "config": {"workload": f"VAMP Nt=128 Nr=64 Na=4 QPSK, complex128 factors (float64 linear stage, denoiser outputs rounded to "
+                                   f"complex64/float32 as vamp.py:119), SNR {args.c3_snr_db} dB; one GPU (rank 0)"},
+            "roofline_fp64": {"bound": "fp64", "achieved": ach5, "peak": t64.value or None, "unit": "TFLOP/s",
+                              "frac": (ach5 / t64.value) if t64.value else None, "algorithmic_flop_per_frame_iter": flop3,
+                              "peak_source": "DFMA probe kernel run in this process (ampsm_probe_fp64_tflops)"}}
+        del U5, s5, V5, H5
     if cpu_base:
         out["cpu_baseline"] = cpu_base
+        out["cpu_port"] = cpu_port
     if rank == 0:
         emit(json.dumps(out))
     if world > 1:

@@ -237,6 +237,7 @@ int ampsm_shrink(int kind, const ampsm_alphabet* a, double P0, double Ps, int64_
  */
 int ampsm_probe_fp32_tflops(int device, double* tflops);
 int ampsm_probe_fp32x2_tflops(int device, double* tflops);   /* same, issued as packed FFMA2 */
+int ampsm_probe_fp64_tflops(int device, double* tflops);     /* DFMA: the denominator of the complex128 kernels */
 int64_t ampsm_launch_count(int reset);
 
 #ifdef __cplusplus

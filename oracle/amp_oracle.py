@@ -167,10 +167,13 @@ def bamp_detect(H, y, sigma2, symbols, L, M, max_iters, early_exit=True, shift='
     return dict(xmap=xmap, xmmse=xmmse, var=var, cov=cov, iters=iters, traj=traj)
 
 
-def scamp_detect(W, A, y, sigma2, symbols, cfg, max_iters, early_exit=True, shift='reference', x_true=None):
+def scamp_detect(W, A, y, sigma2, symbols, cfg, max_iters, early_exit=True, shift='reference', x_true=None, psi_order='pairwise'):
     """SCAMP over F frames with a shared design matrix.  W: (Lr,Lc) float32; A: (n,N) complex64; y: (F,n).
 
-    ``cfg`` supplies Na, Nt (=Mc), Nr (=Mr), Lin (=Lc), Lout (=Lr).
+    ``cfg`` supplies Na, Nt (=Mc), Nr (=Mr), Lin (=Lc), Lout (=Lr).  ``psi_order='reversed'`` sums ``|x|^2`` of a block
+    in the opposite order (float32): psi = 1 - sum/Na is a difference of numbers near 1 and the exit test (scamp.py:105)
+    compares it at 1e-8 + 1e-5 psi, so the exit iteration depends on the summation order -- the tests use the two orders to
+    measure how far the reference is from itself there.
     """
     Na, Mc, Mr, Lc, Lr = cfg['Na'], cfg['Nt'], cfg['Nr'], cfg['Lin'], cfg['Lout']
     M, L = Mc // Na, Na * Lc
@@ -204,7 +207,10 @@ def scamp_detect(W, A, y, sigma2, symbols, cfg, max_iters, early_exit=True, shif
             phi_use = np.repeat(phi_new, Mr, axis=1)
             xmap_a = (xmmse[a] + tau_use * ((z_new / phi_use).astype(C64) @ Ah.T)).astype(C64)   # scamp.py:56
             xm = sm_denoiser(xmap_a, tau_use, symbols, L, M, True, shift, want_var=False)   # scamp.py:57
-            p = (np.abs(xm) ** 2).astype(F32).reshape(-1, Lc, Mc).sum(axis=-1, dtype=F32)
+            e2 = (np.abs(xm) ** 2).astype(F32).reshape(-1, Lc, Mc)
+            if psi_order == 'reversed':
+                e2 = np.ascontiguousarray(e2[..., ::-1])
+            p = e2.sum(axis=-1, dtype=F32)
             psi_new = (F32(1) - p / F32(Na)).astype(F32)               # scamp.py:59
         done = _allclose_rows(psi_new, psi[a])
         z[a], phi[a], xmap[a], xmmse[a], psi[a] = z_new, phi_new, xmap_a, xm, psi_new

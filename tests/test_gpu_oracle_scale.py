@@ -1,0 +1,370 @@
+"""Parity AT SCALE against the oracle (10 k-frame parity subsets per SNR point).
+
+The headline kernels (register-resident BAMP / VAMP, tcgen05 SCAMP) and the numpy oracle (oracle/amp_oracle.py, pinned to
+the reference's own outputs by tests/test_oracle_golden.py) detect the SAME seeded frames.  The oracle additionally
+detects the frames a second time with the observation moved by ONE float32 ulp (y * (1 + 2^-23)): a frame whose oracle
+result changes under that perturbation (another decision, another exit iteration, or estimates that move by more than 1e-3
+of the frame's largest |xmap|) is *rounding-determined* -- the reference itself does not pin it down, two BLAS builds of the
+reference would disagree on it.  Acceptance, per SNR point:
+
+  1. per-frame hard decisions (loss.py:282-302) of kernel and oracle are compared; every frame that decides differently is
+     LISTED (frame, iterations of both paths, both decisions, relative gap between the two candidates' decision metrics
+     evaluated on the oracle's xmap, largest |xmap_gpu - xmap_oracle|) and classified:
+       near-tie  : gap < NEAR_TIE (2e-4 = twice the complex64 trajectory tolerance BASELINE.json's north_star states; the
+                   sub-list with gap < 1e-6 is counted separately);
+       sensitive : the estimates differ by more than 1e-3 AND the oracle certifies the frame as rounding-determined (the
+                   one-ulp run above, an 8-ulp random-sign run, or one of four further 8-ulp draws for the listed frames);
+     anything else FAILS the test.  The number of listed frames is bounded by twice the number of frames on which the oracle
+     disagrees with its own run on y moved by 8 ulps with random signs (1e-6 relative: the size of float32 summation-order
+     effects in this path's dot products), plus a stated share of the frames.
+  2. the listed frames are REMOVED, the kept frames are run through the kernel AGAIN (one call, so the in-kernel counters
+     see exactly the kept set) and EVERY integer counter of that call must equal the oracle's Loss counters
+     (oracle/loss_oracle.py on the oracle's estimates) on the same kept set: identical, no slack.
+  3. exit iterations on the kept frames agree with the oracle's at least as often as the oracle's own perturbed run does
+     (minus 3 points), and for >= 98 % of the frames wherever the oracle agrees with itself that often (bamp.py:140 tests
+     at float32 resolution; SCAMP's psi = 1 - (~1) sits ON that resolution, scamp.py:59,105).
+  4. soft estimates: on kept frames that are not rounding-determined, max|xmmse_gpu - xmmse_oracle| has a median below 1e-5
+     and a 99 % quantile below 1e-3 (the 99.9 % quantile and the maximum are printed).
+"""
+import numpy as np
+import pytest
+import torch
+
+import amp_sparc_spatialmodulation_b200 as pkg
+from oracle import amp_oracle as ao
+from oracle import loss_oracle as lo
+from parity_utils import INT_KEYS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NEAR_TIE = 2e-4
+
+
+def draw_frames(cfg, frames, snr_db, seed, shared_matrix=False):
+    """Seeded frames on the host (numpy): i.i.d. CN(0, 1/Nr) channel (channel.py:53-55 with Lh = Lin = 1), one active
+    antenna per section with a uniform symbol (data.py:74-91), AWGN of variance Na/Nr/SNR (channel.py:113-115)."""
+    rng = np.random.default_rng(seed)
+    n, N, M, L = cfg.n, cfg.N, cfg.M, cfg.L
+    shape = (n, N) if shared_matrix else (frames, n, N)
+    H = ((rng.standard_normal(shape, dtype=np.float32) + 1j * rng.standard_normal(shape, dtype=np.float32))
+         * np.float32(np.sqrt(1 / cfg.Nr / 2))).astype(np.complex64)
+    ant = rng.integers(0, M, (frames, L))
+    k = rng.integers(0, cfg.K, (frames, L))
+    pos = ant + np.arange(L) * M
+    x = np.zeros((frames, N), np.complex64)
+    np.put_along_axis(x, pos, np.asarray(cfg.symbols)[k].astype(np.complex64), axis=1)
+    sigma2 = (cfg.Na / cfg.Nr) / 10 ** (snr_db / 10)
+    noise = ((rng.standard_normal((frames, n), dtype=np.float32) + 1j * rng.standard_normal((frames, n), dtype=np.float32))
+             * np.float32(np.sqrt(sigma2 / 2))).astype(np.complex64)
+    y = ((x @ H.T) if shared_matrix else np.matmul(H, x[..., None])[..., 0]).astype(np.complex64) + noise
+    lab = np.asarray(cfg.gray)[k].reshape(-1).astype(np.int64)
+    return H, y.astype(np.complex64), x, lab, pos.astype(np.int64), np.float32(sigma2)
+
+
+def compare_decisions(cfg, xmap_gpu, xmap_ref, it_gpu, it_ref):
+    """Frames deciding differently, with the near-tie gap measured on the oracle's estimate."""
+    M, K = cfg.M, cfg.K
+    F = xmap_ref.shape[0]
+    sym = np.asarray(cfg.symbols, dtype=np.complex128)
+    _, ant_g, k_g = lo.map_decision(np.asarray(xmap_gpu).astype(np.complex64), cfg.symbols, cfg.gray, M)
+    _, ant_r, k_r = lo.map_decision(np.asarray(xmap_ref).astype(np.complex64), cfg.symbols, cfg.gray, M)
+    ant_g, k_g, ant_r, k_r = (v.reshape(F, -1) for v in (ant_g, k_g, ant_r, k_r))
+    # the 16-QAM table holds -1+3j twice (config.py:112): the decision VALUE is what loss.py:133,150 compare, the LABEL
+    # (first maximum) what loss.py:166,172 compare -- both must agree, so compare (antenna, k) itself
+    bad = np.nonzero(((ant_g != ant_r) | (k_g != k_r)).any(axis=1))[0]
+    rows = []
+    xr = np.asarray(xmap_ref).astype(np.complex64).reshape(F, -1, M)
+    for f in bad:
+        sec = int(np.nonzero((ant_g[f] != ant_r[f]) | (k_g[f] != k_r[f]))[0][0])
+        m_ref = (xr[f, sec, ant_r[f, sec]].astype(np.complex128) * np.conj(sym[k_r[f, sec]])).real
+        m_gpu = (xr[f, sec, ant_g[f, sec]].astype(np.complex128) * np.conj(sym[k_g[f, sec]])).real
+        gap = abs(m_ref - m_gpu) / max(abs(m_ref), 1e-300)
+        dx = float(np.abs(np.asarray(xmap_gpu[f]) - np.asarray(xmap_ref[f])).max() / max(np.abs(xmap_ref[f]).max(), 1e-30))
+        rows.append(dict(frame=int(f), section=sec, it_gpu=int(it_gpu[f]), it_ref=int(it_ref[f]),
+                         gpu=(int(ant_g[f, sec]), int(k_g[f, sec])), ref=(int(ant_r[f, sec]), int(k_r[f, sec])), gap=float(gap), dx=dx))
+    return rows
+
+
+def sensitivity(cfg, ref, pert):
+    """Per-frame flag: the oracle's own result moves when its input moves by one float32 ulp."""
+    F = ref["xmap"].shape[0]
+    M = cfg.M
+    _, a0, k0 = lo.map_decision(np.asarray(ref["xmap"]).astype(np.complex64), cfg.symbols, cfg.gray, M)
+    _, a1, k1 = lo.map_decision(np.asarray(pert["xmap"]).astype(np.complex64), cfg.symbols, cfg.gray, M)
+    dec = ((a0 != a1) | (k0 != k1)).reshape(F, -1).any(axis=1)
+    with np.errstate(invalid='ignore'):
+        scale = np.maximum(np.abs(ref["xmap"]).max(axis=1), 1e-30)
+        dx = np.abs(pert["xmap"] - ref["xmap"]).max(axis=1) / scale
+    moved = ~(dx <= 1e-3)                                 # NaN counts as moved
+    its = pert["iters"] != ref["iters"]
+    return dec | moved | its, dec, its
+
+
+def classify(rows, sens, resens):
+    """resens(frames) -> bool array: further perturbations for listed frames the first one did not flag."""
+    near, sensitive, pending = [], [], []
+    for r in rows:
+        if r["gap"] < NEAR_TIE:
+            near.append(r)
+        elif r["dx"] > 1e-3 and sens[r["frame"]]:
+            sensitive.append(r)
+        else:
+            pending.append(r)
+    other = []
+    if pending:
+        flags = resens(np.array([r["frame"] for r in pending], dtype=np.int64))
+        for r, fl in zip(pending, flags):
+            (sensitive if (fl and r["dx"] > 1e-3) else other).append(r)
+    return near, sensitive, other
+
+
+def show(title, rows, limit=40):
+    print(f"  {title}: {len(rows)}")
+    for r in rows[:limit]:
+        print(f"    frame {r['frame']:6d} sec {r['section']:2d} iters gpu/oracle {r['it_gpu']:2d}/{r['it_ref']:2d} "
+              f"decision gpu {r['gpu']} oracle {r['ref']} gap {r['gap']:.2e} max|dxmap| {r['dx']:.2e}")
+    if len(rows) > limit:
+        print(f"    ... {len(rows) - limit} more")
+
+
+def oracle_counters(cfg, ref, x, lab, pos, keep):
+    """The oracle's Loss counters on the kept frames, numbered 0..len(keep)-1 like the kernel's second call."""
+    Fk = len(keep)
+    idx = (pos[keep] + (np.arange(Fk) * cfg.N)[:, None]).reshape(-1)
+    L = pos.shape[1]
+    labk = lab.reshape(-1, L)[keep].reshape(-1)
+    return lo.error_counters(ref["xmap"][keep].astype(np.complex64), ref["xmmse"][keep], x[keep], labk, idx, cfg.symbols, cfg.gray,
+                             dict(Nt=cfg.Nt, Na=cfg.Na, Lin=cfg.Lin), iters=ref["iters"][keep]), idx, labk
+
+
+def jitter(y, ulps, seed):
+    """y with every real and imaginary part moved by +-`ulps` float32 ulps (relative), signs drawn at random."""
+    rng = np.random.default_rng(seed)
+    e = np.float32(ulps * 2.0 ** -23)
+    fr = (1 + e * rng.choice(np.float32([-1, 1]), y.shape)).astype(np.float32)
+    fi = (1 + e * rng.choice(np.float32([-1, 1]), y.shape)).astype(np.float32)
+    return (y.real * fr + 1j * (y.imag * fi)).astype(np.complex64)
+
+
+def finish(name, cfg, gpu, ref, run_oracle, y, rerun_kept, x, lab, pos, extra_share, alt=None, exit_floor=None):
+    """gpu: dict(xmap, xmmse, iters) of the kernel's first call; run_oracle(y, frames=None) -> oracle result for (a subset of)
+    the frames with observation y; rerun_kept(keep, idx, lab) -> counters of the kernel on the kept frames; alt: the oracle's
+    result with another float32 summation order where the exit test depends on one (SCAMP's psi)."""
+    F = x.shape[0]
+    pert = run_oracle((y * np.float32(1.0 + 2.0 ** -23)).astype(np.complex64))       # one ulp, all entries alike
+    sens1, dec_self, its_self = sensitivity(cfg, ref, pert)
+    # 8 ulps with random signs = 1e-6 relative: the size of float32 summation-order effects in this path's dot products
+    # (64..512 complex terms: sqrt(2 N) 2^-24 = 0.7..2e-6) -- what two BLAS builds of the reference differ by
+    pert8 = run_oracle(jitter(y, 8, 99))
+    sens8, dec_self8, its_self8 = sensitivity(cfg, ref, pert8)
+    sens = sens1 | sens8
+    if alt is not None:
+        sens_a, dec_a, its_a = sensitivity(cfg, ref, alt)
+        sens = sens | sens_a
+    rows = compare_decisions(cfg, gpu["xmap"], ref["xmap"], gpu["iters"], ref["iters"])
+
+    level = {}
+
+    def resens(frames):
+        """Escalating random-sign jitter for listed frames the two full runs did not flag: 8, 32, 128 ulps (1e-6, 4e-6, 1.5e-5
+        relative -- the last still seven times below the complex64 tolerance of 1e-4 the north star states)."""
+        flags = np.zeros(len(frames), bool)
+        sub = {k: ref[k][frames] for k in ("xmap", "iters")}
+        for ulps in (8, 32, 128):
+            for seed in (1, 2, 3):
+                todo = np.nonzero(~flags)[0]
+                if todo.size == 0:
+                    break
+                p = run_oracle(jitter(y[frames[todo]], ulps, seed), frames[todo])
+                hit = sensitivity(cfg, {k: v[todo] for k, v in sub.items()}, p)[0]
+                for j in todo[hit]:
+                    level[int(frames[j])] = ulps
+                flags[todo[hit]] = True
+        return flags
+    near, sensitive, other = classify(rows, sens, resens)
+    print(f"\n[{name}] {F} frames: {len(rows)} frames decide differently from the oracle.  The oracle against itself: one ulp on y -> "
+          f"{int(dec_self.sum())} other decisions, {int(its_self.sum())} other exit iterations; 8 ulps (1e-6) -> {int(dec_self8.sum())} / "
+          f"{int(its_self8.sum())}; rounding-determined frames {int(sens.sum())}"
+          + (f"; other summation order -> {int(dec_a.sum())} / {int(its_a.sum())}" if alt is not None else ""))
+    show("near-ties (gap < %.0e)" % NEAR_TIE, near)
+    print(f"    of which gap < 1e-6: {sum(r['gap'] < 1e-6 for r in near)}")
+    show("sensitive (estimates differ by > 1e-3; certified rounding-determined by the oracle)", sensitive)
+    if level:
+        print("    certified only by the escalated jitter (frame: ulps): " + ", ".join(f"{f}: {u}" for f, u in sorted(level.items())))
+    show("UNEXPLAINED", other)
+    assert not other, f"{name}: {len(other)} decision differences are neither near-ties nor rounding-determined frames"
+    bound = 2 * int(dec_self8.sum()) + max(3, extra_share * F)
+    assert len(rows) <= bound, f"{name}: {len(rows)} listed frames exceed 2 x {int(dec_self8.sum())} + {max(3, extra_share * F):.0f}"
+    drop = np.array(sorted({r["frame"] for r in rows}), dtype=np.int64)
+    keep = np.setdiff1d(np.arange(F), drop)
+    want, idx_k, lab_k = oracle_counters(cfg, ref, x, lab, pos, keep)
+    have = rerun_kept(keep, idx_k, lab_k)
+    diff = {k: (have[k], want[k]) for k in INT_KEYS if int(have[k]) != int(want[k])}
+    print(f"  kept {len(keep)} frames: counters gpu == oracle: {not diff}   "
+          + ", ".join(f"{k}={have[k]}" for k in ("frame_err", "index_err", "symbol_err", "index_bit_err", "symbol_bit_err")))
+    assert not diff, f"{name}: counters differ on the kept frames: {diff}"
+    ig, ir = gpu["iters"][keep], ref["iters"][keep]
+    eq, near1 = float((ig == ir).mean()), float((np.abs(ig - ir) <= 1).mean())
+    eq_self = near1_self = 1.0
+    for other_run in (pert8, alt):
+        if other_run is not None:
+            ip = other_run["iters"][keep]
+            eq_self, near1_self = min(eq_self, float((ip == ir).mean())), min(near1_self, float((np.abs(ip - ir) <= 1).mean()))
+    print(f"  exit iterations equal {eq:.4f} (oracle vs its own perturbed runs: {eq_self:.4f}), within +-1 {near1:.4f} ({near1_self:.4f}); "
+          f"mean T gpu {ig.mean():.3f} oracle {ir.mean():.3f}")
+    if exit_floor is None:
+        assert eq >= min(0.98, eq_self - 0.03) and near1 >= min(0.995, near1_self - 0.03), (eq, eq_self, near1, near1_self)
+    else:
+        assert eq >= exit_floor[0] and near1 >= exit_floor[1], (eq, near1, exit_floor)
+    assert abs(ig.mean() - ir.mean()) <= 0.01 * ir.mean() + 0.02
+    calm = keep[~sens[keep]]
+    d = np.abs(gpu["xmmse"][calm] - ref["xmmse"][calm]).max(axis=1)
+    print(f"  soft estimates on {len(calm)} calm kept frames: max|xmmse - oracle| median {np.median(d):.2e}, 99 % {np.quantile(d, 0.99):.2e}, "
+          f"99.9 % {np.quantile(d, 0.999):.2e}, max {d.max():.2e}")
+    assert np.median(d) < 1e-5 and np.quantile(d, 0.99) < 1e-3
+    return len(near), len(sensitive)
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+def gpu_result(det, F, N):
+    return dict(xmap=det.xmap.cpu().numpy().reshape(F, N), xmmse=det.xmmse.cpu().numpy().reshape(F, N), iters=det.iters.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------- BAMP
+def run_bamp_point(cfg_args, alphabet, F, snr_db, seed, kernel, extra_share):
+    Nt, Na, Nr = cfg_args
+    cfg = pkg.Config(Nt, Na, Nr, 1, 1, batch=F, generator_mode='sparc', iterations=20, alphabet=alphabet,
+                     channel_profile='uniform', device=DEV)
+    H, y, x, lab, pos, sigma2 = draw_frames(cfg, F, snr_db, seed)
+    snr = 10 ** (snr_db / 10)
+
+    def run_oracle(yy, frames=None):
+        return ao.bamp_detect(H if frames is None else H[frames], yy, sigma2, cfg.symbols, cfg.L, cfg.M, cfg.N_Layers, shift='section')
+    ref = run_oracle(y)
+    dH, dy, dx = t(H), t(y), t(x)
+    idx = (pos + (np.arange(F) * cfg.N)[:, None]).reshape(-1)
+    det = pkg.BAMP(cfg, kernel=kernel, outputs=True).detect(dH, dy, snr, dx, lab, idx)
+
+    def rerun(keep, idx_k, lab_k):
+        ck = pkg.Config(Nt, Na, Nr, 1, 1, batch=len(keep), generator_mode='sparc', iterations=20, alphabet=alphabet,
+                        channel_profile='uniform', device=DEV)
+        kk = torch.as_tensor(keep, device=DEV)
+        return pkg.BAMP(ck, kernel=kernel, outputs=False).detect(dH[kk], dy[kk], snr, dx[kk], lab_k, idx_k).counters_dict()
+    return finish(f"BAMP {Nt}x{Nr} {alphabet} {kernel} @ {snr_db} dB", cfg, gpu_result(det, F, cfg.N), ref, run_oracle, y, rerun,
+                  x, lab, pos, extra_share)
+
+
+@pytest.mark.parametrize("snr_db", [5.0, 10.0, 15.0, 20.0])
+def test_bamp_c2_fast_kernel_counts_equal_oracle_10k(snr_db):
+    """BASELINE config 2 (BAMP 64 x 32, 16-QAM, Na = 1) through the register-resident one-warp kernel, 10 k frames per point.
+    Listed frames <= 2 x (frames the oracle decides differently under a one-ulp perturbation) + 1e-3 of the frames."""
+    run_bamp_point((64, 1, 32), '16QAM', 10000, snr_db, seed=1000 + int(snr_db), kernel='fast', extra_share=1e-3)
+
+
+def test_bamp_c1_counts_equal_oracle_10k_sweep():
+    """BASELINE config 1 (BAMP 8 x 4, QPSK, Na = 1): 10 k frames at each of 0, 2, ..., 20 dB through the library's default
+    kernel for that shape (the one-warp kernel's 8 x 4 instantiation)."""
+    total_near = total_sens = 0
+    for snr_db in range(0, 22, 2):
+        a, b = run_bamp_point((8, 1, 4), 'QPSK', 10000, float(snr_db), seed=2000 + snr_db, kernel='auto', extra_share=1e-3)
+        total_near += a
+        total_sens += b
+    print(f"\n[BAMP C1 sweep] near-tie flips {total_near}, rounding-determined {total_sens} of 110000 frames")
+
+
+# ------------------------------------------------------------------------------------------------------------- VAMP
+def cpu_svd(H):
+    """The reference caller's factorisation (vamp_model.py:58): torch.linalg.svd(A, full_matrices=False) on the CPU."""
+    U, s, Vh = torch.linalg.svd(torch.as_tensor(H), full_matrices=False)
+    return U.contiguous().numpy(), s.contiguous().numpy(), Vh.contiguous().numpy()
+
+
+def run_vamp_point(cfg_args, alphabet, F, snr_db, seed, extra_share):
+    Nt, Na, Nr = cfg_args
+    cfg = pkg.Config(Nt, Na, Nr, 1, 1, batch=F, generator_mode='sparc', iterations=20, alphabet=alphabet,
+                     channel_profile='uniform', device=DEV)
+    H, y, x, lab, pos, sigma2 = draw_frames(cfg, F, snr_db, seed)
+    U, s, Vh = cpu_svd(H)
+    snr = 10 ** (snr_db / 10)
+
+    def run_oracle(yy, frames=None):
+        sl = slice(None) if frames is None else frames
+        return ao.vamp_detect(U[sl], s[sl], Vh[sl], yy, float(sigma2), cfg.Na / cfg.Nt, cfg.symbols, cfg.L, cfg.M, cfg.N_Layers,
+                              shift='section')
+    ref = run_oracle(y)
+    dU, ds, dV, dy, dx = t(U), t(s), t(Vh), t(y), t(x)
+    idx = (pos + (np.arange(F) * cfg.N)[:, None]).reshape(-1)
+    det = pkg.VAMP(cfg, kernel='fast', outputs=True).detect(dU, ds, dV, dy, snr, dx, lab, idx)
+
+    def rerun(keep, idx_k, lab_k):
+        ck = pkg.Config(Nt, Na, Nr, 1, 1, batch=len(keep), generator_mode='sparc', iterations=20, alphabet=alphabet,
+                        channel_profile='uniform', device=DEV)
+        kk = torch.as_tensor(keep, device=DEV)
+        return pkg.VAMP(ck, kernel='fast', outputs=False).detect(dU[kk], ds[kk], dV[kk], dy[kk], snr, dx[kk], lab_k,
+                                                                 idx_k).counters_dict()
+    return finish(f"VAMP {Nt}x{Nr} {alphabet} Na={Na} @ {snr_db} dB", cfg, gpu_result(det, F, cfg.N), ref, run_oracle, y, rerun,
+                  x, lab, pos, extra_share)
+
+
+@pytest.mark.parametrize("snr_db", [5.0, 10.0, 15.0, 20.0])
+def test_vamp_c2_fast_kernel_counts_equal_oracle_10k(snr_db):
+    """VAMP on the 64 x 32 16-QAM frames (factors from the CPU LAPACK SVD like the reference's caller) through the
+    register-resident one-warp kernel.  VAMP divides by 1 - dxdr with dxdr clipped at 1 - 1e-5 (vamp.py:86-91): rounding is
+    amplified by up to 1e5 in one step, so a share of the frames is rounding-determined in the reference itself (the oracle
+    decides 0.2-2.5 % of these frames differently when y moves by 1e-6) -- the oracle's own perturbed runs measure that share
+    and the listed frames are bounded against it."""
+    run_vamp_point((64, 1, 32), '16QAM', 10000, snr_db, seed=3000 + int(snr_db), extra_share=5e-3)
+
+
+@pytest.mark.parametrize("snr_db", [0.0, 4.0])
+def test_vamp_c3_quad_kernel_counts_equal_oracle(snr_db):
+    """BASELINE config 3 (VAMP 128 x 64, Na = 4, QPSK) through the four-warps-per-frame kernel, 2 k frames per point."""
+    run_vamp_point((128, 4, 64), 'QPSK', 2000, snr_db, seed=3100 + int(snr_db), extra_share=3e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------- SCAMP
+@pytest.mark.parametrize("exp", ["f64", "f32"])
+@pytest.mark.parametrize("shape,F,ebn0_db", [((64, 2, 8, 8, 3), 256, 5.0), ((128, 8, 32, 16, 3), 256, 6.0), ((64, 2, 8, 8, 3), 200, 8.0)])
+def test_scamp_tensor_core_path_matches_oracle(shape, F, ebn0_db, exp):
+    """The tcgen05 SCAMP path (batches >= 128 frames; scamp.py:43-59, 77-108) against ``ao.scamp_detect`` on the reference's
+    own coupled design matrix (channel.py:76-96) -- a C4-lite instance (Nt = 128, Na = 8, Nr = 32, Lin = 16, Lh = 3, tail:
+    A 576 x 2048) included; ragged frame count in the third case.  SCAMP's exit test compares psi = 1 - sum|x|^2/Na, a
+    difference of two numbers near 1, at 1e-8 + 1e-5 psi: it sits on float32 resolution, so exit iterations are compared
+    against the oracle's own perturbed runs (see the module docstring) with ``exp='f64'`` (the denoiser evaluated in float64 like
+    the reference's, scamp.py:61-68).  The default ``exp='f32'`` denoiser differs from the float64 one in the last bit of the
+    estimates, which moves the exit by one iteration for ~10 % of the frames and changes no decision: there the floor is
+    80 % equal, 99 % within one iteration, the mean within 1 %."""
+    Nt, Na, Nr, Lin, Lh = shape
+    cfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet='QPSK',
+                     channel_profile='uniform', channel_truncation='tail', device='cpu')
+    np.random.seed(5)
+    torch.manual_seed(5)
+    ch, da = pkg.Channel(cfg), pkg.Data(cfg)
+    W, A = ch.generate_as_sparc()
+    x, lab, idx = da.generate_message()
+    snr = 10 ** ((ebn0_db + 10 * np.log10(cfg.code_rate)) / 10)
+    y = A @ x + ch.awgn(snr)
+    sigma2 = np.float32((cfg.Na / cfg.Nr) / snr)
+    dims = dict(Na=Na, Nt=Nt, Nr=Nr, Lin=cfg.Lin, Lout=cfg.Lout)
+    yn = y.numpy()[..., 0]
+
+    def run_oracle(yy, frames=None, psi_order='pairwise'):
+        return ao.scamp_detect(W.numpy(), A.numpy(), yy, sigma2, cfg.symbols, dims, cfg.N_Layers, shift='section', psi_order=psi_order)
+    ref = run_oracle(yn)
+    alt = run_oracle(yn, psi_order='reversed')            # psi = 1 - sum|x|^2/Na summed in the opposite order (scamp.py:59)
+    gcfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet='QPSK',
+                      channel_profile='uniform', channel_truncation='tail', device=DEV)
+    det = pkg.SCAMP(gcfg, outputs=True, exp=exp).detect(W, A, y, snr, x, lab, idx)
+    xn = x.numpy()[..., 0]
+    pos = (np.asarray(idx).reshape(F, -1) - (np.arange(F) * cfg.N)[:, None]).astype(np.int64)
+
+    def rerun(keep, idx_k, lab_k):
+        ck = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=len(keep), generator_mode='sparc', iterations=20, alphabet='QPSK',
+                        channel_profile='uniform', channel_truncation='tail', device=DEV)
+        kk = torch.as_tensor(keep)
+        return pkg.SCAMP(ck, outputs=False, exp=exp).detect(W, A, y[kk], snr, x[kk], lab_k, idx_k).counters_dict()
+    finish(f"SCAMP tc {shape} F={F} exp={exp} @ Eb/N0 {ebn0_db} dB", cfg, gpu_result(det, F, cfg.N), ref, run_oracle, yn, rerun, xn,
+           np.asarray(lab), pos, extra_share=1e-2, alt=alt, exit_floor=(0.80, 0.99) if exp == 'f32' else None)
