@@ -20,7 +20,7 @@ SQERR_NAMES = ['sqerr', 'sqerr_first', 'sqerr_mid', 'sqerr_last']
 # every symbol include/ampsm_b200.h declares (checked by tests/test_host_api.py::test_cabi_library_exports_every_declared_symbol)
 EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp_detect", "ampsm_bamp_detect_taps", "ampsm_bamp_detect_host",
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
-           "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect",
+           "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect", "ampsm_scamp_taps_workspace_bytes", "ampsm_scamp_detect_taps",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops", "ampsm_probe_fp64_tflops",
            "ampsm_launch_count"]
 
@@ -74,6 +74,9 @@ def lib():
     L.ampsm_scamp_detect_host.argtypes = scamp + [i32]
     L.ampsm_scamp_workspace_bytes.argtypes = [PP, i64]
     L.ampsm_scamp_workspace_bytes.restype = i64
+    L.ampsm_scamp_taps_workspace_bytes.argtypes = [PP, i64, i32]
+    L.ampsm_scamp_taps_workspace_bytes.restype = i64
+    L.ampsm_scamp_detect_taps.argtypes = [PP, AP, i64, vp, vp, i32, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_loss_count.argtypes = [PP, AP, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_shrink.argtypes = [i32, AP, dbl, dbl, i64, i32, vp, vp, i64, vp, vp, vp, vp]
     L.ampsm_probe_fp32_tflops.argtypes = [i32, C.POINTER(dbl)]

@@ -455,6 +455,34 @@ int ampsm_scamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t 
     return launch_scamp(k, p->exp_f64 != 0, (cudaStream_t)stream);
 }
 
+int64_t ampsm_scamp_taps_workspace_bytes(const ampsm_problem* p, int64_t frames, int32_t Lh) {
+    Geom g{};
+    DevAlphabet al{};
+    ampsm_alphabet dummy{};
+    dummy.K = 1;
+    if (make_geom(p, &dummy, &g, &al, false)) return -1;
+    return scamp_taps_workspace_bytes(g, frames, Lh);
+}
+
+int ampsm_scamp_detect_taps(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const float* W, const void* taps, int32_t Lh,
+                            const void* y, double sigma2, const float* sigma2_per_frame, const void* x_true,
+                            const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* psi, int32_t* iters,
+                            float* traj, uint64_t* counters, void* workspace, void* stream) {
+    ScampArgs k{};
+    if (p && p->decision == 2) { set_error("SCAMP is defined for sectioned messages only (scamp.py:61-68)"); return AMPSM_EINVAL; }
+    if (int e = make_geom(p, a, &k.g, &k.al, false)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || Lh < 1 || (frames > 0 && (!W || !taps || !y))) { set_error("SCAMP taps: W / taps / y is NULL, Lh < 1 or frames < 0"); return AMPSM_EINVAL; }
+    if (reinterpret_cast<uintptr_t>(taps) % 8) { set_error("SCAMP taps: taps must be 8-byte aligned"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    k.W = W; k.A = nullptr; k.taps = (const float2*)taps; k.Lh = Lh; k.y = (const float2*)y; k.sigma2 = (float)sigma2; k.sigma2_pf = sigma2_per_frame;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.psi = psi; k.iters = iters; k.traj = traj; k.frames = frames;
+    k.workspace = workspace;
+    return launch_scamp(k, p->exp_f64 != 0, (cudaStream_t)stream);
+}
+
 int ampsm_scamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const float* W, const void* A,
                             const void* y, double sigma2, const float* sigma2_per_frame, const void* x_true,
                             const int64_t* sym_true, const int64_t* idx_true, void* xmap, void* xmmse, float* psi,

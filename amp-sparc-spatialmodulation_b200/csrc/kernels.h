@@ -72,7 +72,9 @@ struct ScampArgs {
     Geom g;
     DevAlphabet al;
     const float* W;              // [Lout][Lin]
-    const float2* A;             // [n][N]
+    const float2* A;             // [n][N]  (nullptr when the design matrix is given by its taps)
+    const float2* taps;          // [Lh][Nr][Nt]: block (r, c) of A = taps[r - c] for 0 <= r - c < Lh (channel.py:89-91), or nullptr
+    int Lh;
     const float2* y;             // [frames][n]
     float sigma2;
     const float* sigma2_pf;
@@ -117,6 +119,7 @@ int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64
 int launch_vamp_quad(const VampArgs& a, cudaStream_t stream);       // complex64 64 x 128 factors (four warps per frame), else AMPSM_ENOFIT
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
+long long scamp_taps_workspace_bytes(const Geom& g, long long frames, int Lh);   // AMPSM_ENOFIT when the shape has no structured path
 int launch_loss(const LossArgs& a, cudaStream_t stream);
 int launch_shrink(const ShrinkArgs& a, int kind, cudaStream_t stream);   // kind 0 bayes, 1 shrinkOOK, 2 sw_shrinkOOK
 // batched thin SVD H = U diag(s) Vh of dense [frames][n][N] complex64 matrices, n <= 32 (svd_jacobi.cu); sweeps optional

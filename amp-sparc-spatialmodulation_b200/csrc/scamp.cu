@@ -21,7 +21,9 @@ __host__ __device__ inline size_t up256(size_t v) { return (v + 255) & ~size_t(2
 
 static bool scamp_use_tc(const Geom& g, long long F) { return F >= 128 && !getenv("AMPSM_SCAMP_SIMT") && scamp_tc_fits(g.n, g.N, F); }
 
-static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, ScampWs* ws, unsigned char* base) {
+// Lh > 0: structured path (design matrix given by its Lh taps, scamp_st.cu): Zs padded per frame, pre-split tap planes
+static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, ScampWs* ws, unsigned char* base, int Lh = 0) {
+    const ScampStPlan sp = Lh > 0 ? scamp_st_plan(g, Lh) : ScampStPlan{};
     size_t o = 0;
     auto take = [&](size_t bytes) {
         size_t at = o;
@@ -31,7 +33,7 @@ static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, S
     ScampWs w{};
     w.Xh = (float2*)take((size_t)F * g.N * 8);
     w.Z = (float2*)take((size_t)F * g.n * 8);
-    w.Zs = (float2*)take((size_t)F * g.n * 8);
+    w.Zs = (float2*)take((size_t)F * (Lh > 0 ? sp.zs_stride : g.n) * 8);
     w.Xmap = (float2*)take(own_xmap ? (size_t)F * g.N * 8 : 0);
     w.psi = (float*)take((size_t)F * g.Lin * 4);
     w.phi = (float*)take((size_t)F * g.Lout * 4);
@@ -41,14 +43,20 @@ static size_t ws_layout(const Geom& g, long long F, bool exp64, bool own_xmap, S
     w.iters = (int*)take((size_t)F * 4);
     w.scr = take((size_t)F * g.N * 3 * (exp64 ? 8 : 4));
     w.nzc = (g.N + TILE - 1) / TILE;
-    w.nz = take((size_t)((g.n + TILE - 1) / TILE) * w.nzc);
-    w.At = (float2*)take(scamp_use_tc(g, F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
+    w.nz = take(Lh > 0 ? 0 : (size_t)((g.n + TILE - 1) / TILE) * w.nzc);
+    w.At = (float2*)take(Lh == 0 && scamp_use_tc(g, F) ? (size_t)g.n * g.N * 8 : 0);     // A^T for the tensor-core `estimate` GEMM
+    w.bplanes0 = take(Lh > 0 ? sp.bplane_bytes0 : 0);
+    w.bplanes1 = take(Lh > 0 ? sp.bplane_bytes1 : 0);
     w.notclose = (int*)take((size_t)F * 4);
     if (ws) *ws = w;
     return o;
 }
 
 long long scamp_workspace_bytes(const Geom& g, long long frames) { return (long long)ws_layout(g, frames, true, true, nullptr, nullptr); }
+long long scamp_taps_workspace_bytes(const Geom& g, long long frames, int Lh) {
+    if (!scamp_st_plan(g, Lh).ok) return AMPSM_ENOFIT;
+    return (long long)ws_layout(g, frames, true, true, nullptr, nullptr, Lh);
+}
 
 // ---- zero-tile map of A -------------------------------------------------------------------------------------
 __global__ void scamp_nzmap_kernel(const float2* __restrict__ A, int n, int N, unsigned char* nz, int nzc) {
@@ -372,43 +380,66 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
     const long long F = a.frames;
     if (F <= 0) return 0;
     const bool own_xmap = a.xmap == nullptr;
+    const int Lh = a.taps ? a.Lh : 0;
+    ScampStPlan sp{};
+    if (Lh > 0) {
+        sp = scamp_st_plan(g, Lh);
+        if (!sp.ok) { set_error("SCAMP taps: shape does not fit the structured tensor-core path (Lin <= 128, Lh Nr <= 128, Nr even)"); return AMPSM_ENOFIT; }
+    }
     unsigned char* base = reinterpret_cast<unsigned char*>(a.workspace);
     bool own_ws = false;
     if (!base) {
-        const size_t bytes = ws_layout(g, F, exp64, own_xmap, nullptr, nullptr);
+        const size_t bytes = ws_layout(g, F, exp64, own_xmap, nullptr, nullptr, Lh);
         if (int e = check_cuda(cudaMallocAsync((void**)&base, bytes, stream), "cudaMallocAsync(scamp workspace)")) return e;
         own_ws = true;
     }
     ScampWs w;
-    ws_layout(g, F, exp64, own_xmap, &w, base);
+    ws_layout(g, F, exp64, own_xmap, &w, base, Lh);
     if (!own_xmap) w.Xmap = a.xmap;
     const int tr = (g.n + TILE - 1) / TILE, tc = (g.N + TILE - 1) / TILE;
-    scamp_nzmap_kernel<<<dim3(tc, tr), 128, 0, stream>>>(a.A, g.n, g.N, w.nz, w.nzc);
-    count_launch();
+    if (Lh > 0) {
+        cudaMemsetAsync(w.Zs, 0, (size_t)F * sp.zs_stride * 8, stream);          // the padding blocks of Zs stay zero
+    } else {
+        scamp_nzmap_kernel<<<dim3(tc, tr), 128, 0, stream>>>(a.A, g.n, g.N, w.nz, w.nzc);
+        count_launch();
+    }
     scamp_init_kernel<<<(unsigned)F, 128, 0, stream>>>(w, g, a.y, F);
     count_launch();
     const dim3 grid_res((g.n + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
     const dim3 grid_est((g.N + BN - 1) / BN, (unsigned)((F + BM - 1) / BM));
     // batches of >= 128 frames: both GEMMs on the tensor cores (tcgen05, 3xTF32, scamp_tc.cu); smaller ones on the SIMT tiles
-    const bool use_tc = scamp_use_tc(g, F);
+    const bool use_tc = Lh == 0 && scamp_use_tc(g, F);
     auto fail = [&](int e) {                               // every exit path returns the workspace it allocated
         if (own_ws) cudaFreeAsync(base, stream);
         return e;
     };
     if (use_tc)
         if (int e = scamp_tc_prepare(a.A, w.At, g.n, g.N, stream)) return fail(e);
+    if (Lh > 0)
+        if (int e = scamp_st_prepare(g, sp, Lh, a.taps, w.bplanes0, w.bplanes1, stream)) return fail(e);
+    // float32-exp mode without trajectory: register-resident denoiser (one warp per section) + exit kernel; on the structured
+    // path it is fused into the estimate GEMM's epilogue when the section size allows
+    const bool fast_dn = !exp64 && g.shift_mode == 0 && !a.traj && g.M <= 128 && g.Nt == g.Na * g.M && F <= 65535 && !getenv("AMPSM_SCAMP_GENERIC_DENOISER");
+    const bool fused = Lh > 0 && fast_dn && scamp_st_can_fuse(g, a.al) && !getenv("AMPSM_SCAMP_UNFUSED");
     for (int t = 0; t < g.max_iters; ++t) {
         scamp_scalars_kernel<<<(unsigned)F, 64, 0, stream>>>(w, g, a.W, a.sigma2, a.sigma2_pf, F);
-        if (use_tc) {
+        count_launch();
+        if (Lh > 0) {
+            if (int e = scamp_st_gemm(0, w, g, sp, Lh, w.bplanes0, a.y, F, a.al, false, stream)) return fail(e);
+            if (int e = scamp_st_gemm(1, w, g, sp, Lh, w.bplanes1, a.y, F, a.al, fused, stream)) return fail(e);
+        } else if (use_tc) {
             if (int e = scamp_tc_gemm(0, w, g, a.A, a.y, F, stream)) return fail(e);
             if (int e = scamp_tc_gemm(1, w, g, w.At, a.y, F, stream)) return fail(e);
         } else {
             scamp_gemm_kernel<0><<<grid_res, 256, 0, stream>>>(w, g, a.A, a.y, F);
             scamp_gemm_kernel<1><<<grid_est, 256, 0, stream>>>(w, g, a.A, a.y, F);
+            count_launch();
+            count_launch();
         }
-        // float32-exp mode without trajectory: fused register-resident denoiser (one warp per section) + exit kernel
-        const bool fast_dn = !exp64 && g.shift_mode == 0 && !a.traj && g.M <= 128 && g.Nt == g.Na * g.M && F <= 65535 && !getenv("AMPSM_SCAMP_GENERIC_DENOISER");
-        if (fast_dn) {
+        count_launch();                                        // the denoiser or, fused, the exit kernel
+        if (fused) {
+            scamp_exit_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(w, g, t, F);
+        } else if (fast_dn) {
             const dim3 gd((unsigned)g.Lin, (unsigned)F);
             if (g.M <= 32) scamp_denoise_fast_kernel<1><<<gd, 256, 0, stream>>>(w, g, a.al, F);
             else if (g.M <= 64) scamp_denoise_fast_kernel<2><<<gd, 256, 0, stream>>>(w, g, a.al, F);
@@ -419,7 +450,6 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
             scamp_denoise_kernel<true><<<(unsigned)F, 256, 0, stream>>>(w, g, a.al, a.io.x_true, a.traj, t, F);
         else
             scamp_denoise_kernel<false><<<(unsigned)F, 256, 0, stream>>>(w, g, a.al, a.io.x_true, a.traj, t, F);
-        for (int q = 0; q < 4; ++q) count_launch();
     }
     scamp_finish_kernel<<<(unsigned)F, 128, 0, stream>>>(w, g, a.xmmse, a.psi, a.iters, a.traj, F);
     count_launch();

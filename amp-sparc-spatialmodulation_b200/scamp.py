@@ -1,16 +1,45 @@
 """SCAMP (SPARC-AMP) detector with the reference call signature (/root/reference/scamp.py:70-108), on sm_100a.
 
 ``SCAMP(config)(W, A, y, SNR, x, symbol, index) -> Loss``: base matrix W (Lout, Lin), design matrix A (n, N)
-shared by the F frames of the call, so both mat-vecs of an iteration become complex GEMMs over the frame batch
-(csrc/scamp.cu); zero tiles of the band-structured A are skipped.
+shared by the F frames of the call, so both mat-vecs of an iteration become complex GEMMs over the frame batch.
+
+``structured='auto'`` (default): a design matrix that is exactly the block-Toeplitz matrix of its first block column -- what
+``Channel.generate_as_sparc`` builds (channel.py:76-96) -- is applied from its ``Lh`` tap matrices by the structured
+tensor-core kernels (csrc/scamp_st.cu, ``ampsm_scamp_detect_taps``): dense GEMMs over (frame, column block) rows fed by tensor
+TMA, the dense A is never read.  The structure test reads A once and synchronises; its verdict is cached per tensor.  Any
+other matrix (or ``structured=False``) runs the dense kernels of csrc/scamp.cu / scamp_tc.cu, which skip all-zero tiles.
 """
 import torch
 
 from . import _cabi
 from ._detect import Detection, Detector, ptr, dense
+from .bamp import taps_from_matrix
 
 
 class SCAMP(Detector):
+    def __init__(self, config, *args, structured='auto', **kw) -> None:
+        super().__init__(config, *args, **kw)
+        self.structured = structured
+        self._structure_cache = {}
+
+    def _taps_of(self, A):
+        """(Lh, Nr, Nt) taps when A is block-Toeplitz (non-cyclic) and the structured kernels take the shape, else None."""
+        key = (A.data_ptr(), tuple(A.shape), A._version)
+        hit = self._structure_cache.get(key)
+        if hit is None:
+            if len(self._structure_cache) > 8:
+                self._structure_cache.clear()
+            st = taps_from_matrix(A, self.config)
+            taps = None
+            if st is not None and not st[1]:
+                taps = st[0].contiguous()
+                prob = _cabi.make_problem(self.config, 1)
+                if _cabi.lib().ampsm_scamp_taps_workspace_bytes(prob, 1, int(taps.shape[0])) < 0:
+                    taps = None
+            hit = (taps,)
+            self._structure_cache[key] = hit
+        return hit[0]
+
     def detect(self, W, A, y, SNR, x=None, symbol=None, index=None, frame_base=0) -> Detection:
         dev = self._cuda_device(y, A)
         cfg = self.config
@@ -31,6 +60,18 @@ class SCAMP(Detector):
         traj = torch.empty(F, cfg.N_Layers, 3, dtype=torch.float32, device=dev) if self.trajectory else None
         prob = self._problem(F, frame_base=frame_base)
         lib = _cabi.lib()
+        taps = self._taps_of(A) if self.structured and self.kernel in ('auto', 'fast') else None
+        if taps is not None:
+            Lh = int(taps.shape[0])
+            ws = torch.empty(int(lib.ampsm_scamp_taps_workspace_bytes(prob, F, Lh)), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.ampsm_scamp_detect_taps(
+                    prob, self._alphabet, F, W.data_ptr(), taps.data_ptr(), Lh, y.data_ptr(), float(self.E / SNR), None, ptr(xt),
+                    ptr(sym), ptr(idx), ptr(xmap), ptr(xmmse), ptr(psi), iters.data_ptr(), ptr(traj), counters.data_ptr(),
+                    ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(rc, "ampsm_scamp_detect_taps")
+            ws.record_stream(torch.cuda.current_stream(dev))
+            return Detection(F, counters, iters, xmap, xmmse, psi, traj)
         ws = torch.empty(int(lib.ampsm_scamp_workspace_bytes(prob, F)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.ampsm_scamp_detect(

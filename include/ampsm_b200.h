@@ -197,6 +197,21 @@ int ampsm_scamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t 
                        void* xmap, void* xmmse, float* psi, int32_t* iters, float* traj,
                        uint64_t* counters, void* workspace, void* stream);
 
+/*
+ * SCAMP on a STRUCTURED design matrix -- what Channel.generate_as_sparc builds (channel.py:76-96): block (r, c) of A is
+ * taps[r - c] (Nr x Nt) for 0 <= r - c < Lh and zero elsewhere.  taps : complex64 [Lh][Nr][Nt]; the dense A (142 MB at
+ * BASELINE config 4) is never formed: both mat-vecs run as dense tensor-core GEMMs over (frame, column block) rows fed by
+ * tensor TMA (csrc/scamp_st.cu).  ampsm_scamp_taps_workspace_bytes returns AMPSM_ENOFIT when the shape has no structured
+ * path (needs Lin <= 128, Lh * Nr <= 128, Nr even): run ampsm_scamp_detect on the dense matrix then.
+ */
+int64_t ampsm_scamp_taps_workspace_bytes(const ampsm_problem* p, int64_t frames, int32_t Lh);
+int ampsm_scamp_detect_taps(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                            const float* W, const void* taps, int32_t Lh, const void* y,
+                            double sigma2, const float* sigma2_per_frame,
+                            const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                            void* xmap, void* xmmse, float* psi, int32_t* iters, float* traj,
+                            uint64_t* counters, void* workspace, void* stream);
+
 int ampsm_scamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
                             const float* W, const void* A, const void* y,
                             double sigma2, const float* sigma2_per_frame,

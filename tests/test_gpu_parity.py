@@ -176,14 +176,19 @@ def test_vamp_batched_shared_factors_equals_per_frame_calls():
         assert int(d_big.iters[i]) == int(d_one.iters[0])
 
 
+@pytest.mark.parametrize("structured", [False, 'auto'])
 @pytest.mark.parametrize("exp", ["f64", "f32"])
-def test_scamp_matches_reference_goldens(exp):
+def test_scamp_matches_reference_goldens(exp, structured):
+    """structured=False: dense SIMT tiles (4 frames per matrix); 'auto': the reference's design matrices are block-Toeplitz, so
+    the call runs the structured tensor-core kernels (tensor TMA + tcgen05, csrc/scamp_st.cu) from the taps."""
     g = load_golden("scamp_small")
     N = g["x"].shape[1]
     for ai in range(g["A"].shape[0]):
         sel = np.nonzero(g["a_of_frame"] == ai)[0]
         cfg = config_from_meta(g["meta"], batch=len(sel), device=DEV)
-        amp = pkg.SCAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section")
+        amp = pkg.SCAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section", structured=structured)
+        if structured:
+            assert amp._taps_of(t(g["A"][ai])) is not None, "the reference's own design matrix must be recognised as structured"
         idx = (g["idx"][sel].reshape(len(sel), -1) + (np.arange(len(sel)) * N)[:, None]).reshape(-1)
         snr = (cfg.Na / cfg.Nr) / float(g["sigma2"][sel[0]])
         amp(t(g["W"][ai]), t(g["A"][ai]), t(g["y"][sel]).unsqueeze(-1), snr, t(g["x"][sel]).unsqueeze(-1),
