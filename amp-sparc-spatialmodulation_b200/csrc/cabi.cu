@@ -62,6 +62,8 @@ static int make_geom(const ampsm_problem* p, const ampsm_alphabet* a, Geom* g, D
         al->im[k] = in ? a->im[k] : 0.0;
         al->ref[k] = (float)al->re[k];
         al->imf[k] = (float)al->im[k];
+        al->rel[k] = (float)(al->re[k] - (double)al->ref[k]);
+        al->iml[k] = (float)(al->im[k] - (double)al->imf[k]);
     }
     return 0;
 }

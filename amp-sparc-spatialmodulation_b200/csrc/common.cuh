@@ -28,6 +28,7 @@ struct DevAlphabet {
     int gray[AMPSM_MAX_K];
     double re[AMPSM_MAX_K], im[AMPSM_MAX_K];
     float ref[AMPSM_MAX_K], imf[AMPSM_MAX_K];
+    float rel[AMPSM_MAX_K], iml[AMPSM_MAX_K];   // float32 residuals re - ref, im - imf (compensated float32 exponents)
 };
 
 // Geometry handed to every kernel.

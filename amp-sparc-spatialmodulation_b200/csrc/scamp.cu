@@ -422,11 +422,13 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
     const bool fast_dn = !exp64 && g.shift_mode == 0 && !a.traj && g.M <= 128 && g.Nt == g.Na * g.M && F <= 65535 && !getenv("AMPSM_SCAMP_GENERIC_DENOISER");
     const bool fused = Lh > 0 && fast_dn && scamp_st_can_fuse(g, a.al) && !getenv("AMPSM_SCAMP_UNFUSED");
     for (int t = 0; t < g.max_iters; ++t) {
-        scamp_scalars_kernel<<<(unsigned)F, 64, 0, stream>>>(w, g, a.W, a.sigma2, a.sigma2_pf, F);
-        count_launch();
+        if (Lh == 0) {                                         // the structured residual kernel computes the block scalars itself
+            scamp_scalars_kernel<<<(unsigned)F, 64, 0, stream>>>(w, g, a.W, a.sigma2, a.sigma2_pf, F);
+            count_launch();
+        }
         if (Lh > 0) {
-            if (int e = scamp_st_gemm(0, w, g, sp, Lh, w.bplanes0, a.y, F, a.al, false, stream)) return fail(e);
-            if (int e = scamp_st_gemm(1, w, g, sp, Lh, w.bplanes1, a.y, F, a.al, fused, stream)) return fail(e);
+            if (int e = scamp_st_gemm(0, w, g, sp, Lh, w.bplanes0, a.y, F, a.al, false, a.W, a.sigma2, a.sigma2_pf, t, stream)) return fail(e);
+            if (int e = scamp_st_gemm(1, w, g, sp, Lh, w.bplanes1, a.y, F, a.al, fused, a.W, a.sigma2, a.sigma2_pf, t, stream)) return fail(e);
         } else if (use_tc) {
             if (int e = scamp_tc_gemm(0, w, g, a.A, a.y, F, stream)) return fail(e);
             if (int e = scamp_tc_gemm(1, w, g, w.At, a.y, F, stream)) return fail(e);
@@ -436,10 +438,9 @@ int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream) {
             count_launch();
             count_launch();
         }
-        count_launch();                                        // the denoiser or, fused, the exit kernel
-        if (fused) {
-            scamp_exit_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(w, g, t, F);
-        } else if (fast_dn) {
+        if (fused) continue;                                   // denoiser, psi, exit test and retirement ran in the estimate kernel
+        count_launch();
+        if (fast_dn) {
             const dim3 gd((unsigned)g.Lin, (unsigned)F);
             if (g.M <= 32) scamp_denoise_fast_kernel<1><<<gd, 256, 0, stream>>>(w, g, a.al, F);
             else if (g.M <= 64) scamp_denoise_fast_kernel<2><<<gd, 256, 0, stream>>>(w, g, a.al, F);

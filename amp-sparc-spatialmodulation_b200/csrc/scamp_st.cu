@@ -40,7 +40,7 @@ constexpr int TM = 128;            // rows per tile (UMMA M)
 constexpr int KS = 16;             // complex reduction elements per stage: one 128-byte swizzled row, two K = 8 MMA steps
 constexpr int kXStages = 2;        // split-plane ring (X operand)
 constexpr int kMaxRaw = 6, kMaxB = 4;
-constexpr int kEpiWarps = 4, kCvtWarps = 4;
+constexpr int kEpiWarps = 8, kCvtWarps = 4;          // two epilogue warps per TMEM lane quarter (the residual mode drains with the first four)
 constexpr int kThreads = (kEpiWarps + kCvtWarps + 2) * 32;     // + producer warp + MMA warp
 constexpr int kRawStage = TM * KS * 8;                         // 16 KiB
 constexpr int kXPlane = TM * KS * 4;                           // 8 KiB: [4 K chunks][128 rows][4 floats]
@@ -148,11 +148,39 @@ struct StArgs {
     int brows;                         // N of the MMAs: outputs per chunk (padded to 32)
     int chunks, nks;                   // output chunks per tile, K stages per chunk
     int zs_stride;                     // complex elements between frames of Zs (padded to (Lin + Lh - 1) Nr)
+    const float* W;                    // [Lout][Lin] base matrix (residual mode computes the block scalars of its frames)
+    float sigma2;
+    const float* sigma2_pf;
+    int t;                             // iteration index (the fused estimate mode retires its frames itself)
+    int dbg;                           // AMPSM_ST_DEBUG bits (timing experiments): 2 skip the MMAs, 4 skip the conversion, 8 skip the Xh loads, 16 skip the epilogue stores, 32 skip the denoiser math
 };
+
+// x - shift for x = q.re s.re + q.im s.im, the symbol given as float32 value + float32 residual of its float64 value: the
+// products are split exactly by FMA (hi + lo), the sum by a two-sum, so the difference to the shift carries the accuracy of
+// the reference's float64 evaluation (bamp.py:69 / scamp.py:64) without leaving the FP32 pipe (float64 conversions run on the
+// XU pipe at a sixteenth of the FP32 rate and bound the first version of this epilogue)
+__device__ __forceinline__ float exponent_diff(float qr, float qi, float sr, float si, float srl, float sil, float shift) {
+    const float h1 = __fmul_rn(qr, sr), l1 = fmaf(qr, sr, -h1);            // intrinsics: never contracted into other FMAs
+    const float h2 = __fmul_rn(qi, si), l2 = fmaf(qi, si, -h2);
+    const float sum = __fadd_rn(h1, h2), t = __fsub_rn(sum, h1);
+    const float err = __fadd_rn(__fsub_rn(h1, __fsub_rn(sum, t)), __fsub_rn(h2, t));
+    const float low = fmaf(qr, srl, fmaf(qi, sil, __fadd_rn(__fadd_rn(l1, l2), err)));
+    return __fadd_rn(__fsub_rn(sum, shift), low);
+}
+
+// reciprocal to one ulp without a slow path (the slow-path call of __frcp_rn sits behind a branch, which costs the epilogue its
+// lock step): MUFU.RCP + one Newton step
+__device__ __forceinline__ float rcp1(float x) {
+    const float r = fast_rcp(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
 
 // MODE 0: residual (X = xh rows, map 2-D);  MODE 1: estimate (X = zs row blocks, map 3-D).  FUSED (estimate only): section
 // denoiser + psi + exit test in the epilogue (float32 exp, per-section shift; M in {8, 16, 32, 64}).
-template <int MODE, bool FUSED>
+// MSEC: section size of the fused denoiser (8, 16, 32, 64), 0 = not fused.  EXACT: every symbol is one of {0, +-1, +-j} (the reference's
+// OOK / BPSK / QPSK tables, config.py:86-95): the exponent q.re s.re + q.im s.im is then ONE exact float32 product, so the plain float32
+// difference to the shift is as accurate as the reference's float64 evaluation and the compensated sum is not needed.
+template <int MODE, int MSEC, bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_constant__ StArgs a, const __grid_constant__ CUtensorMap xmap_desc) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_base_s;
@@ -208,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
             mbar_init(&xp_full[s], kCvtWarps * 32);
             mbar_init(&xp_empty[s], 1);
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kEpiWarps * 32);
+            mbar_init(&acc_empty[s], kEpiWarps * 32);      // estimate mode: both warp sets read every accumulator buffer
         }
         for (int s = 0; s < kMaxB; ++s) {
             mbar_init(&b_full[s], 1);
@@ -247,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
             const uint32_t id_pos = umma_idesc(a.brows, false), id_neg = umma_idesc(a.brows, true);
             const uint32_t x_lbo = TM * 16, b_lbo = (uint32_t)a.brows * 16, sbo = 128;
             const uint32_t bplane = 4 * (uint32_t)a.brows * 16;          // bytes of one B plane of a stage
+            const uint64_t xdesc0 = umma_desc(smem_u32(smem + L.xpl), x_lbo, sbo), bdesc0 = umma_desc(smem_u32(smem + L.bpl), b_lbo, sbo);
             for (int ch = 0; ch < a.chunks; ++ch) {
                 const int buf = MODE == 1 ? (ch & 1) : 0, v = MODE == 1 ? (ch >> 1) : ch;
                 mbar_wait(&acc_empty[buf], (v & 1) ^ 1);
@@ -259,16 +288,17 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                     mbar_wait(&xp_full[ps], pu & 1);
                     mbar_wait(&b_full[bs], bu & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t xs = smem_u32(smem + L.xpl + ps * kXStage), bsm = smem_u32(smem + L.bpl + bs * bstage_bytes);
+                    // descriptors differ only in their start-address field (bits 0-13, units of 16 bytes): base + offset
+                    const uint64_t xd0 = xdesc0 + (uint64_t)((ps * kXStage) >> 4), bd0 = bdesc0 + (uint64_t)((bs * bstage_bytes) >> 4);
 #pragma unroll
-                    for (int j = 0; j < KS / 8; ++j) {
+                    for (int j = 0; j < ((a.dbg & 2) ? 0 : KS / 8); ++j) {
                         // planes: 0 re_hi, 1 re_lo, 2 im_hi, 3 im_lo;  re = XrBr - XiBi, im = XrBi + XiBr  (the estimate mode's conjugate
                         // lives in its pre-split B planes)
                         uint64_t xd[4], bd[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            xd[q] = umma_desc(xs + q * kXPlane + 2 * j * x_lbo, x_lbo, sbo);
-                            bd[q] = umma_desc(bsm + q * bplane + 2 * j * b_lbo, b_lbo, sbo);
+                            xd[q] = xd0 + (uint64_t)((q * kXPlane + 2 * j * x_lbo) >> 4);
+                            bd[q] = bd0 + (uint64_t)((q * bplane + 2 * j * b_lbo) >> 4);
                         }
                         const uint32_t acc = (ks > 0 || j > 0) ? 1u : 0u;
                         const int xsel[4] = {0, 2, 0, 2}, bsel[4] = {0, 2, 2, 0};
@@ -305,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
             mbar_wait(&xp_empty[ps], (pu & 1) ^ 1);
             unsigned char* xp = smem + L.xpl + ps * kXStage + r * 16;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {                      // K chunk c = elements 4c .. 4c+3 = raw chunks 2c, 2c+1
+            for (int c = 0; c < ((a.dbg & 4) ? 0 : 4); ++c) {                      // K chunk c = elements 4c .. 4c+3 = raw chunks 2c, 2c+1
                 const float4 p = v[2 * c], q = v[2 * c + 1];
                 const float re[4] = {p.x, p.z, q.x, q.z}, im[4] = {p.y, p.w, q.y, q.w};
                 float rh[4], rl[4], ih[4], il[4];
@@ -327,16 +357,18 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
         }
     } else {
         // ===================================================== epilogue warps 0-3: thread = TMEM lane = row
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int quarter = warp & 3, eset = warp >> 2;        // TMEM lanes 32 quarter ..; set 0 takes rows 0-15 of the quarter, set 1 rows 16-31
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         if (MODE == 1) {
             // per-warp transpose buffer: 16 rows x 64 columns (+1 pad) complex sums
             float2* tbuf = reinterpret_cast<float2*>(smem + L.epi) + warp * kTbufRows * kTbufStride;
-            const int M = g.M, K = a.al.K;
-            const int segw = M < 32 ? M : 32;
+            constexpr bool FUSED = MSEC > 0;
+            constexpr int M = MSEC, segw = MSEC < 32 ? MSEC : 32;
+            const int K = a.al.K;
             const int pairs = (a.brows + 63) / 64;             // 64-column pairs of 32-column groups per chunk
             auto prefetch_chunk = [&](int ch) {                // this thread's row: the chunk's segment of Xh -> L2
                     const int cols = min(a.brows, g.Nt - ch * a.brows);
-                    if (ch < a.chunks && row_f[tid] >= 0 && cols > 0 && ((cols * 8) & 15) == 0) {
+                    if (tid < TM && ch < a.chunks && row_f[tid] >= 0 && cols > 0 && ((cols * 8) & 15) == 0) {
                         const float2* src = w.Xh + row_off[tid] + (long long)ch * a.brows;
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(cols * 8) : "memory");
                     }
@@ -352,9 +384,11 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                     const bool haveB = pr * 64 + 32 < a.brows;
                     const int oA = ch * a.brows + pr * 64 + lane, oB = oA + 32;
                     const bool okA = oA < g.Nt, okB = haveB && oB < g.Nt;
+                    const bool ldA = okA && !(a.dbg & 8), ldB = okB && !(a.dbg & 8), stA = okA && !(a.dbg & 16), stB = okB && !(a.dbg & 16);
                     // the 32 rows of this warp in two passes of 16: the lanes of the pass park their row (64 complex sums) in the
                     // transpose buffer, then the warp walks the 16 rows with lane = antenna (columns oA = lane, oB = lane + 32)
-                    for (int pass = 0; pass < 2; ++pass) {
+                    {
+                        const int pass = eset;
                         {
                             uint32_t vr[32], vi[32];
                             tmem_ld32(lane_addr + col0 + pr * 64, vr);
@@ -377,12 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                                 }
                             }
                         }
-                        if (pass == 1 && pr == pairs - 1) {    // last read of this accumulator buffer: hand it back to the MMA warp
+                        if (pr == pairs - 1) {                 // last read of this accumulator buffer: hand it back to the MMA warp
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             mbar_arrive(&acc_empty[buf]);
                         }
                         __syncwarp();
-                        const int rbase = warp * 32 + pass * 16;
+                        const int rbase = quarter * 32 + pass * 16;
                         // the previous estimates of four rows at a time, requested one block ahead (their lines were pulled into L2
                         // by the bulk prefetch issued one chunk earlier)
                         float2 pa[4], pb[4];
@@ -390,8 +424,8 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                         for (int u = 0; u < 4; ++u) {
                             pa[u] = pb[u] = make_float2(0.f, 0.f);
                             if (row_f[rbase + u] >= 0) {
-                                if (okA) pa[u] = w.Xh[row_off[rbase + u] + oA];
-                                if (okB) pb[u] = w.Xh[row_off[rbase + u] + oB];
+                                if (ldA) pa[u] = w.Xh[row_off[rbase + u] + oA];
+                                if (ldB) pb[u] = w.Xh[row_off[rbase + u] + oB];
                             }
                         }
 #pragma unroll 1
@@ -407,93 +441,153 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                                 for (int u = 0; u < 4; ++u) {
                                     const int rn = rbase + r4 + 4 + u;
                                     if (row_f[rn] >= 0) {
-                                        if (okA) pa[u] = w.Xh[row_off[rn] + oA];
-                                        if (okB) pb[u] = w.Xh[row_off[rn] + oB];
+                                        if (ldA) pa[u] = w.Xh[row_off[rn] + oA];
+                                        if (ldB) pb[u] = w.Xh[row_off[rn] + oB];
                                     }
                                 }
                             }
+                            // four rows in lock step, phase by phase: their dependent chains (shuffle reductions, float64 exponent
+                            // products, MUFU) interleave, which is what keeps the one epilogue warp of a scheduler busy
+                            bool live[4];
+                            long long at[4];
+                            float tau[4];
+                            float2 ma[4], mb[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                            const int rr = r4 + u;
-                            const int row = rbase + rr;
-                            const float2 xa = ca[u], xb = cb[u];
-                            if (row_f[row] < 0) continue;      // uniform over the warp
-                            const long long at = row_off[row];
-                            const float tau = row_tau[row];
-                            const float2 sa = tbuf[rr * kTbufStride + lane];
-                            const float2 sb = haveB ? tbuf[rr * kTbufStride + 32 + lane] : make_float2(0.f, 0.f);
-                            const float2 ma = make_float2(fmaf(tau, sa.x, xa.x), fmaf(tau, sa.y, xa.y));     // scamp.py:56
-                            const float2 mb = make_float2(fmaf(tau, sb.x, xb.x), fmaf(tau, sb.y, xb.y));
-                            if (okA) w.Xmap[at + oA] = ma;
-                            if (okB) w.Xmap[at + oB] = mb;
-                            if (FUSED) {
+                                const int row = rbase + r4 + u;
+                                live[u] = row_f[row] >= 0;
+                                at[u] = row_off[row];
+                                tau[u] = row_tau[row];
+                                const float2 sa = tbuf[(r4 + u) * kTbufStride + lane];
+                                const float2 sb = haveB ? tbuf[(r4 + u) * kTbufStride + 32 + lane] : make_float2(0.f, 0.f);
+                                ma[u] = make_float2(fmaf(tau[u], sa.x, ca[u].x), fmaf(tau[u], sa.y, ca[u].y));     // scamp.py:56
+                                mb[u] = make_float2(fmaf(tau[u], sb.x, cb[u].x), fmaf(tau[u], sb.y, cb[u].y));
+                                if (live[u] && stA) w.Xmap[at[u] + oA] = ma[u];
+                                if (live[u] && stB) w.Xmap[at[u] + oB] = mb[u];
+                            }
+                            if (FUSED && !(a.dbg & 32)) {
                                 // section-wise posterior mean (scamp.py:61-68): s / (tau / 2) in complex64, exponents as float64 products,
                                 // float32 ex2 of the difference to the SECTION maximum, lanes = antennas
-                                const float rt = __frcp_rn(tau / 2.0f);
-                                const float qar = __fmul_rn(ma.x, rt), qai = __fmul_rn(ma.y, rt), qbr = __fmul_rn(mb.x, rt), qbi = __fmul_rn(mb.y, rt);
-                                float la = -INFINITY, lb = -INFINITY;
-                                for (int k = 0; k < K; ++k) {
-                                    la = fmaxf(la, fmaf(qar, a.al.ref[k], qai * a.al.imf[k]));
-                                    lb = fmaxf(lb, fmaf(qbr, a.al.ref[k], qbi * a.al.imf[k]));
-                                }
-                                if (!okA) la = -INFINITY;
-                                if (!okB) lb = -INFINITY;
-                                if (M == 64) la = lb = fmaxf(la, lb);
+                                float qar[4], qai[4], qbr[4], qbi[4], la[4], lb[4];
 #pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) {
-                                    if (o < segw) {
-                                        la = fmaxf(la, __shfl_xor_sync(0xffffffffu, la, o));
-                                        lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+                                for (int u = 0; u < 4; ++u) {
+                                    const float rt = rcp1(tau[u] / 2.0f);
+                                    qar[u] = __fmul_rn(ma[u].x, rt);
+                                    qai[u] = __fmul_rn(ma[u].y, rt);
+                                    qbr[u] = __fmul_rn(mb[u].x, rt);
+                                    qbi[u] = __fmul_rn(mb[u].y, rt);
+                                    la[u] = lb[u] = -INFINITY;
+                                }
+                                for (int k = 0; k < K; ++k) {
+                                    const float sr = a.al.ref[k], si = a.al.imf[k];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        la[u] = fmaxf(la[u], fmaf(qar[u], sr, qai[u] * si));
+                                        lb[u] = fmaxf(lb[u], fmaf(qbr[u], sr, qbi[u] * si));
                                     }
                                 }
-                                const double sha = (double)la, shb = (double)lb;
-                                const double qard = (double)qar, qaid = (double)qai, qbrd = (double)qbr, qbid = (double)qbi;
-                                float za = 0.f, zb = 0.f, nar = 0.f, nai = 0.f, nbr = 0.f, nbi = 0.f;
-                                for (int k = 0; k < K; ++k) {
-                                    const float ea = fast_ex2((float)(fma(qard, a.al.re[k], qaid * a.al.im[k]) - sha) * 1.4426950408889634f);
-                                    const float eb = fast_ex2((float)(fma(qbrd, a.al.re[k], qbid * a.al.im[k]) - shb) * 1.4426950408889634f);
-                                    za += ea;
-                                    nar = fmaf(a.al.ref[k], ea, nar);
-                                    nai = fmaf(a.al.imf[k], ea, nai);
-                                    zb += eb;
-                                    nbr = fmaf(a.al.ref[k], eb, nbr);
-                                    nbi = fmaf(a.al.imf[k], eb, nbi);
-                                }
-                                if (!okA) za = nar = nai = 0.f;
-                                if (!okB) zb = nbr = nbi = 0.f;
-                                // section sums of Z and of |numerator|^2 (the energy of the normalised estimates is (sum |n|^2) / Z^2)
-                                float ua = fmaf(nar, nar, nai * nai), ub = fmaf(nbr, nbr, nbi * nbi);
-                                if (M == 64) {
-                                    za = zb = za + zb;
-                                    ua += ub;
-                                    ub = 0.f;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (!okA) la[u] = -INFINITY;
+                                    if (!okB) lb[u] = -INFINITY;
+                                    if (M == 64) la[u] = lb[u] = fmaxf(la[u], lb[u]);
                                 }
 #pragma unroll
                                 for (int o = 16; o > 0; o >>= 1) {
                                     if (o < segw) {
-                                        za += __shfl_xor_sync(0xffffffffu, za, o);
-                                        zb += __shfl_xor_sync(0xffffffffu, zb, o);
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            la[u] = fmaxf(la[u], __shfl_xor_sync(0xffffffffu, la[u], o));
+                                            if (M != 64) lb[u] = fmaxf(lb[u], __shfl_xor_sync(0xffffffffu, lb[u], o));
+                                        }
                                     }
                                 }
-                                const float rza = __frcp_rn(za), rzb = __frcp_rn(zb);
-                                if (okA) w.Xh[at + oA] = make_float2(nar * rza, nai * rza);
-                                if (okB) w.Xh[at + oB] = make_float2(nbr * rzb, nbi * rzb);
-                                // energy of the row's 64 estimates: per-lane contributions, folded once per row by one warp sum
-                                float en = (okA ? ua * rza * rza : 0.f) + (okB && M != 64 ? ub * rzb * rzb : 0.f);
-                                en = warp_sum(en);
-                                if (lane == 0) row_e[row] += en;
-                            }
+                                float za[4], zb[4], nar[4], nai[4], nbr[4], nbi[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (M == 64) lb[u] = la[u];
+                                    za[u] = zb[u] = nar[u] = nai[u] = nbr[u] = nbi[u] = 0.f;
+                                }
+                                if (EXACT) {
+                                    for (int k = 0; k < K; ++k) {
+                                        const float sr = a.al.ref[k], si = a.al.imf[k];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            const float ea = fast_ex2((fmaf(qar[u], sr, qai[u] * si) - la[u]) * 1.4426950408889634f);
+                                            const float eb = fast_ex2((fmaf(qbr[u], sr, qbi[u] * si) - lb[u]) * 1.4426950408889634f);
+                                            za[u] += ea;
+                                            nar[u] = fmaf(sr, ea, nar[u]);
+                                            nai[u] = fmaf(si, ea, nai[u]);
+                                            zb[u] += eb;
+                                            nbr[u] = fmaf(sr, eb, nbr[u]);
+                                            nbi[u] = fmaf(si, eb, nbi[u]);
+                                        }
+                                    }
+                                } else {
+                                    for (int k = 0; k < K; ++k) {
+                                        const float sr = a.al.ref[k], si = a.al.imf[k];
+                                        const float srl = a.al.rel[k], sil = a.al.iml[k];          // float32 residuals of the float64 symbols
+    #pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            const float ea = fast_ex2(exponent_diff(qar[u], qai[u], sr, si, srl, sil, la[u]) * 1.4426950408889634f);
+                                            const float eb = fast_ex2(exponent_diff(qbr[u], qbi[u], sr, si, srl, sil, lb[u]) * 1.4426950408889634f);
+                                            za[u] += ea;
+                                            nar[u] = fmaf(sr, ea, nar[u]);
+                                            nai[u] = fmaf(si, ea, nai[u]);
+                                            zb[u] += eb;
+                                            nbr[u] = fmaf(sr, eb, nbr[u]);
+                                            nbi[u] = fmaf(si, eb, nbi[u]);
+                                        }
+                                    }
+                                }
+                                // section sums of Z; the energy of the normalised estimates is (sum |n|^2) / Z^2 per section
+                                float en[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (!okA) za[u] = nar[u] = nai[u] = 0.f;
+                                    if (!okB) zb[u] = nbr[u] = nbi[u] = 0.f;
+                                    if (M == 64) za[u] = zb[u] = za[u] + zb[u];
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    if (o < segw) {
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            za[u] += __shfl_xor_sync(0xffffffffu, za[u], o);
+                                            if (M != 64) zb[u] += __shfl_xor_sync(0xffffffffu, zb[u], o);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (M == 64) zb[u] = za[u];
+                                    const float rza = rcp1(za[u]), rzb = rcp1(zb[u]);
+                                    const float2 va = make_float2(nar[u] * rza, nai[u] * rza), vb = make_float2(nbr[u] * rzb, nbi[u] * rzb);
+                                    if (live[u] && stA) w.Xh[at[u] + oA] = va;
+                                    if (live[u] && stB) w.Xh[at[u] + oB] = vb;
+                                    en[u] = (okA ? fmaf(va.x, va.x, va.y * va.y) : 0.f) + (okB ? fmaf(vb.x, vb.x, vb.y * vb.y) : 0.f);
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) en[u] += __shfl_xor_sync(0xffffffffu, en[u], o);
+                                }
+                                if (lane < 4) {
+                                    const float e = lane == 0 ? en[0] : lane == 1 ? en[1] : lane == 2 ? en[2] : en[3];
+                                    const bool lv = lane == 0 ? live[0] : lane == 1 ? live[1] : lane == 2 ? live[2] : live[3];
+                                    if (lv) row_e[rbase + r4 + lane] += e;
+                                }
                             }
                         }
                         __syncwarp();
                     }
                 }
             }
-            if (FUSED) {
+            if (MSEC > 0) {
                 // psi of the column block and its allclose test (scamp.py:59,105): lane rr finishes row rr of this warp
                 __syncwarp();
-                const int row = warp * 32 + lane;
-                if (row_f[row] >= 0) {
+                const int row = quarter * 32 + eset * 16 + (lane & 15);
+                if (lane < 16 && row_f[row] >= 0) {
                     const long long f = f0 + row_f[row];
                     const int c = row % g.Lin;
                     const float pn = 1.0f - row_e[row] / (float)g.Na;
@@ -502,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                     w.psi[f * g.Lin + c] = pn;
                 }
             }
-        } else {
+        } else if (warp < 4) {
             // P -> shared memory [row][brows + 1] (the rings are idle once acc_full has fired: every MMA has completed)
             const int r = tid;
             mbar_wait(&acc_full[0], 0);
@@ -516,6 +610,31 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int q = 0; q < 32; ++q) P[r * pstride + gq * kEpiCols + q] = make_float2(__uint_as_float(vr[q]), __uint_as_float(vi[q]));
+            }
+        } else if (MODE == 0) {
+            // warps 4-7, idle in this mode: the block scalars of the tile's frames under the main loop (scamp.py:45-52):
+            // gamma = W psi / Lc, b = gamma / phi_old, phi = sigma2 + gamma, tau = L / (W^T (1 / phi)) / Mr
+            const int j = tid - 4 * 32;
+            const int Lr = g.Lout, Lc = g.Lin;
+            for (int e = j; e < a.FR * Lr; e += 128) {
+                const int fl = e / Lr, r = e % Lr;
+                if (row_f[fl * Lc] < 0) continue;
+                const long long f = f0 + fl;
+                float acc = 0.f;
+                for (int c = 0; c < Lc; ++c) acc = fmaf(a.W[r * Lc + c], w.psi[f * Lc + c], acc);
+                const float gma = acc / (float)Lc;
+                const float s2 = a.sigma2_pf ? a.sigma2_pf[f] : a.sigma2;
+                w.b[f * Lr + r] = gma / w.phi[f * Lr + r];          // old phi (inf on the first pass -> 0)
+                w.phi[f * Lr + r] = s2 + gma;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four warps of this role: phi is complete
+            for (int e = j; e < a.FR * Lc; e += 128) {
+                const int fl = e / Lc, c = e % Lc;
+                if (row_f[fl * Lc] < 0) continue;
+                const long long f = f0 + fl;
+                float acc = 0.f;
+                for (int r = 0; r < Lr; ++r) acc = fmaf(a.W[r * Lc + c], __frcp_rn(w.phi[f * Lr + r]), acc);
+                w.tau[f * Lc + c] = (float)g.L / acc / (float)g.Nr;      // L = Na*Lin, Mr = Nr (scamp.py:52)
             }
         }
     }
@@ -570,6 +689,13 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                 w.Zs[f * (long long)a.zs_stride + o] = cdiv_real(zn, ph[u]);                                     // z / phi_use
             }
         }
+    }
+    if (MODE == 1 && MSEC > 0 && tid < a.FR && row_f[tid * g.Lin] >= 0) {
+        // the tile holds every column block of its frames: retire them here (scamp.py:105); `notclose` was raised by this CTA's rows
+        const long long f = f0 + tid;
+        w.iters[f] = a.t + 1;
+        if (g.early_exit && !w.notclose[f]) w.active[f] = 0;
+        w.notclose[f] = 0;
     }
     __syncthreads();
     if (warp == kEpiWarps + kCvtWarps + 1) {
@@ -638,7 +764,7 @@ ScampStPlan scamp_st_plan(const Geom& g, int Lh) {
     if (g.n != g.Lout * g.Nr || g.N != g.Lin * g.Nt) return p;
     p.brows0 = round_up(Lh * g.Nr, 32);
     if (p.brows0 > 128) return p;                              // P staging and TMEM: N of the residual MMAs <= 128
-    p.brows1 = g.Nt >= 128 ? 128 : round_up(g.Nt, 32);
+    p.brows1 = g.Nt >= 64 ? 64 : round_up(g.Nt, 32);        // one 64-column pair per chunk: 16 KiB design stages, two accumulator buffers of 128 columns
     p.chunks1 = (g.Nt + p.brows1 - 1) / p.brows1;
     p.nks0 = (g.Nt + KS - 1) / KS;
     p.kpb = (g.Nr + KS - 1) / KS;
@@ -661,12 +787,21 @@ int scamp_st_prepare(const Geom& g, const ScampStPlan& p, int Lh, const float2* 
     return check_cuda(cudaGetLastError(), "scamp_st_split_kernel launch");
 }
 
+// every symbol in {0, +-1, +-j}: one exact float32 product per exponent
+static bool is_exact_alphabet(const DevAlphabet& al) {
+    for (int k = 0; k < al.K; ++k) {
+        const double ar = al.re[k] < 0 ? -al.re[k] : al.re[k], ai = al.im[k] < 0 ? -al.im[k] : al.im[k];
+        if (!((ar == 0.0 || ar == 1.0) && (ai == 0.0 || ai == 1.0) && !(ar == 1.0 && ai == 1.0))) return false;
+    }
+    return true;
+}
+
 bool scamp_st_can_fuse(const Geom& g, const DevAlphabet& al) {
     return (g.M == 8 || g.M == 16 || g.M == 32 || g.M == 64) && g.Nt == g.Na * g.M && al.K >= 1 && al.K <= AMPSM_MAX_K;
 }
 
 int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& p, int Lh, const unsigned char* bplanes, const float2* y,
-                  long long F, const DevAlphabet& al, bool fused, cudaStream_t stream) {
+                  long long F, const DevAlphabet& al, bool fused, const float* W, float sigma2, const float* sigma2_pf, int t, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return AMPSM_ENOFIT; }
     CUtensorMap map;
@@ -690,8 +825,10 @@ int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& 
     }
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for SCAMP mode %d", (int)r, mode); return AMPSM_ENOFIT; }
     StArgs a{};
+    a.W = W; a.sigma2 = sigma2; a.sigma2_pf = sigma2_pf; a.t = t;
     a.w = w; a.g = g; a.al = al; a.y = y; a.bplanes = bplanes; a.F = F; a.Lh = Lh; a.FR = p.FR; a.zs_stride = p.zs_stride; a.kpb = p.kpb;
     a.brows = mode == 0 ? p.brows0 : p.brows1;
+    if (const char* d = getenv("AMPSM_ST_DEBUG")) a.dbg = atoi(d);
     a.chunks = mode == 0 ? 1 : p.chunks1;
     a.nks = mode == 0 ? p.nks0 : p.nks1;
     const int smem = st_smem(a.brows, mode).total;
@@ -701,13 +838,19 @@ int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& 
         kern<<<grid, kThreads, smem, stream>>>(a, map);
         return 0;
     };
-    if (mode == 0) {
-        if (int e = run(scamp_st_kernel<0, false>, "cudaFuncSetAttribute(scamp_st<0>)")) return e;
-    } else if (fused) {
-        if (int e = run(scamp_st_kernel<1, true>, "cudaFuncSetAttribute(scamp_st<1, fused>)")) return e;
-    } else {
-        if (int e = run(scamp_st_kernel<1, false>, "cudaFuncSetAttribute(scamp_st<1>)")) return e;
-    }
+    int e = 0;
+    const bool exact = fused && is_exact_alphabet(al) && !getenv("AMPSM_SCAMP_NO_EXACT");
+    if (mode == 0) e = run(scamp_st_kernel<0, 0, false>, "cudaFuncSetAttribute(scamp_st<0>)");
+    else if (!fused) e = run(scamp_st_kernel<1, 0, false>, "cudaFuncSetAttribute(scamp_st<1>)");
+#define AMPSM_ST_CASE(MM) \
+    else if (g.M == MM) e = exact ? run(scamp_st_kernel<1, MM, true>, "cudaFuncSetAttribute(scamp_st<1, " #MM ", exact>)") \
+                                 : run(scamp_st_kernel<1, MM, false>, "cudaFuncSetAttribute(scamp_st<1, " #MM ">)");
+    AMPSM_ST_CASE(64)
+    AMPSM_ST_CASE(32)
+    AMPSM_ST_CASE(16)
+    AMPSM_ST_CASE(8)
+#undef AMPSM_ST_CASE
+    if (e) return e;
     count_launch();
     return check_cuda(cudaGetLastError(), "scamp_st_kernel launch");
 }

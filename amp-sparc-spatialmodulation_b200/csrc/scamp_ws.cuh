@@ -41,7 +41,8 @@ int scamp_st_prepare(const Geom& g, const ScampStPlan& p, int Lh, const float2* 
                      cudaStream_t stream);
 bool scamp_st_can_fuse(const Geom& g, const DevAlphabet& al);   // section denoiser + psi + exit test in the estimate GEMM's epilogue
 int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& p, int Lh, const unsigned char* bplanes, const float2* y,
-                  long long F, const DevAlphabet& al, bool fused, cudaStream_t stream);
+                  long long F, const DevAlphabet& al, bool fused, const float* W, float sigma2, const float* sigma2_pf, int t, cudaStream_t stream);
+// the residual mode computes the block scalars (gamma, b, phi, tau) of its frames itself; the fused estimate mode retires its frames
 
 // tensor-core GEMMs (scamp_tc.cu): mode 0 = residual with Bm = A, mode 1 = estimate with Bm = A^T
 bool scamp_tc_fits(int n, int N, long long F);

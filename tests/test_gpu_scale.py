@@ -531,23 +531,30 @@ def test_fast_kernel_falls_back_on_misaligned_loss_inputs():
         pkg.BAMP(cfg, kernel='fast', outputs=False).detect(H, y, 10 ** 1.5, xm, lab, idx)
 
 
-@pytest.mark.parametrize("shape,F,trunc", [((64, 2, 8, 8, 3), 300, 'tail'), ((128, 4, 16, 6, 2), 150, 'tail'), ((64, 2, 8, 8, 3), 130, 'trunc'),
-                                            ((48, 2, 6, 5, 2), 140, 'tail'), ((128, 8, 32, 16, 3), 37, 'tail')])
-def test_scamp_structured_path_matches_dense_path(shape, F, trunc):
+@pytest.mark.parametrize("shape,F,trunc,alphabet", [((64, 2, 8, 8, 3), 300, 'tail', 'QPSK'), ((128, 4, 16, 6, 2), 150, 'tail', 'QPSK'),
+                                                     ((64, 2, 8, 8, 3), 130, 'trunc', 'QPSK'), ((48, 2, 6, 5, 2), 140, 'tail', 'QPSK'),
+                                                     ((128, 8, 32, 16, 3), 37, 'tail', 'QPSK'), ((64, 2, 8, 8, 3), 160, 'tail', 'QPSK-generic'),
+                                                     ((128, 2, 16, 6, 2), 140, 'tail', 'BPSK')])
+def test_scamp_structured_path_matches_dense_path(shape, F, trunc, alphabet, monkeypatch):
     """The structured tensor-core kernels (design matrix applied from its taps: tensor TMA, tcgen05, csrc/scamp_st.cu) against
     the dense tensor-core / SIMT kernels reading the full matrix, same frames: estimates of frames that exit at the same
     iteration agree to float32 rounding, decisions agree on all but near-tie / non-converged frames.  Shapes cover ragged tiles
     (Lin = 6, 5: 126 / 125 rows per tile), a truncated channel (zero padding blocks of Zs), Nt and Lh Nr that are not multiples of
-    the MMA tile (48 columns, 12 / 16 / 24 reduction rows), and a batch smaller than one tile."""
+    the MMA tile (48 columns, 12 / 16 / 24 reduction rows), a batch smaller than one tile, and alphabets that take the generic
+    (compensated float32 exponent) branch of the fused denoiser instead of the QPSK factorisation."""
     Nt, Na, Nr, Lin, Lh = shape
-    cfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet='QPSK',
+    if alphabet == 'QPSK-generic':        # the compensated float32 exponent branch (what an alphabet outside {0, +-1, +-j} takes)
+        monkeypatch.setenv("AMPSM_SCAMP_NO_EXACT", "1")
+        alphabet = 'QPSK'
+    cfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet=alphabet,
                      channel_profile='uniform', channel_truncation=trunc, device=str(DEV))
     np.random.seed(13)
     torch.manual_seed(13)
     ch, da = pkg.Channel(cfg), pkg.Data(cfg)
     W, A = ch.generate_as_sparc()
     x, sym, idx = da.generate_message()
-    snr = 10 ** ((6.0 + 10 * np.log10(cfg.code_rate)) / 10)
+    ebn0 = 6.0
+    snr = 10 ** ((ebn0 + 10 * np.log10(cfg.code_rate)) / 10)
     y = A @ x + ch.awgn(snr)
     st = pkg.SCAMP(cfg, outputs=True)
     assert st._taps_of(A.to(DEV) if not A.is_cuda else A) is not None
