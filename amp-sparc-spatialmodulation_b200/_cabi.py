@@ -22,7 +22,7 @@ EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
            "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect", "ampsm_scamp_taps_workspace_bytes", "ampsm_scamp_detect_taps",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops", "ampsm_probe_fp64_tflops",
-           "ampsm_launch_count"]
+           "ampsm_launch_count", "ampsm_host_alloc", "ampsm_host_free", "ampsm_host_numa_info"]
 
 
 class Alphabet(C.Structure):
@@ -82,6 +82,9 @@ def lib():
     L.ampsm_probe_fp32_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ampsm_probe_fp32x2_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ampsm_probe_fp64_tflops.argtypes = [i32, C.POINTER(dbl)]
+    L.ampsm_host_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp)]
+    L.ampsm_host_free.argtypes = [vp]
+    L.ampsm_host_numa_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32)]
     L.ampsm_launch_count.argtypes = [i32]
     L.ampsm_launch_count.restype = i64
     for name in EXPORTS:
@@ -139,3 +142,30 @@ def counters_to_dict(buf):
     sq = buf[16:20].view(np.float64)
     out.update({k: float(sq[i]) for i, k in enumerate(SQERR_NAMES)})
     return out
+
+
+class HostBuffer:
+    """Pinned host memory placed on the NUMA node of a GPU (``ampsm_host_alloc``), viewed as a numpy array; for the buffers
+    handed to the ``*_detect_host`` entry points."""
+
+    def __init__(self, device: int, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(v) for v in np.atleast_1d(shape))
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().ampsm_host_alloc(int(device), self.nbytes, C.byref(p)), "ampsm_host_alloc")
+        self.ptr = p.value
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().ampsm_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

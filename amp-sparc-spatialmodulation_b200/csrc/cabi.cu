@@ -9,6 +9,9 @@
 #include <mutex>
 #include <vector>
 
+#include <sched.h>
+#include <unistd.h>
+
 #include "kernels.h"
 
 namespace ampsm {
@@ -74,6 +77,51 @@ static int check_loss_io(const void* x_true, const int64_t* sym, const int64_t* 
     return 0;
 }
 
+// ---- NUMA placement of the host path ----------------------------------------------------------------------------
+// The copies of the host entry points are PCIe transfers from the caller's buffers: on a two-socket box a buffer (or the
+// thread issuing the copies) on the other socket crosses the inter-socket link (SCALE_r01: 22 GB/s per GPU at 8 GPUs against
+// 55 GB/s alone).  The CPUs next to a GPU are read from sysfs (local_cpulist of its PCI device); HostBind pins the calling
+// thread to them for its lifetime, ampsm_host_alloc first-touches pinned memory from such a thread so that its pages live on
+// the GPU's node.  On a single-node machine (or when sysfs says nothing) both are no-ops.
+static bool gpu_local_cpus(int device, cpu_set_t* set) {
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return false;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    char line[1024] = "";
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {      // "0-15,32-47"
+        int lo = 0, hi = 0;
+        const int k = sscanf(tok, "%d-%d", &lo, &hi);
+        if (k < 1) continue;
+        if (k == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) { CPU_SET(c, set); ++count; }
+    }
+    return count > 0;
+}
+struct HostBind {
+    cpu_set_t old;
+    bool bound = false;
+    explicit HostBind(int device) {
+        if (getenv("AMPSM_NO_NUMA_BIND")) return;
+        cpu_set_t local, want;
+        if (sched_getaffinity(0, sizeof(old), &old) != 0 || !gpu_local_cpus(device, &local)) return;
+        CPU_AND(&want, &old, &local);
+        if (CPU_COUNT(&want) == 0 || CPU_EQUAL(&want, &old)) return;      // nothing to narrow (single node, or an outer binding)
+        bound = sched_setaffinity(0, sizeof(want), &want) == 0;
+    }
+    ~HostBind() {
+        if (bound) sched_setaffinity(0, sizeof(old), &old);
+    }
+};
+
 // ---- host-buffer runner: chunks of frames, two streams, grow-only per-device arenas ---------------------------
 struct Arena {
     unsigned char* base = nullptr;
@@ -119,6 +167,7 @@ static int run_host(int device, long long frames, const std::vector<Field>& fiel
                     const std::vector<std::pair<const void*, size_t>>& shared_in, std::vector<void*>* shared_dev,
                     size_t scratch_per_frame, size_t scratch_fixed, uint64_t* h_counters, const LaunchFn& launch) {
     if (int e = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return e;
+    HostBind bind(device);                       // the copies are issued from a CPU next to the GPU
     DeviceCtx* cx = device_ctx(device);
     std::lock_guard<std::mutex> lk(cx->mu);
     for (int s = 0; s < 2; ++s)
@@ -221,6 +270,33 @@ int ampsm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, i
 
 int64_t ampsm_launch_count(int reset) {
     return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+// Pinned host memory whose pages live on the NUMA node of `device`: allocated and first-touched by a thread bound to the CPUs
+// next to that GPU.  For the buffers handed to the *_detect_host entry points.
+int ampsm_host_alloc(int device, size_t bytes, void** out) {
+    if (!out) { set_error("ampsm_host_alloc: out is NULL"); return AMPSM_EINVAL; }
+    *out = nullptr;
+    if (int e = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return e;
+    HostBind bind(device);
+    void* p = nullptr;
+    if (int e = check_cuda(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc")) return e;
+    memset(p, 0, bytes);                         // first touch from the bound thread
+    *out = p;
+    return 0;
+}
+int ampsm_host_free(void* p) { return p ? check_cuda(cudaFreeHost(p), "cudaFreeHost") : 0; }
+// 1 when the calling thread would be narrowed to CPUs next to `device` (a multi-node machine), 0 otherwise; n_local = their number
+int ampsm_host_numa_info(int device, int* n_local, int* n_allowed) {
+    cpu_set_t cur, local, want;
+    if (n_local) *n_local = 0;
+    if (n_allowed) *n_allowed = 0;
+    if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 0;
+    if (n_allowed) *n_allowed = CPU_COUNT(&cur);
+    if (!gpu_local_cpus(device, &local)) return 0;
+    CPU_AND(&want, &cur, &local);
+    if (n_local) *n_local = CPU_COUNT(&want);
+    return CPU_COUNT(&want) > 0 && !CPU_EQUAL(&want, &cur);
 }
 
 int ampsm_probe_fp32_tflops(int device, double* tflops) { return probe_fp32(device, tflops); }

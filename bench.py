@@ -532,18 +532,23 @@ def main():
 
     # end to end through the C-ABI host entry point: pinned host buffers, H2D/D2H inside the timed region
     fe = min(args.e2e_frames, frames)
-    hH = H[:fe].cpu().pin_memory()
-    hy = y[:fe].cpu().pin_memory()
-    hx = x[:fe].cpu().pin_memory()
-    hl = labels[:fe].cpu().pin_memory()
-    hi = (idx[:fe] - 0).cpu().pin_memory()
+    # pinned host buffers placed on this GPU's NUMA node (ampsm_host_alloc: allocated and first-touched by a thread bound to the
+    # CPUs next to the GPU); the host entry point binds the calling thread the same way while it issues the copies
+    def host_copy(tensor, dtype):
+        hb = _cabi.HostBuffer(local, tuple(tensor.shape), dtype)
+        torch.from_numpy(hb.array).copy_(tensor)
+        return hb
+    hH, hy, hx = host_copy(H[:fe], np.complex64), host_copy(y[:fe], np.complex64), host_copy(x[:fe], np.complex64)
+    hl, hi = host_copy(labels[:fe], np.int64), host_copy(idx[:fe], np.int64)
+    nl, na = ctypes.c_int32(0), ctypes.c_int32(0)
+    numa_narrowed = int(lib.ampsm_host_numa_info(local, ctypes.byref(nl), ctypes.byref(na)))
     prob = _cabi.make_problem(cfg, fe, kernel=args.kernel)
     alpha = _cabi.make_alphabet(cfg)
     hcount = np.zeros(_cabi.NUM_COUNTERS, dtype=np.int64)
 
     def host_step():
-        rc = lib.ampsm_bamp_detect_host(prob, alpha, fe, hH.data_ptr(), cfg.n * cfg.N, hy.data_ptr(), float((NA / NR) / snr), None,
-                                        hx.data_ptr(), hl.data_ptr(), hi.data_ptr(), None, None, None, None, None,
+        rc = lib.ampsm_bamp_detect_host(prob, alpha, fe, hH.ptr, cfg.n * cfg.N, hy.ptr, float((NA / NR) / snr), None,
+                                        hx.ptr, hl.ptr, hi.ptr, None, None, None, None, None,
                                         hcount.ctypes.data, local)
         _cabi.check(rc, "ampsm_bamp_detect_host")
     for _ in range(max(1, args.warmup)):
@@ -567,12 +572,14 @@ def main():
     h2d = fe * (BYTES_PER_FRAME + 16)
     out["e2e"] = {"value": float(e2e_iters[0] / e2e_iters[1]), "unit": "frame-iter/s", "h2d_bytes_per_step": int(h2d),
                   "d2h_bytes_per_step": _cabi.NUM_COUNTERS * 8, "frames_per_step": fe,
-                  "api": "ampsm_bamp_detect_host (C-ABI, pinned host buffers, chunked copies overlapped with the kernel)"}
+                  "api": "ampsm_bamp_detect_host (C-ABI, pinned host buffers from ampsm_host_alloc, chunked copies overlapped with the kernel)",
+                  "numa": {"thread_narrowed_to_gpu_local_cpus": bool(numa_narrowed), "gpu_local_cpus": int(nl.value), "allowed_cpus": int(na.value)}}
     # ---- VAMP leg: the same 64 x 32 16-QAM frames through VAMP (vamp.py:159-191) with per-frame SVD factors resident
     # in HBM (the reference's caller computes them once per channel draw, vamp_model.py:58)
     if args.vamp_frames > 0:
         fv = min(args.vamp_frames, frames)
-        del hH, hy, hx, hl, hi
+        for hb in (hH, hy, hx, hl, hi):
+            hb.free()
         Us, ss, Vs = [], [], []
         for H1 in H[:fv].split(16384):                      # thin SVD through the Hermitian eigenproblem of H H^H (float64)
             Hd = H1.to(torch.complex128)

@@ -22,6 +22,7 @@
 #ifndef AMPSM_B200_H
 #define AMPSM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -244,6 +245,16 @@ int ampsm_loss_count(const ampsm_problem* p, const ampsm_alphabet* a, int64_t fr
 #define AMPSM_SHRINK_SW_OOK 2
 int ampsm_shrink(int kind, const ampsm_alphabet* a, double P0, double Ps, int64_t elems, int32_t M, const void* r,
                  const float* cov, int64_t cov_stride, void* out_c, float* out_f, double* der_sum, void* stream);
+
+/*
+ * NUMA placement of the host entry points (*_detect_host).  They pin the calling thread, for the duration of the call, to the
+ * CPUs next to the GPU (sysfs local_cpulist of its PCI device; AMPSM_NO_NUMA_BIND=1 disables it).  ampsm_host_alloc returns
+ * pinned host memory first-touched from such a thread, so that its pages live on the GPU's node: hand those buffers to the
+ * host entry points.  ampsm_host_numa_info: 1 when binding narrows the thread's CPU set (a multi-node machine), else 0.
+ */
+int ampsm_host_alloc(int device, size_t bytes, void** out);
+int ampsm_host_free(void* p);
+int ampsm_host_numa_info(int device, int* n_local_cpus, int* n_allowed_cpus);
 
 /*
  * Measurement helpers (bench.py): FP32 FFMA throughput of the device in TFLOP/s (the roofline denominator for

@@ -104,7 +104,17 @@ def run_bamp(name, args, kwargs, snrs_db, frames, seed, matrix='channel', taps_o
     save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, matrix=matrix, seed=seed, alg='bamp'))
 
 
-def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False):
+def exp_corr_root(m, rho):
+    """Hermitian square root of the exponential correlation matrix R[i, j] = rho^|i-j| (float64)."""
+    i = np.arange(m)
+    w, V = np.linalg.eigh(rho ** np.abs(i[:, None] - i[None, :]).astype(np.float64))
+    return (V * np.sqrt(np.clip(w, 0, None))) @ V.T
+
+
+def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False, kronecker=None):
+    """kronecker = (rho_r, rho_t): BASELINE config 5 -- the channel is H = Rr^(1/2) G Rt^(1/2) with G the reference's own
+    i.i.d. draw (Channel.generate_channel, CN(0, 1/Nr)) and exponential correlation on both sides; the reference has no
+    correlated generator, its VAMP is fed torch.linalg.svd(H) exactly as vamp_model.py:56-61 does."""
     c = cfg(*args, **kwargs)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -115,7 +125,11 @@ def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False):
     for snr_db in snrs_db:
         snr = 10 ** (snr_db / 10)
         for _ in range(frames):
-            _, A = ch.generate_as_sparc()
+            if kronecker:
+                G = ch.generate_channel().numpy().astype(np.complex128)
+                A = torch.tensor(exp_corr_root(n, kronecker[0]) @ G @ exp_corr_root(N, kronecker[1]), dtype=torch.complex64)
+            else:
+                _, A = ch.generate_as_sparc()
             U, s, Vh = torch.linalg.svd(A, full_matrices=False)
             x, sym, i = da.generate_message()
             y = A @ x + ch.awgn(snr)
@@ -145,7 +159,7 @@ def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False):
     F = len(out['U'])
     xm32 = [np.asarray(v).astype(np.complex64) for v in out['xmap']]
     bl, gidx = batch_loss((args, kwargs), F, xm32, out['xmmse'], out['x'], out['sym'], out['idx'], N)
-    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='vamp', double=double))
+    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='vamp', double=double, kronecker=kronecker))
 
 
 def run_scamp(name, args, kwargs, snrs_db, frames, seed, res):
@@ -290,6 +304,11 @@ if __name__ == "__main__":
         run_vamp('vamp_c2', (64, 1, 32, 1, 1, '16QAM'), {}, [5, 10, 15, 20], 4, seed=8)
     if want('vamp_c2_na4'):
         run_vamp('vamp_c2_na4', (64, 4, 32, 1, 1, 'QPSK'), {}, [2, 8], 4, seed=9)
+    # C5: VAMP on Kronecker-correlated (ill-conditioned) channels, rho = 0.7 and 0.9 on both sides, 64 x 32 QPSK
+    if want('vamp_c5_rho07'):
+        run_vamp('vamp_c5_rho07', (64, 1, 32, 1, 1, 'QPSK'), {}, [6, 12], 6, seed=31, kronecker=(0.7, 0.7))
+    if want('vamp_c5_rho09'):
+        run_vamp('vamp_c5_rho09', (64, 1, 32, 1, 1, 'QPSK'), {}, [10, 18], 6, seed=32, kronecker=(0.9, 0.9))
     # 'random' mode (i.i.d. prior, random_denoiser bamp.py:79-97, random_decision loss.py:252-280; B=1 only in the reference)
     if want('bamp_random'):
         run_bamp('bamp_random', (32, 4, 16, 1, 1, 'QPSK'), dict(mode='random'), [0, 6, 12], 8, seed=10)

@@ -29,7 +29,7 @@ def test_bamp_oracle_matches_reference(name):
     assert decision_mismatch_frames(cfg, r["xmap"], g["xmap"]).size == 0
 
 
-@pytest.mark.parametrize("name", BAMP_CASES + ["vamp_c3", "vamp_isi", "vamp_c2", "vamp_c2_na4", "scamp_small"])
+@pytest.mark.parametrize("name", BAMP_CASES + ["vamp_c3", "vamp_isi", "vamp_c2", "vamp_c2_na4", "vamp_c5_rho07", "vamp_c5_rho09", "scamp_small"])
 def test_loss_oracle_matches_reference_per_frame(name):
     """Reference Loss with batch=1 per frame (the stored `loss` rows) == oracle counters -> rates."""
     g = load_golden(name)
@@ -45,7 +45,7 @@ def test_loss_oracle_matches_reference_per_frame(name):
             assert abs(got[k] - want[k]) <= tol, (name, f, k, got[k], want[k])
 
 
-@pytest.mark.parametrize("name", ["bamp_c1", "bamp_c2", "bamp_isi", "vamp_c3", "vamp_isi", "vamp_c2", "vamp_c2_na4", "scamp_small"])
+@pytest.mark.parametrize("name", ["bamp_c1", "bamp_c2", "bamp_isi", "vamp_c3", "vamp_isi", "vamp_c2", "vamp_c2_na4", "vamp_c5_rho07", "vamp_c5_rho09", "scamp_small"])
 def test_loss_oracle_matches_reference_batched(name):
     """Reference Loss evaluated once on all frames stacked (B = frames): pins the B-dependent index-bit truncation."""
     g = load_golden(name)
@@ -74,7 +74,7 @@ def test_loss_only_goldens(name):
 
 
 @pytest.mark.parametrize("name,double", [("vamp_c3", False), ("vamp_isi", False), ("vamp_c2", False), ("vamp_c2_na4", False),
-                                         ("vamp_c3_c128", True)])
+                                         ("vamp_c5_rho07", False), ("vamp_c5_rho09", False), ("vamp_c3_c128", True)])
 def test_vamp_oracle_matches_reference(name, double):
     g = load_golden(name)
     cfg = config_from_meta(g["meta"])
@@ -85,6 +85,8 @@ def test_vamp_oracle_matches_reference(name, double):
     # complex128: var is rounded to float32 every iteration (vamp.py:119), so a summation-order change moves it by one
     # float32 ulp (6e-8) -- the 1e-10 of the north star is reachable for the linear stage only
     tight = 5e-7 if double else 1e-4
+    if name.startswith("vamp_c5"):
+        tight = 1e-3        # one-section frames at high SNR: sigma2_tilde is posterior tail mass (1e-7 of the unit symbol) from the first iteration on
     s2t, varm = r["traj"]["sigma2"].T, r["traj"]["var"].T
     # one-section 16-QAM frames (vamp_c2): the posterior collapses in the first iteration, so sigma2_tilde is tail mass
     # -- chaotic at the 1e-3 .. 1e-1 level -- from iteration 2 on already
