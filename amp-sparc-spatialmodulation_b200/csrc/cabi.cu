@@ -418,6 +418,10 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
         set_error("VAMP register-resident kernel supports complex64, exp_f64=0, shift_mode=0 only");
         return AMPSM_ENOFIT;
     }
+    if (is_double && p->kernel != 1) {                       // complex128 64 x 128 factors: register-resident DFMA kernel
+        const int rc = launch_vamp_dbl(k, (cudaStream_t)stream);
+        if (rc != AMPSM_ENOFIT) return rc;
+    }
     return launch_vamp_generic(k, is_double != 0, p->exp_f64 != 0, (cudaStream_t)stream);
 }
 

@@ -116,7 +116,8 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENO
 int launch_bamp_pair(const BampArgs& a, cudaStream_t stream);       // two warps per frame (64 x 32 shapes), else AMPSM_ENOFIT
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
 int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64 32 x 64 factors, else AMPSM_ENOFIT
-int launch_vamp_quad(const VampArgs& a, cudaStream_t stream);       // complex64 64 x 128 factors (four warps per frame), else AMPSM_ENOFIT
+int launch_vamp_quad(const VampArgs& a, cudaStream_t stream);
+int launch_vamp_dbl(const VampArgs& a, cudaStream_t stream);        // complex128 64 x 128 factors in registers (FP64 pipe), else AMPSM_ENOFIT
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);
 long long scamp_taps_workspace_bytes(const Geom& g, long long frames, int Lh);   // AMPSM_ENOFIT when the shape has no structured path

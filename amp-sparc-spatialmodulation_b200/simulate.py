@@ -21,6 +21,7 @@ SCAMP shares one design matrix per call and keeps the reference's own ``Channel.
 import argparse
 import json
 import os
+import time
 
 import numpy as np
 import torch
@@ -168,17 +169,21 @@ class MonteCarlo:
         out = []
         for pi, EbN0dB in enumerate(np.arange(start, final + step, step)):
             SNRdB = EbN0dB + 10 * np.log10(self.rate)
-            c = self.run_point(float(EbN0dB), pi)
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            c = self.run_point(float(EbN0dB), pi)              # ends with the all-reduce and a host read: synchronised
+            seconds = time.perf_counter() - t0
             self.loss.dump()
             self.loss.loss = {}
             self.loss.record(c, c['iters'] / max(c['frames'], 1))
             rates = {k: float(np.asarray(self.loss.loss[k])) for k in self.loss.keys}
             point = dict(EbN0dB=float(EbN0dB), SNRdB=float(SNRdB), T=c['iters'] / max(c['frames'], 1), frames=c['frames'],
-                         nan_frames=c['nan_frames'], **rates)
+                         nan_frames=c['nan_frames'], seconds=seconds, frames_per_s=c['frames'] / seconds, ranks=self.world, **rates)
             out.append(point)
             if self.rank == 0:
                 print(f"EbN0dB={EbN0dB:g} frames={c['frames']} FER={rates['fer']:.3e} ier={rates['ier']:.3e} "
-                      f"ber={rates['ber']:.3e} iter={point['T']:.2f}", flush=True)
+                      f"ber={rates['ber']:.3e} iter={point['T']:.2f} {seconds:.2f} s ({c['frames'] / seconds:.3e} frames/s on {self.world} rank(s), "
+                      f"generation + SVD + detection)", flush=True)
                 if self.path:
                     os.makedirs(self.path, exist_ok=True)
                     self.loss.export(SNRdB, float(EbN0dB), self.path)
@@ -247,6 +252,9 @@ def main(argv=None):
     pts = mc.simulate(final=a.final, start=a.start, step=a.step)
     if mc.rank == 0:
         print(json.dumps(pts))
+        if a.path:
+            with open(os.path.join(a.path, "sweep_record.json"), "w") as f:
+                json.dump(dict(args=vars(a), world_size=world, points=pts), f, indent=1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -576,3 +576,32 @@ def test_scamp_structured_path_matches_dense_path(shape, F, trunc, alphabet, mon
     assert np.intersect1d(bad, np.nonzero(conv_np)[0]).size <= max(1, 0.01 * conv_np.sum()), bad
     for k in INT_KEYS:
         assert abs(ca[k] - cb[k]) <= max(8, 0.1 * cb[k]) * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
+
+
+def test_vamp_complex128_register_kernel_matches_generic_double_kernel(monkeypatch):
+    """complex128 factors at BASELINE config 3 (VAMP 128 x 64, Na = 4): the register-resident DFMA kernel (csrc/vamp_dbl.cu)
+    against the generic float64 kernel (Vh in shared memory) on 1500 frames with per-frame factors, plus a shared-factor call:
+    same exit iterations, estimates to 1e-6 (var is rounded to float32 every iteration, vamp.py:119), identical counters."""
+    F = 1500
+    cfg = c3(F)
+    H, y, x, lab, idx = make_frames(cfg, F, 3.0, seed=41)
+    U, s, Vh = torch.linalg.svd(H.to(torch.complex128), full_matrices=False)
+    U, s, Vh, yd = U.contiguous(), s.contiguous(), Vh.contiguous(), y.to(torch.complex128)
+    snr = 10 ** 0.3
+    a = pkg.VAMP(cfg, outputs=True).detect(U, s, Vh, yd, snr, x, lab, idx)
+    monkeypatch.setenv("AMPSM_VAMP_DBL_GENERIC", "1")
+    b = pkg.VAMP(cfg, outputs=True).detect(U, s, Vh, yd, snr, x, lab, idx)
+    monkeypatch.delenv("AMPSM_VAMP_DBL_GENERIC")
+    ca, cb = a.counters_dict(), b.counters_dict()
+    assert ca["frames"] == cb["frames"] == F and ca["nan_frames"] == cb["nan_frames"] == 0
+    ia, ib = a.iters.cpu().numpy(), b.iters.cpu().numpy()
+    assert (ia == ib).mean() > 0.995, (ia == ib).mean()
+    same = torch.as_tensor(ia == ib, device=DEV)
+    d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
+    assert float(d[same].max()) < 1e-5 and float(d.median()) < 1e-7
+    for k in INT_KEYS:
+        assert abs(ca[k] - cb[k]) <= 2 * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
+    sh = pkg.VAMP(cfg, outputs=True).detect(U[0], s[0], Vh[0], yd[:70], snr, x[:70], lab[:70 * cfg.L], idx[:70 * cfg.L])
+    pf = pkg.VAMP(cfg, outputs=True).detect(U[:1].expand(70, -1, -1).contiguous(), s[:1].expand(70, -1).contiguous(),
+                                            Vh[:1].expand(70, -1, -1).contiguous(), yd[:70], snr, x[:70], lab[:70 * cfg.L], idx[:70 * cfg.L])
+    assert torch.equal(sh.xmmse, pf.xmmse)
