@@ -116,6 +116,7 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
                 RT tau = tau_vec ? tau_vec[(base + m) / tau_div] : tau_scalar;
                 if (halve) tau = tau / (RT)2;
                 CT q = cdiv_real(s[base + m], tau);
+#pragma unroll 4
                 for (int k = 0; k < al.K; ++k) {
                     const double x = sm_exponent<true>(q, al, k);
                     smax = (x > smax || x != x) ? x : smax;   // NaN sticks
@@ -136,7 +137,8 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
             if (halve) tau = tau / (RT)2;
             CT q = cdiv_real(s[base + m], tau);
             E s0 = 0, s1r = 0, s1i = 0;
-            for (int k = 0; k < al.K; ++k) {
+#pragma unroll 4
+            for (int k = 0; k < al.K; ++k) {       // independent exponentials: unrolled so that their latency chains overlap
                 E e = exp_shifted<EXP64>(sm_exponent<true>(q, al, k), smax);
                 s0 += e;
                 if constexpr (EXP64) {
@@ -163,6 +165,7 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
                 if (halve) tau = tau / (RT)2;
                 CT q = cdiv_real(s[base + m], tau);
                 double spread = 0.0;
+#pragma unroll 4
                 for (int k = 0; k < al.K; ++k) {
                     E e = exp_shifted<EXP64>(sm_exponent<true>(q, al, k), smax);
                     const double dr = xr - al.re[k], di = xi - al.im[k];

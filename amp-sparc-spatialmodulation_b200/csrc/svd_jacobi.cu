@@ -1,7 +1,8 @@
 // Batched thin SVD of wide complex64 matrices by one-sided (Hestenes) Jacobi: ONE WARP PER MATRIX, matrix in shared memory.
 //
 // Replaces the caller-side `torch.linalg.svd(A, full_matrices=False)` of the reference's VAMP driver
-// (vamp_model.py:56-58) for per-frame channel matrices: H [n][N] (n <= 32 rows, n <= N) -> U [n][n], s [n] (descending),
+// (vamp_model.py:56-58) for per-frame channel matrices: H [n][N] (n <= 32 rows here, 33 .. 64 in the one-CTA-per-matrix kernel
+// further down; n <= N) -> U [n][n], s [n] (descending),
 // Vh [n][N] with H = U diag(s) Vh.  VAMP only ever uses V f(S) V^H and V S U^H (vamp.py:22,67,72), so the phases of the
 // singular-vector pairs are free; they differ from LAPACK's.
 //
@@ -388,6 +389,200 @@ int launch_svd_nc(const float2* H, long long frames, int n, float2* U, float* S,
                  : launch_svd_nc_b<NC, WITHY, false>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream);
 }
 
+
+// ---- 33 .. 64 rows (BASELINE config 3: 64 x 128): ONE CTA OF 128 THREADS PER MATRIX --------------------------------------------
+// Same method, 64 tournament positions: 63 steps of 32 disjoint pairs per sweep, FOUR lanes per pair -- lane (j, h) takes the
+// columns 16 (c >> 2) + 4 h + (c & 3) of both rows (with rows one apart in neighbouring pairs and an odd row stride the 16 lanes
+// of a half-warp hit 16 distinct bank pairs), forms its share of the three inner products, combines them with its three partners
+// by two shuffle rounds and rotates in registers.  The pairs of a step are disjoint, so the four warps only meet at one CTA
+// barrier per step.  W (64 x 129 complex64 = 66 KiB) + Q (64 x 65) or the rotated vector y live in shared memory.
+constexpr int kSvd64Rows = 64, kSvd64Threads = 128, kSvd64MaxSweeps = 20;
+template <int NC, bool WITHY>
+struct Svd64Shape {
+    static constexpr int wstride = NC + 1;
+    static constexpr int qstride = kSvd64Rows + 1;
+    static constexpr int q_elems = WITHY ? kSvd64Rows : kSvd64Rows * qstride;
+    static constexpr int bytes = (kSvd64Rows * wstride + q_elems) * 8 + 2 * kSvd64Rows * 4 + 16;   // + perm, 1/s, flags
+};
+template <int NC>
+__device__ __forceinline__ constexpr int svd64_col(int c, int h) { return 16 * (c >> 2) + 4 * h + (c & 3); }
+
+template <int NC, bool WITHY>
+__global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float2* __restrict__ H, long long frames, int n, float2* __restrict__ U,
+                                                                    float* __restrict__ S, float2* __restrict__ Vh, int* __restrict__ sweeps_out,
+                                                                    const float2* __restrict__ yin, float2* __restrict__ yrot) {
+    using Sh = Svd64Shape<NC, WITHY>;
+    constexpr int QC = NC / 4, QQ = kSvd64Rows / 4;            // columns of W / Q per lane
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* W = reinterpret_cast<float2*>(smem);
+    float2* Q = W + kSvd64Rows * Sh::wstride;
+    int* perm = reinterpret_cast<int*>(Q + Sh::q_elems);
+    float* sinv = reinterpret_cast<float*>(perm + kSvd64Rows);
+    const int tid = threadIdx.x;
+    const int j = tid >> 2, h = tid & 3;
+
+    for (long long f = blockIdx.x; f < frames; f += gridDim.x) {
+        const float2* Hf = H + f * (long long)n * NC;
+        for (int e = tid; e < kSvd64Rows * NC; e += kSvd64Threads) {
+            const int r = e / NC, c = e - r * NC;
+            W[r * Sh::wstride + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
+        }
+        if constexpr (WITHY) {
+            if (tid < kSvd64Rows) Q[tid] = tid < n ? __ldg(yin + f * n + tid) : make_float2(0.f, 0.f);
+        } else {
+            for (int e = tid; e < kSvd64Rows * kSvd64Rows; e += kSvd64Threads) {
+                const int r = e >> 6, c = e & 63;
+                Q[r * Sh::qstride + c] = make_float2(r == c ? 1.f : 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+
+        int sweeps = 0;
+        for (; sweeps < kSvd64MaxSweeps; ++sweeps) {
+            bool rotated = false;
+            for (int step = 0; step < kSvd64Rows - 1; ++step) {
+                int p, q;                                      // tournament pairing: position 63 stays, the others rotate
+                if (j == 0) {
+                    p = kSvd64Rows - 1;
+                    q = step;
+                } else {
+                    p = step + j;
+                    if (p >= kSvd64Rows - 1) p -= kSvd64Rows - 1;
+                    q = step - j;
+                    if (q < 0) q += kSvd64Rows - 1;
+                }
+                float2* wa = W + p * Sh::wstride;
+                float2* wb = W + q * Sh::wstride;
+                float2 a[QC], b[QC];
+                float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
+#pragma unroll
+                for (int c = 0; c < QC; ++c) {
+                    a[c] = wa[svd64_col<NC>(c, h)];
+                    b[c] = wb[svd64_col<NC>(c, h)];
+                    alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
+                    beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
+                    gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
+                    gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+                    beta += __shfl_xor_sync(0xffffffffu, beta, o);
+                    gr += __shfl_xor_sync(0xffffffffu, gr, o);
+                    gi += __shfl_xor_sync(0xffffffffu, gi, o);
+                }
+                const float g2 = gr * gr + gi * gi;
+                const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
+                if (rot) {
+                    const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
+                    const float pr = gr * ginv, pi = -gi * ginv;                    // e^{-i phi} = conj(gamma) / |gamma|
+                    const float zeta = (beta - alpha) * (0.5f * ginv);
+                    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+                    const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
+                    const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
+                    // a' = c a - (s p) b ; b' = s a + (c p) b
+#pragma unroll
+                    for (int c = 0; c < QC; ++c) {
+                        const float2 x = a[c], y = b[c];
+                        wa[svd64_col<NC>(c, h)] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                        wb[svd64_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                    }
+                    if constexpr (WITHY) {
+                        if (h == 0) {
+                            const float2 x = Q[p], y = Q[q];
+                            Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        }
+                    } else {
+                        float2* qa = Q + p * Sh::qstride;
+                        float2* qb = Q + q * Sh::qstride;
+#pragma unroll
+                        for (int c = 0; c < QQ; ++c) {
+                            const int cq = svd64_col<kSvd64Rows>(c, h);
+                            const float2 x = qa[cq], y = qb[cq];
+                            qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        }
+                    }
+                    rotated = true;
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(rotated ? 1 : 0)) {
+                ++sweeps;
+                break;
+            }
+        }
+
+        // ---- singular values = row norms of W (two threads per row), descending order by rank counting
+        {
+            const int r = tid >> 1, half = tid & 1;
+            float nrm = 0.f;
+            for (int c = half; c < NC; c += 2) {
+                const float2 w = W[r * Sh::wstride + c];
+                nrm = fmaf(w.x, w.x, fmaf(w.y, w.y, nrm));
+            }
+            nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
+            if (half == 0) sinv[r] = sqrtf(nrm);                       // sinv holds s for the moment
+        }
+        __syncthreads();
+        float sv = 0.f;
+        int rank = 0;
+        if (tid < kSvd64Rows) {
+            sv = sinv[tid];
+            for (int o = 0; o < kSvd64Rows; ++o) {
+                const float other = sinv[o];
+                rank += (other > sv) || (other == sv && o < tid);
+            }
+        }
+        __syncthreads();
+        if (tid < kSvd64Rows) {
+            perm[rank] = tid;
+            sinv[rank] = sv > 0.f ? 1.0f / sv : 0.f;
+            if (rank < n) S[f * n + rank] = sv;
+        }
+        __syncthreads();
+        // Vh[k][:] = W[row_k][:] / s_k, U[i][k] = conj(Q[row_k][i]): coalesced stores
+        for (int e = tid; e < n * NC; e += kSvd64Threads) {
+            const int k = e / NC, c = e - k * NC;
+            const float2 w = W[perm[k] * Sh::wstride + c];
+            const float sc = sinv[k];
+            Vh[(f * n + k) * (long long)NC + c] = make_float2(w.x * sc, w.y * sc);
+        }
+        if constexpr (WITHY) {
+            if (tid < n) yrot[f * n + tid] = Q[perm[tid]];
+        } else {
+            for (int e = tid; e < n * n; e += kSvd64Threads) {
+                const int i = e / n, k = e - i * n;
+                const float2 qv = Q[perm[k] * Sh::qstride + i];
+                U[(f * n + i) * (long long)n + k] = make_float2(qv.x, -qv.y);
+            }
+        }
+        if (sweeps_out && tid == 0) sweeps_out[f] = sweeps;
+        __syncthreads();
+    }
+}
+
+template <int NC, bool WITHY>
+int launch_svd64(const float2* H, long long frames, int n, float2* U, float* S, float2* Vh, int* sweeps, const float2* y, float2* yrot,
+                 cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = svd_jacobi64_kernel<NC, WITHY>;
+    const size_t smem = Svd64Shape<NC, WITHY>::bytes;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(svd64)")) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSvd64Threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > frames) grid = frames;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kSvd64Threads, smem, stream>>>(H, frames, n, U, S, Vh, sweeps, y, yrot);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "svd_jacobi64_kernel launch");
+}
+
 __global__ void identity_kernel(float2* I, int n) {
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) I[e] = make_float2((e / n) == (e % n) ? 1.f : 0.f, 0.f);
 }
@@ -397,8 +592,16 @@ __global__ void identity_kernel(float2* I, int n) {
 // y == nullptr: U, s, Vh.  y != nullptr: s, Vh and yrot = U^H y (U is not formed; see WITHY).
 int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, const float2* y,
                       float2* yrot, cudaStream_t stream) {
-    if (n < 1 || n > kSvdRows || N < n) {
-        set_error("batched SVD: needs 1 <= n <= 32 rows and n <= N columns (got %d x %d)", n, N);
+    if (n < 1 || n > kSvd64Rows || N < n) {
+        set_error("batched SVD: needs 1 <= n <= 64 rows and n <= N columns (got %d x %d)", n, N);
+        return AMPSM_ENOFIT;
+    }
+    if (n > kSvdRows) {                                        // 33 .. 64 rows: one CTA per matrix
+        if (N == 64) return y ? launch_svd64<64, true>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream)
+                              : launch_svd64<64, false>(H, frames, n, U, S, Vh, sweeps, nullptr, nullptr, stream);
+        if (N == 128) return y ? launch_svd64<128, true>(H, frames, n, U, S, Vh, sweeps, y, yrot, stream)
+                               : launch_svd64<128, false>(H, frames, n, U, S, Vh, sweeps, nullptr, nullptr, stream);
+        set_error("batched SVD with more than 32 rows: column counts 64 and 128 are instantiated (got %d)", N);
         return AMPSM_ENOFIT;
     }
 #define AMPSM_SVD_NC(NCC) \

@@ -138,8 +138,8 @@ def test_vamp_matches_reference_goldens(name, double, exp):
         tight = 1e-3        # sigma2_tilde is posterior tail mass from the first iteration on (tests/test_oracle_golden.py)
     # (vamp_c2: sigma2_tilde is tail mass from iteration 2 on -- see tests/test_oracle_golden.py)
     for it in range(1 if name == "vamp_c2" else 2):
-        assert np.abs(s2t[:, it] - g["sigma2t"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["sigma2t"][:, it]).max()
-        assert np.abs(varm[:, it] - g["varm"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["varm"][:, it]).max()
+        assert np.abs(s2t[:, it] - g["sigma2t"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["sigma2t"][:, it]).max() + 1e-12
+        assert np.abs(varm[:, it] - g["varm"][:, it]).max() <= max(tight, 2e-7) * np.abs(g["varm"][:, it]).max() + 1e-12
     if double:
         assert (iters == g["iters"]).all()
         assert np.abs(xmmse - g["xmmse"]).max() < 1e-6

@@ -304,11 +304,11 @@ def test_vamp_fast_and_generic_kernels_agree(alphabet, Na, snr_db):
     assert fixed["iters"] == 20 * F
 
 
-@pytest.mark.parametrize("n,N", [(32, 64), (24, 64), (8, 16), (4, 8), (32, 32)])
+@pytest.mark.parametrize("n,N", [(32, 64), (24, 64), (8, 16), (4, 8), (32, 32), (64, 128), (48, 64), (64, 64), (40, 128)])
 def test_batched_jacobi_svd_reconstructs_and_matches_lapack(n, N):
     """ampsm_svd_batched: H = U diag(s) Vh to float32 accuracy, orthonormal factors, singular values equal to LAPACK's
     (torch.linalg.svdvals in float64), descending order; an ill-conditioned (Kronecker-correlated) batch included."""
-    F = 3000
+    F = 3000 if n <= 32 else 600                       # more than 32 rows: the one-CTA-per-matrix kernel (64 x 128 = BASELINE config 3)
     g = torch.Generator(device=DEV).manual_seed(4)
     H = torch.view_as_complex(torch.randn(F, n, N, 2, device=DEV, generator=g) * float(np.sqrt(0.5 / n)))
     # second half: exponential correlation on both sides (rho = 0.9): condition numbers of 1e2 .. 1e3
@@ -321,13 +321,14 @@ def test_batched_jacobi_svd_reconstructs_and_matches_lapack(n, N):
     U, s, Vh, sw = pkg.svd_batched(H, return_sweeps=True)
     rec = (U * s.unsqueeze(-2).to(torch.complex64)) @ Vh
     scale = H.abs().amax(dim=(1, 2))
-    assert float(((rec - H).abs().amax(dim=(1, 2)) / scale).max()) < 2e-5
+    tol = 2e-5 if n <= 32 else 6e-5                    # float32 through ~200 (n <= 32) / ~600 (n = 64) rotations per row
+    assert float(((rec - H).abs().amax(dim=(1, 2)) / scale).max()) < tol
     eye_n = torch.eye(n, dtype=torch.complex64, device=DEV)
-    assert float((U.mH @ U - eye_n).abs().max()) < 2e-5 and float((Vh @ Vh.mH - eye_n).abs().max()) < 2e-5
+    assert float((U.mH @ U - eye_n).abs().max()) < tol and float((Vh @ Vh.mH - eye_n).abs().max()) < tol
     ref = torch.linalg.svdvals(H.to(torch.complex128))
-    assert float(((s.double() - ref).abs() / ref[:, :1]).max()) < 3e-5      # float32 through ~200 rotations per row
+    assert float(((s.double() - ref).abs() / ref[:, :1]).max()) < 1.5 * tol
     assert bool((s[:, :-1] >= s[:, 1:]).all())
-    assert 2 <= int(sw.min()) and int(sw.max()) <= 14
+    assert 2 <= int(sw.min()) and int(sw.max()) <= (14 if n <= 32 else 19)
 
 
 def test_vamp_from_channel_equals_factor_entry_point():
@@ -346,6 +347,26 @@ def test_vamp_from_channel_equals_factor_entry_point():
     assert (ia == ib).mean() > 0.97
     for k in INT_KEYS:
         assert abs(ca[k] - cb[k]) <= max(4, 2e-3 * F) * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
+    d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
+    assert float(d.median()) < 1e-5
+
+
+def test_vamp_from_channel_config3_equals_factor_entry_point():
+    """BASELINE config 3 from the channel matrices: 64 x 128 Jacobi SVD (one CTA per matrix) + the four-warps-per-frame VAMP
+    kernel in one call, against float64 eigh factors fed to the factor entry point."""
+    F = 3000
+    cfg = c3(F)
+    H, y, x, lab, idx = make_frames(cfg, F, 4.0, seed=33)
+    snr = 10 ** 0.4
+    U, s, Vh = svd_factors(H)
+    a = pkg.VAMP(cfg, outputs=True).detect(U, s, Vh, y, snr, x, lab, idx)
+    b = pkg.VAMP(cfg, outputs=True).detect_from_channel(H, y, snr, x, lab, idx)
+    ca, cb = a.counters_dict(), b.counters_dict()
+    assert cb["frames"] == F and cb["nan_frames"] == 0
+    ia, ib = a.iters.cpu().numpy(), b.iters.cpu().numpy()
+    assert (np.abs(ia - ib) <= 1).mean() > 0.95, (np.abs(ia - ib) <= 1).mean()
+    for k in INT_KEYS:
+        assert abs(ca[k] - cb[k]) <= max(6, 3e-3 * F * cfg.L) * (4 if k.endswith("bit_err") else 1), (k, ca[k], cb[k])
     d = (a.xmmse - b.xmmse).abs().reshape(F, -1).amax(dim=1)
     assert float(d.median()) < 1e-5
 

@@ -91,8 +91,8 @@ def test_vamp_oracle_matches_reference(name, double):
     # one-section 16-QAM frames (vamp_c2): the posterior collapses in the first iteration, so sigma2_tilde is tail mass
     # -- chaotic at the 1e-3 .. 1e-1 level -- from iteration 2 on already
     for it in range(1 if name == "vamp_c2" else 2):
-        assert np.abs(s2t[:, it] - g["sigma2t"][:, it]).max() <= tight * np.abs(g["sigma2t"][:, it]).max()
-        assert np.abs(varm[:, it] - g["varm"][:, it]).max() <= tight * np.abs(g["varm"][:, it]).max()
+        assert np.abs(s2t[:, it] - g["sigma2t"][:, it]).max() <= tight * np.abs(g["sigma2t"][:, it]).max() + 1e-12
+        assert np.abs(varm[:, it] - g["varm"][:, it]).max() <= tight * np.abs(g["varm"][:, it]).max() + 1e-12
     if double:
         assert (r["iters"] == g["iters"]).all()
         assert np.abs(r["xmmse"] - g["xmmse"]).max() < 1e-6
