@@ -130,7 +130,7 @@ def make_problem(config, frames, *, R=0, early_exit=True, shift='section', exp='
     p.decision = {'sparc': 0, 'segmented': 1, 'random': 2}[config.mode]      # decision rule and, for 'random', the i.i.d. prior
     count = config.Lin * max(int(frames), 1) * config.Na
     p.index_bits_kept = int(math.ceil(math.log2(count))) if count > 0 else 0
-    p.kernel = {'auto': 0, 'generic': 1, 'fast': 2, 'pair': 3}[kernel]
+    p.kernel = {'auto': 0, 'generic': 1, 'fast': 2}[kernel]
     p.frame_base = int(frame_base)
     return p
 

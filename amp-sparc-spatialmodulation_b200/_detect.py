@@ -34,7 +34,7 @@ class Detector(nn.Module):
     shift      : 'section' (per-section soft-max shift, finite everywhere) or 'reference' (frame-global max|x| in
                  float64 as bamp.py:70 -- reproduces the reference's NaN frames)
     exp        : 'f32' or 'f64' arithmetic for the denoiser exponents (the reference uses float64)
-    kernel     : 'auto' | 'generic' | 'fast' (one warp per frame) | 'pair' (two warps per frame, 64 x 32 shapes)
+    kernel     : 'auto' | 'generic' | 'fast' (the register-resident kernels; raises when the shape has none)
     trajectory : also return per-iteration {tau, var, mse} means (costs a few block reductions per iteration)
     outputs    : materialise xmap / xmmse in HBM (needed by ``last``); the counters never need them
     """

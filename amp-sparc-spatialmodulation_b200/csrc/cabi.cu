@@ -322,15 +322,11 @@ int ampsm_bamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     k.xmap = (float2*)xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->kernel != 1 && !p->exp_f64 && p->shift_mode == 0 && p->decision != 2) {
-        if (p->kernel == 3 || (p->kernel == 0 && getenv("AMPSM_PAIR"))) {   // measured slower than the one-warp kernel: opt-in
-            const int rc = launch_bamp_pair(k, st);
-            if (rc != AMPSM_ENOFIT || p->kernel == 3) return rc;
-        }
         const int rc = launch_bamp_fast(k, st);
         if (rc != AMPSM_ENOFIT) return rc;
         if (p->kernel == 2) return rc;
-    } else if (p->kernel == 2 || p->kernel == 3) {
-        set_error("BAMP register-resident kernels support exp_f64=0, shift_mode=0 only");
+    } else if (p->kernel == 2) {
+        set_error("BAMP register-resident kernel supports exp_f64=0, shift_mode=0 only");
         return AMPSM_ENOFIT;
     }
     return launch_bamp_generic(k, p->exp_f64 != 0, st);

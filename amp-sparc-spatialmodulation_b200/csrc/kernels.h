@@ -113,7 +113,6 @@ struct ShrinkArgs {
 
 int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
-int launch_bamp_pair(const BampArgs& a, cudaStream_t stream);       // two warps per frame (64 x 32 shapes), else AMPSM_ENOFIT
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
 int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64 32 x 64 factors, else AMPSM_ENOFIT
 int launch_vamp_quad(const VampArgs& a, cudaStream_t stream);

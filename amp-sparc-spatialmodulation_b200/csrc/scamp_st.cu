@@ -446,8 +446,11 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                                     }
                                 }
                             }
-                            // four rows in lock step, phase by phase: their dependent chains (shuffle reductions, float64 exponent
-                            // products, MUFU) interleave, which is what keeps the one epilogue warp of a scheduler busy
+                            // rows of frames that met the exit test are frozen: a block of four rows belongs to one frame when
+                            // 4 | Lin, so whole blocks drop out as the batch converges
+                            if (row_f[rbase + r4] < 0 && row_f[rbase + r4 + 1] < 0 && row_f[rbase + r4 + 2] < 0 && row_f[rbase + r4 + 3] < 0) continue;
+                            // four rows in lock step, phase by phase: their dependent chains (shuffle reductions, exponent sums,
+                            // MUFU) interleave, which is what keeps the two epilogue warps of a scheduler busy
                             bool live[4];
                             long long at[4];
                             float tau[4];

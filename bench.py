@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--snr-db", type=float, default=15.0)
     ap.add_argument("--e2e-frames", type=int, default=1 << 17)
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast", "pair"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--vamp-frames", type=int, default=1 << 18, help="frames per GPU of the VAMP leg (0 = skip it)")
     ap.add_argument("--c3-frames", type=int, default=1 << 14, help="frames per GPU of the config-3 VAMP leg (128 x 64; 0 = skip it)")
     ap.add_argument("--c3-snr-db", type=float, default=2.0)

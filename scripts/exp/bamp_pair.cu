@@ -1,3 +1,5 @@
+// KEPT AS EVIDENCE, NOT BUILT: measured 15 % slower than the one-warp kernel on B200; it was removed from the
+// product library in round 2.  To try it again: copy it to amp-sparc-spatialmodulation_b200/csrc/ and restore its dispatch in cabi.cu.
 // Register-resident BAMP kernel, TWO WARPS PER FRAME (one 64-thread CTA per frame, 64 x 32 shapes).
 //
 // bamp_fast.cu keeps a whole 32 x 64 channel matrix in the registers of ONE warp (192 registers of tile per lane),

@@ -43,7 +43,7 @@ def ints(c):
     return {k: c[k] for k in INT_KEYS}
 
 
-@pytest.mark.parametrize("fast", ["pair", "fast"])
+@pytest.mark.parametrize("fast", ["fast"])
 def test_fast_and_generic_kernels_agree_on_every_count_c2(fast):
     """Two independent kernels (register-resident FFMA2 + separable denoiser vs shared-memory float64-exponent one)
     must take identical hard decisions on 40k frames per SNR point."""
@@ -102,12 +102,12 @@ def test_high_snr_qpsk_decodes_every_frame():
     F = 20000
     cfg = c2(F, alphabet='QPSK')
     H, y, x, lab, idx = make_frames(cfg, F, 30.0, seed=3)
-    for kernel in ('pair', 'fast', 'generic'):
+    for kernel in ('fast', 'generic'):
         c = pkg.BAMP(cfg, kernel=kernel, outputs=False).detect(H, y, 10 ** 3.0, x, lab, idx).counters_dict()
         assert c["frame_err"] == 0 and c["index_bit_err"] == 0 and c["symbol_bit_err"] == 0 and c["nan_frames"] == 0
 
 
-@pytest.mark.parametrize("fast,Na,alphabet", [("pair", 4, "QPSK"), ("fast", 4, "QPSK"), ("pair", 2, "QPSK"), ("fast", 2, "QPSK"),
+@pytest.mark.parametrize("fast,Na,alphabet", [("fast", 4, "QPSK"), ("fast", 2, "QPSK"),
                                               ("fast", 4, "16QAM")])
 def test_multi_section_fast_shape_matches_generic(fast, Na, alphabet):
     """64 x 32, QPSK, Na = 4 / 2 (sections of 16 / 32 antennas: sub-warp and whole-warp section reductions)."""
@@ -134,7 +134,7 @@ def test_multi_section_fast_shape_matches_generic(fast, Na, alphabet):
 def test_shared_matrix_and_edge_frame_counts():
     cfg = c2(7)
     H, y, x, lab, idx = make_frames(cfg, 7, 12.0, seed=2, shared_H=True)
-    for kernel in ('pair', 'fast', 'generic'):
+    for kernel in ('fast', 'generic'):
         d = pkg.BAMP(pkg.Config(64, 1, 32, 1, 1, batch=7, generator_mode='sparc', alphabet='16QAM', channel_profile='uniform',
                                 device=DEV), kernel=kernel).detect(H, y, 10 ** 1.2, x, lab, idx)
         assert d.counters_dict()["frames"] == 7
