@@ -28,6 +28,13 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// reciprocal to <= 1 ulp without a slow path: MUFU.RCP + one Newton step (two FMAs).  For the scalars whose error VAMP
+// amplifies (1 / (1 - alpha), 1 / (1 - dxdr) with the ratios clipped at 1 - 1e-5, vamp.py:79-91): the reference divides in IEEE
+// float32, and every ulp of the kernel's own adds to the share of rounding-determined frames (tests/test_gpu_oracle_scale.py).
+__device__ __forceinline__ float rcp_ulp(float x) {
+    const float r = fast_rcp(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
 // Packed fp32x2 arithmetic on 64-bit register pairs (FFMA2, sm_100).  The pairs are held in 64-bit containers so
 // that ptxas keeps the H tile PACKED across the whole frame; with float2 values it re-assembles every operand pair
 // with two MOVs per FFMA2 inside the iteration loop.
