@@ -179,8 +179,10 @@ __device__ __forceinline__ float rcp1(float x) {
 // denoiser + psi + exit test in the epilogue (float32 exp, per-section shift; M in {8, 16, 32, 64}).
 // MSEC: section size of the fused denoiser (8, 16, 32, 64), 0 = not fused.  EXACT: every symbol is one of {0, +-1, +-j} (the reference's
 // OOK / BPSK / QPSK tables, config.py:86-95): the exponent q.re s.re + q.im s.im is then ONE exact float32 product, so the plain float32
-// difference to the shift is as accurate as the reference's float64 evaluation and the compensated sum is not needed.
-template <int MODE, int MSEC, bool EXACT>
+// difference to the shift is as accurate as the reference's float64 evaluation and the compensated sum is not needed.  The
+// reference's QPSK table {1, j, -1, -j} (config.py:93) is special-cased further: the four exponents are +-q.re, +-q.im, their
+// maximum is max(|q.re|, |q.im|), the symbol-weighted sums are differences of two exponentials.
+template <int MODE, int MSEC, int ALPH>      // ALPH: 0 compensated exponents, 1 exact products, 2 the four axis symbols {1, j, -1, -j}
 __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_constant__ StArgs a, const __grid_constant__ CUtensorMap xmap_desc) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_base_s;
@@ -481,12 +483,20 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                                     qbi[u] = __fmul_rn(mb[u].y, rt);
                                     la[u] = lb[u] = -INFINITY;
                                 }
-                                for (int k = 0; k < K; ++k) {
-                                    const float sr = a.al.ref[k], si = a.al.imf[k];
+                                if (ALPH == 2) {
 #pragma unroll
                                     for (int u = 0; u < 4; ++u) {
-                                        la[u] = fmaxf(la[u], fmaf(qar[u], sr, qai[u] * si));
-                                        lb[u] = fmaxf(lb[u], fmaf(qbr[u], sr, qbi[u] * si));
+                                        la[u] = fmaxf(fabsf(qar[u]), fabsf(qai[u]));
+                                        lb[u] = fmaxf(fabsf(qbr[u]), fabsf(qbi[u]));
+                                    }
+                                } else {
+                                    for (int k = 0; k < K; ++k) {
+                                        const float sr = a.al.ref[k], si = a.al.imf[k];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            la[u] = fmaxf(la[u], fmaf(qar[u], sr, qai[u] * si));
+                                            lb[u] = fmaxf(lb[u], fmaf(qbr[u], sr, qbi[u] * si));
+                                        }
                                     }
                                 }
 #pragma unroll
@@ -511,7 +521,22 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
                                     if (M == 64) lb[u] = la[u];
                                     za[u] = zb[u] = nar[u] = nai[u] = nbr[u] = nbi[u] = 0.f;
                                 }
-                                if (EXACT) {
+                                if (ALPH == 2) {
+                                    constexpr float L2E = 1.4426950408889634f;
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float a1 = fast_ex2((qar[u] - la[u]) * L2E), a2 = fast_ex2((-qar[u] - la[u]) * L2E);
+                                        const float a3 = fast_ex2((qai[u] - la[u]) * L2E), a4 = fast_ex2((-qai[u] - la[u]) * L2E);
+                                        const float b1 = fast_ex2((qbr[u] - lb[u]) * L2E), b2 = fast_ex2((-qbr[u] - lb[u]) * L2E);
+                                        const float b3 = fast_ex2((qbi[u] - lb[u]) * L2E), b4 = fast_ex2((-qbi[u] - lb[u]) * L2E);
+                                        za[u] = (a1 + a2) + (a3 + a4);
+                                        nar[u] = a1 - a2;
+                                        nai[u] = a3 - a4;
+                                        zb[u] = (b1 + b2) + (b3 + b4);
+                                        nbr[u] = b1 - b2;
+                                        nbi[u] = b3 - b4;
+                                    }
+                                } else if (ALPH == 1) {
                                     for (int k = 0; k < K; ++k) {
                                         const float sr = a.al.ref[k], si = a.al.imf[k];
 #pragma unroll
@@ -799,6 +824,21 @@ static bool is_exact_alphabet(const DevAlphabet& al) {
     return true;
 }
 
+// exactly the four symbols 1, j, -1, -j in any order (the reference's QPSK table, config.py:93)
+static bool is_axis4_alphabet(const DevAlphabet& al) {
+    if (al.K != 4) return false;
+    int seen = 0;
+    for (int k = 0; k < 4; ++k) {
+        const double r = al.re[k], i = al.im[k];
+        if (r == 1.0 && i == 0.0) seen |= 1;
+        else if (r == -1.0 && i == 0.0) seen |= 2;
+        else if (r == 0.0 && i == 1.0) seen |= 4;
+        else if (r == 0.0 && i == -1.0) seen |= 8;
+        else return false;
+    }
+    return seen == 15;
+}
+
 bool scamp_st_can_fuse(const Geom& g, const DevAlphabet& al) {
     return (g.M == 8 || g.M == 16 || g.M == 32 || g.M == 64) && g.Nt == g.Na * g.M && al.K >= 1 && al.K <= AMPSM_MAX_K;
 }
@@ -843,11 +883,13 @@ int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& 
     };
     int e = 0;
     const bool exact = fused && is_exact_alphabet(al) && !getenv("AMPSM_SCAMP_NO_EXACT");
-    if (mode == 0) e = run(scamp_st_kernel<0, 0, false>, "cudaFuncSetAttribute(scamp_st<0>)");
-    else if (!fused) e = run(scamp_st_kernel<1, 0, false>, "cudaFuncSetAttribute(scamp_st<1>)");
+    const bool axis4 = exact && is_axis4_alphabet(al) && !getenv("AMPSM_SCAMP_NO_AXIS4");
+    if (mode == 0) e = run(scamp_st_kernel<0, 0, 0>, "cudaFuncSetAttribute(scamp_st<0>)");
+    else if (!fused) e = run(scamp_st_kernel<1, 0, 0>, "cudaFuncSetAttribute(scamp_st<1>)");
 #define AMPSM_ST_CASE(MM) \
-    else if (g.M == MM) e = exact ? run(scamp_st_kernel<1, MM, true>, "cudaFuncSetAttribute(scamp_st<1, " #MM ", exact>)") \
-                                 : run(scamp_st_kernel<1, MM, false>, "cudaFuncSetAttribute(scamp_st<1, " #MM ">)");
+    else if (g.M == MM) e = axis4 ? run(scamp_st_kernel<1, MM, 2>, "cudaFuncSetAttribute(scamp_st<1, " #MM ", axis4>)") \
+                          : exact ? run(scamp_st_kernel<1, MM, 1>, "cudaFuncSetAttribute(scamp_st<1, " #MM ", exact>)") \
+                                  : run(scamp_st_kernel<1, MM, 0>, "cudaFuncSetAttribute(scamp_st<1, " #MM ">)");
     AMPSM_ST_CASE(64)
     AMPSM_ST_CASE(32)
     AMPSM_ST_CASE(16)

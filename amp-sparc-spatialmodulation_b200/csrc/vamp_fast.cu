@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             // var_ratio: python-float division on the first pass, tensor division afterwards (vamp.py:66).  The scalar
             // divisions of the bookkeeping are MUFU reciprocals (2^-23 relative): an IEEE division is a ~15-instruction
             // dependent sequence, eight of them per iteration sat on the critical path of the first version.
-            const float rs2t = rcp_ulp(s2t);
+            const float rs2t = fast_rcp(s2t);
             const float ratio = (it == 0) ? ratio0 : nv * rs2t;
             __syncwarp();
             // ================= LMMSE in the SVD basis: d = scale (y~ + ratio q) - q (vamp.py:68-72) =================
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                 const float qx = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
                 const float qy = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
                 const float4 rs = rowstate[lane];
-                scale = rcp_ulp(rs.z + ratio);
+                scale = fast_rcp(rs.z + ratio);
                 const float dx = scale * (rs.x + ratio * qx) - qx, dy = scale * (rs.y + ratio * qy) - qy;
                 rowvec[lane] = make_float2(dx, dy);
             }
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             const float var_lmmse = (scale_tot * (1.0f / (float)R)) * nv;      // scale.mean() * noise_var
             const float xt_var = eta * var_lmmse + one_m_eta * s2t;
             const float alpha = clampF(xt_var * rs2t, ratio_min, ratio_max);
-            const float inv_1ma = rcp_ulp(1.0f - alpha);
+            const float inv_1ma = fast_rcp(1.0f - alpha);
             const float sig2 = clampF(alpha * inv_1ma * s2t, var_min, var_max);
             const float rsig = __frcp_rn(sig2);                                // the one accurate reciprocal: it scales every exponent
             __syncwarp();
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             const float vtot = warp_sum(vs);
             const float vmean = vtot * (1.0f / (float)N);
             const float dxdr = clampF(vmean * rsig, ratio_min, ratio_max);
-            const float norm = rcp_ulp(1.0f - dxdr);
+            const float norm = fast_rcp(1.0f - dxdr);
             float s_mse = 0.f;
 #pragma unroll
             for (int t = 0; t < CP; ++t) {

@@ -554,7 +554,7 @@ def test_fast_kernel_falls_back_on_misaligned_loss_inputs():
 
 @pytest.mark.parametrize("shape,F,trunc,alphabet", [((64, 2, 8, 8, 3), 300, 'tail', 'QPSK'), ((128, 4, 16, 6, 2), 150, 'tail', 'QPSK'),
                                                      ((64, 2, 8, 8, 3), 130, 'trunc', 'QPSK'), ((48, 2, 6, 5, 2), 140, 'tail', 'QPSK'),
-                                                     ((128, 8, 32, 16, 3), 37, 'tail', 'QPSK'), ((64, 2, 8, 8, 3), 160, 'tail', 'QPSK-generic'),
+                                                     ((128, 8, 32, 16, 3), 37, 'tail', 'QPSK'), ((64, 2, 8, 8, 3), 160, 'tail', 'QPSK-generic'), ((64, 2, 8, 8, 3), 160, 'tail', 'QPSK-exact'),
                                                      ((128, 2, 16, 6, 2), 140, 'tail', 'BPSK')])
 def test_scamp_structured_path_matches_dense_path(shape, F, trunc, alphabet, monkeypatch):
     """The structured tensor-core kernels (design matrix applied from its taps: tensor TMA, tcgen05, csrc/scamp_st.cu) against
@@ -566,6 +566,9 @@ def test_scamp_structured_path_matches_dense_path(shape, F, trunc, alphabet, mon
     Nt, Na, Nr, Lin, Lh = shape
     if alphabet == 'QPSK-generic':        # the compensated float32 exponent branch (what an alphabet outside {0, +-1, +-j} takes)
         monkeypatch.setenv("AMPSM_SCAMP_NO_EXACT", "1")
+        alphabet = 'QPSK'
+    if alphabet == 'QPSK-exact':          # the exact-product branch without the axis-symbol shortcut the reference's QPSK table takes
+        monkeypatch.setenv("AMPSM_SCAMP_NO_AXIS4", "1")
         alphabet = 'QPSK'
     cfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet=alphabet,
                      channel_profile='uniform', channel_truncation=trunc, device=str(DEV))
