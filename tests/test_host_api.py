@@ -204,3 +204,28 @@ def test_dense_materialises_lazy_conjugate_views():
     assert np.array_equal(np.frombuffer(dense(w, 'cpu', torch.complex64).numpy().tobytes(), np.complex64),
                           a.conj().resolve_conj().numpy().ravel())
     assert dense(a, 'cpu', torch.complex64, -1, 1).shape == (15, 1)
+
+
+def test_scamp_design_matrix_is_recognised_as_block_toeplitz():
+    """Channel.generate_as_sparc (channel.py:76-96) builds A = sum_l kron(eye(Lout, Lin, -l) sqrt(W), h_l): block (r, c) = taps[r - c].
+    The host-side structure test behind SCAMP's structured route must recover the taps bit-exactly for 'tail' and 'trunc'
+    layouts, rebuild A from them, and reject a matrix that is not block-Toeplitz."""
+    import torch
+    from amp_sparc_spatialmodulation_b200.bamp import matrix_from_taps, taps_from_matrix
+    for shape, trunc in (((64, 2, 8, 8, 3), 'tail'), ((48, 2, 6, 5, 2), 'tail'), ((64, 2, 8, 8, 3), 'trunc'), ((32, 4, 16, 6, 1), 'trunc')):
+        cfg = pkg.Config(*shape, batch=2, generator_mode='sparc', iterations=20, alphabet='QPSK', channel_profile='exponential',
+                         channel_truncation=trunc, device='cpu')
+        np.random.seed(3)
+        W, A = pkg.Channel(cfg).generate_as_sparc()
+        st = taps_from_matrix(A, cfg)
+        assert st is not None and st[1] is False
+        taps = st[0]
+        assert tuple(taps.shape) == (min(cfg.Lh, cfg.Lout), cfg.Nr, cfg.Nt)
+        assert torch.equal(matrix_from_taps(taps, cfg.Lin, cfg.Lout), A)
+        if cfg.Lin > 1:
+            B = A.clone()
+            B[-1, 0] = 1.0 + 0j                                    # an entry outside the band
+            assert taps_from_matrix(B, cfg) is None
+            C_ = A.clone()
+            C_[cfg.Nr, cfg.Nt] += 1e-3                              # block (1, 1) no longer equals block (0, 0)
+            assert taps_from_matrix(C_, cfg) is None
