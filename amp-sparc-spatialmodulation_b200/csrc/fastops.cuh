@@ -58,6 +58,15 @@ __device__ __forceinline__ pair_t fmul2(pair_t a, pair_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// Scheduling tie: returns v unchanged (opaque_zero is a kernel parameter that is always 0, which ptxas cannot know), but as the
+// result of an instruction that also reads the low half of `acc` -- so everything computed from the returned value is issued
+// after the instruction that produced `acc`.  Used to spread a latency chain over a stream of independent FFMA2 (vamp_quad.cu).
+__device__ __forceinline__ float chain_tie(float v, pair_t acc, unsigned opaque_zero) {
+    unsigned r = __float_as_uint(v);
+    const unsigned lo = (unsigned)acc;
+    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(r) : "r"(lo), "r"(opaque_zero));      // r | (lo & zero)
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float fast_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -344,6 +353,62 @@ __device__ __forceinline__ void fast_denoise(const float (&q_r)[CP], const float
             vn_[t] = fmaf(fmaf(xr, xr, xi * xi), others[t] * rz, spread * rz);
         }
     }
+}
+
+// Every symbol in {0, +-1, +-j} (the reference's OOK / BPSK / QPSK tables, config.py:86-95): the exponent
+// q.re s.re + q.im s.im is then ONE exact float32 product, and its float32 difference to the float32 shift is the correctly
+// rounded difference -- the same number the float64 path of fast_denoise rounds to float32 before ex2.
+inline bool alphabet_is_exact(const DevAlphabet& al) {
+    for (int k = 0; k < al.K; ++k) {
+        const double ar = al.re[k] < 0 ? -al.re[k] : al.re[k], ai = al.im[k] < 0 ? -al.im[k] : al.im[k];
+        if (!((ar == 0.0 || ar == 1.0) && (ai == 0.0 || ai == 1.0) && !(ar == 1.0 && ai == 1.0))) return false;
+    }
+    return true;
+}
+
+// Section denoiser for such alphabets with ONE column per lane (the four-warps-per-frame kernel): same operations in the same
+// order as the generic branch of fast_denoise (bit-identical results for these alphabets) without any float64 instruction
+// (conversions run on the XU pipe at a sixteenth of the FP32 rate and sat on the iteration's critical path), the exponentials
+// in registers, the section maximum by one masked REDUX.
+template <int M_, int K_>
+__device__ __forceinline__ void exact_denoise1(float q_r, float q_i, const DevAlphabet& al, int lane, float& xr_, float& xi_, float& vn_) {
+    static_assert(M_ == 32 || M_ == 16 || M_ == 8, "a section is an aligned group of lanes");
+    float x[K_];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K_; ++k) {
+        x[k] = fmaf(q_r, al.ref[k], q_i * al.imf[k]);
+        m = fmaxf(m, x[k]);
+    }
+    float smax;
+    if constexpr (M_ == 32) {
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(smax) : "f"(m));
+    } else {
+        const unsigned mask = ((M_ == 16) ? 0xffffu : 0xffu) << (lane & ~(M_ - 1));
+        asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(smax) : "f"(m), "r"(mask));
+    }
+    float e[K_], s0 = 0.f, s1r = 0.f, s1i = 0.f;
+#pragma unroll
+    for (int k = 0; k < K_; ++k) {
+        e[k] = fast_ex2((x[k] - smax) * 1.4426950408889634f);
+        s0 += e[k];
+        s1r = fmaf(al.ref[k], e[k], s1r);
+        s1i = fmaf(al.imf[k], e[k], s1i);
+    }
+    const float S0[1] = {s0};
+    float Z[1], others[1];
+    section_sum_excl<M_, 1>(S0, Z, others);
+    const float rz = fast_rcp(Z[0]);
+    const float xr = s1r * rz, xi = s1i * rz;
+    float spread = 0.f;
+#pragma unroll
+    for (int k = 0; k < K_; ++k) {
+        const float dr = xr - al.ref[k], di = xi - al.imf[k];
+        spread = fmaf(fmaf(dr, dr, di * di), e[k], spread);
+    }
+    xr_ = xr;
+    xi_ = xi;
+    vn_ = fmaf(fmaf(xr, xr, xi * xi), others[0] * rz, spread * rz);
 }
 
 // ---- Loss on the column-owner layout: MAP decision + counters (loss.py:282-302, 67-179), Lin = 1, one warp per frame ----

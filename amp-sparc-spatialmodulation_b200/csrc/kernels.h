@@ -66,6 +66,7 @@ struct VampArgs {
     float* traj;
     long long frames;
     int stage_Vh;
+    unsigned opaque_zero;        // always 0; the kernels use it for scheduling ties the compiler cannot fold (fastops.cuh chain_tie)
 };
 
 struct ScampArgs {

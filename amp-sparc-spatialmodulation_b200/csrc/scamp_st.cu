@@ -25,6 +25,7 @@
 // the tile of a CTA is FR = floor(128 / Lin) whole frames.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "blockops.cuh"
@@ -53,7 +54,7 @@ struct StSmem {          // byte offsets into dynamic shared memory (1024-byte a
     int raw, xpl, bpl, epi, meta, bars, total;
     int nraw, nb;        // ring depths
 };
-__host__ __device__ inline StSmem st_smem(int brows, int mode) {
+__host__ __device__ inline StSmem st_smem(int brows, int mode, int force_raw = 0, int force_b = 0) {
     StSmem s;
     const int bstage = 4 * KS * brows * 4;                     // B stage: 4 planes x [4 K chunks][brows][4 floats]
     const int epi_bytes = mode == 1 ? kEpiWarps * kTbufRows * kTbufStride * 8 : 0;
@@ -66,6 +67,11 @@ __host__ __device__ inline StSmem st_smem(int brows, int mode) {
         grew = false;
         if (s.nraw < kMaxRaw && fixed + (s.nraw + 1) * kRawStage + s.nb * bstage <= kSmemMax) { ++s.nraw; grew = true; }
         if (s.nb < kMaxB && fixed + s.nraw * kRawStage + (s.nb + 1) * bstage <= kSmemMax) { ++s.nb; grew = true; }
+    }
+    if (force_raw >= 2 && force_b >= 1 && force_raw <= kMaxRaw && force_b <= kMaxB &&
+        fixed + force_raw * kRawStage + force_b * bstage <= kSmemMax) {       // experiments: AMPSM_ST_RINGS="raw,b"
+        s.nraw = force_raw;
+        s.nb = force_b;
     }
     s.raw = 0;
     s.xpl = s.raw + s.nraw * kRawStage;
@@ -152,6 +158,7 @@ struct StArgs {
     float sigma2;
     const float* sigma2_pf;
     int t;                             // iteration index (the fused estimate mode retires its frames itself)
+    int ring_raw, ring_b;              // forced ring depths (0: automatic)
     int dbg;                           // AMPSM_ST_DEBUG bits (timing experiments): 2 skip the MMAs, 4 skip the conversion, 8 skip the Xh loads, 16 skip the epilogue stores, 32 skip the denoiser math
 };
 
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) scamp_st_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows = a.FR * g.Lin;                                  // valid rows of a tile (<= 128)
     const long long f0 = (long long)blockIdx.x * a.FR;
-    const StSmem L = st_smem(a.brows, MODE);
+    const StSmem L = st_smem(a.brows, MODE, a.ring_raw, a.ring_b);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t *raw_full = bars, *raw_empty = bars + kMaxRaw, *xp_full = bars + 2 * kMaxRaw, *xp_empty = xp_full + kXStages,
              *b_full = xp_empty + kXStages, *b_empty = b_full + kMaxB, *acc_full = b_empty + kMaxB, *acc_empty = acc_full + 2;
@@ -874,7 +881,8 @@ int scamp_st_gemm(int mode, const ScampWs& w, const Geom& g, const ScampStPlan& 
     if (const char* d = getenv("AMPSM_ST_DEBUG")) a.dbg = atoi(d);
     a.chunks = mode == 0 ? 1 : p.chunks1;
     a.nks = mode == 0 ? p.nks0 : p.nks1;
-    const int smem = st_smem(a.brows, mode).total;
+    if (const char* r = getenv(mode == 0 ? "AMPSM_ST_RINGS0" : "AMPSM_ST_RINGS1")) sscanf(r, "%d,%d", &a.ring_raw, &a.ring_b);
+    const int smem = st_smem(a.brows, mode, a.ring_raw, a.ring_b).total;
     const unsigned grid = (unsigned)((F + p.FR - 1) / p.FR);
     auto run = [&](auto kern, const char* what) -> int {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what)) return e;

@@ -304,6 +304,16 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
             }
             __syncwarp();
             CLK(1);                            // row reduction, LMMSE
+            // scalars (vamp.py:71-82), the same in every lane.  They depend on `ratio` only, so they are issued ahead of the column
+            // pass and overlap it; rcp_ulp = __frcp_rn for the clipped range of sig2 without its slow-path branch (a basic-block
+            // boundary in the middle of the iteration that kept ptxas from moving anything across it)
+            const float scale_tot = warp_sum(scale);
+            const float var_lmmse = (scale_tot * (1.0f / (float)R)) * nv;      // scale.mean() * noise_var
+            const float xt_var = eta * var_lmmse + one_m_eta * s2t;
+            const float alpha = clampF(xt_var * rs2t, ratio_min, ratio_max);
+            const float inv_1ma = fast_rcp(1.0f - alpha);
+            const float sig2 = clampF(alpha * inv_1ma * s2t, var_min, var_max);
+            const float rsig = rcp_ulp(sig2);                                  // the one accurate reciprocal: it scales every exponent
             // ================= column pass: V d (vamp.py:72) =================
             {
                 constexpr int CH = CTL > 4 ? CTL / 2 : CTL;
@@ -342,14 +352,6 @@ __global__ void __launch_bounds__(32, WPS) vamp_fast_kernel(const __grid_constan
                     }
                 }
             }
-            // scalars (vamp.py:71-82), the same in every lane
-            const float scale_tot = warp_sum(scale);
-            const float var_lmmse = (scale_tot * (1.0f / (float)R)) * nv;      // scale.mean() * noise_var
-            const float xt_var = eta * var_lmmse + one_m_eta * s2t;
-            const float alpha = clampF(xt_var * rs2t, ratio_min, ratio_max);
-            const float inv_1ma = fast_rcp(1.0f - alpha);
-            const float sig2 = clampF(alpha * inv_1ma * s2t, var_min, var_max);
-            const float rsig = __frcp_rn(sig2);                                // the one accurate reciprocal: it scales every exponent
             __syncwarp();
             CLK(2);                            // column pass, scalars
             // ================= r = (x~ - alpha r~)/(1 - alpha), denoiser with the scalar variance (vamp.py:79-84) ==========

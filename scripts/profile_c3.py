@@ -16,6 +16,7 @@ ap.add_argument("--frames", type=int, default=148 * 2 * 16)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--fixed", action="store_true")
 ap.add_argument("--snr-db", type=float, default=2.0)
+ap.add_argument("--double", action="store_true", help="complex128 factors: the register-resident DFMA kernel (csrc/vamp_dbl.cu)")
 a = ap.parse_args()
 cfg = pkg.Config(128, 4, 64, 1, 1, batch=a.frames, generator_mode='sparc', iterations=20, alphabet='QPSK',
                  channel_profile='uniform', device="cuda:0")
@@ -27,6 +28,8 @@ x, sym, idx = da.generate_message()
 _, A = ch.generate_as_sparc()
 y = A @ x + ch.awgn(snr)
 U, s, Vh = torch.linalg.svd(A, full_matrices=False)
+if a.double:
+    U, s, Vh, y = U.to(torch.complex128), s.to(torch.float64), Vh.to(torch.complex128), y.to(torch.complex128)
 amp = pkg.VAMP(cfg, outputs=False, early_exit=not a.fixed)
 for _ in range(a.launches):
     det = amp.detect(U, s, Vh, y, snr, x, sym, idx)
