@@ -13,6 +13,7 @@ from .bamp import BAMP
 from .scamp import SCAMP
 from .vamp import VAMP, svd_batched
 from .shrink import Shrink
+from .framegen import FrameStream
 from .simulate import MonteCarlo, device_frames, run_scamp
 
 __all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink", "svd_batched", "MonteCarlo", "device_frames", "run_scamp"]

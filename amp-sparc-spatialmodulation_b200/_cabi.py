@@ -22,7 +22,8 @@ EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp
            "ampsm_vamp_detect", "ampsm_vamp_detect_host", "ampsm_svd_batched", "ampsm_vamp_from_h_workspace_bytes",
            "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect", "ampsm_scamp_taps_workspace_bytes", "ampsm_scamp_detect_taps",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops", "ampsm_probe_fp64_tflops",
-           "ampsm_launch_count", "ampsm_host_alloc", "ampsm_host_free", "ampsm_host_numa_info"]
+           "ampsm_launch_count", "ampsm_host_alloc", "ampsm_host_free", "ampsm_host_numa_info", "ampsm_generate_frames",
+           "ampsm_vamp_detect_generated"]
 
 
 class Alphabet(C.Structure):
@@ -34,6 +35,11 @@ class Problem(C.Structure):
                 ("Nr", C.c_int32), ("Lin", C.c_int32), ("Lout", C.c_int32), ("max_iters", C.c_int32),
                 ("early_exit", C.c_int32), ("shift_mode", C.c_int32), ("exp_f64", C.c_int32), ("decision", C.c_int32),
                 ("index_bits_kept", C.c_int32), ("kernel", C.c_int32), ("reserved0", C.c_int32), ("frame_base", C.c_int64)]
+
+
+class Gen(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("counter_base", C.c_int64), ("h_var", C.c_double), ("Rr_root", C.c_void_p), ("Rt_root", C.c_void_p),
+                ("real_roots", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class AmpsmError(RuntimeError):
@@ -69,6 +75,9 @@ def lib():
     L.ampsm_vamp_from_h_workspace_bytes.argtypes = [PP, i64]
     L.ampsm_vamp_from_h_workspace_bytes.restype = i64
     L.ampsm_vamp_detect_from_h.argtypes = [PP, AP, i64, vp, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    GP = C.POINTER(Gen)
+    L.ampsm_generate_frames.argtypes = [PP, AP, GP, i64, dbl, vp, vp, vp, vp, vp, vp]
+    L.ampsm_vamp_detect_generated.argtypes = [PP, AP, GP, i64, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     scamp = [PP, AP, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_scamp_detect.argtypes = scamp + [vp, vp]
     L.ampsm_scamp_detect_host.argtypes = scamp + [i32]

@@ -1,6 +1,7 @@
 // C-ABI entry points of libampsm_b200.so (declared in include/ampsm_b200.h): argument checking, kernel selection,
 // and the host-buffer variants that overlap chunked host<->device copies with the kernels on two streams.
 #include <cstdlib>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -503,6 +504,64 @@ int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, in
     if (int e = launch_identity(eye, p->n, (cudaStream_t)stream)) return e;
     return ampsm_vamp_detect(p, a, frames, 0, eye, 0, s, (int64_t)n, Vh, (int64_t)(n * N), yrot, sigma2, sigma2_per_frame,
                              sparsity, x_true, sym_true, idx_true, xmap, xmmse, var, iters, traj, counters, stream);
+}
+
+// ---------------------------------------------------------------- on-device frame generation (csrc/framegen.cuh)
+static int make_gen(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm_gen* gen, double sigma2, void* x, int64_t* sym, int64_t* idx,
+                    Geom* g, GenArgs* ga) {
+    DevAlphabet al{};
+    if (int e = make_geom(p, a, g, &al, false)) return e;
+    if (!gen) { set_error("frame generation: ampsm_gen pointer is NULL"); return AMPSM_EINVAL; }
+    if (p->decision != 0) { set_error("frame generation draws sectioned messages (decision = 0; data.py:74-91)"); return AMPSM_EINVAL; }
+    if (!(gen->h_var > 0.0) || !(sigma2 >= 0.0)) { set_error("frame generation: h_var must be positive and sigma2 non-negative"); return AMPSM_EINVAL; }
+    if (check_loss_io(x, sym, idx)) return AMPSM_EINVAL;
+    ga->seed = gen->seed;
+    ga->counter_base = gen->counter_base;
+    ga->h_std = (float)sqrt(gen->h_var / 2.0);
+    ga->noise_std = (float)sqrt(sigma2 / 2.0);
+    ga->Rr_root = (const float2*)gen->Rr_root;
+    ga->Rt_root = (const float2*)gen->Rt_root;
+    ga->real_roots = gen->real_roots != 0;
+    ga->K = a->K;
+    for (int k = 0; k < AMPSM_MAX_K; ++k) {
+        ga->sym[k] = make_float2(al.ref[k], al.imf[k]);
+        ga->gray[k] = al.gray[k];
+    }
+    ga->x_out = (float2*)x;
+    ga->idx_out = (long long*)idx;
+    ga->sym_out = (long long*)sym;
+    return 0;
+}
+
+int ampsm_generate_frames(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm_gen* gen, int64_t frames, double sigma2, void* H,
+                          void* y, void* x, int64_t* sym, int64_t* idx, void* stream) {
+    Geom g{};
+    GenArgs ga{};
+    if (int e = make_gen(p, a, gen, sigma2, x, sym, idx, &g, &ga)) return e;
+    if (frames < 0) { set_error("frame generation: frames < 0"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    return launch_generate_frames(ga, g, frames, (float2*)H, (float2*)y, (cudaStream_t)stream);
+}
+
+int ampsm_vamp_detect_generated(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm_gen* gen, int64_t frames, double sigma2,
+                                double sparsity, void* x, int64_t* sym, int64_t* idx, void* xmap, void* xmmse, float* var, int32_t* iters,
+                                uint64_t* counters, void* workspace, void* stream) {
+    Geom g{};
+    GenArgs ga{};
+    if (int e = make_gen(p, a, gen, sigma2, x, sym, idx, &g, &ga)) return e;
+    if (frames < 0 || (frames > 0 && (!workspace || !x))) { set_error("VAMP on generated frames: workspace / ground-truth buffers are NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (p->R != p->n || p->n > p->N) { set_error("VAMP on generated frames: needs R = n <= N (got n=%d N=%d R=%d)", p->n, p->N, p->R); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    const size_t n = p->n, N = p->N;
+    unsigned char* w = (unsigned char*)workspace;                      // same layout as ampsm_vamp_detect_from_h
+    float2* yrot = (float2*)w;
+    float* s = (float*)(w + align256((size_t)frames * n * 8));
+    void* Vh = w + align256((size_t)frames * n * 8) + align256((size_t)frames * n * 4);
+    float2* eye = (float2*)((unsigned char*)Vh + align256((size_t)frames * n * N * 8));
+    if (int e = launch_svd_jacobi_gen(ga, g, frames, s, (float2*)Vh, yrot, (cudaStream_t)stream)) return e;
+    if (int e = launch_identity(eye, p->n, (cudaStream_t)stream)) return e;
+    return ampsm_vamp_detect(p, a, frames, 0, eye, 0, s, (int64_t)n, Vh, (int64_t)(n * N), yrot, sigma2, nullptr, sparsity, x, sym, idx,
+                             xmap, xmmse, var, iters, nullptr, counters, stream);
 }
 
 // ---------------------------------------------------------------- SCAMP

@@ -112,6 +112,24 @@ struct ShrinkArgs {
     double* sum;
 };
 
+// On-device frame generation (framegen.cuh): Philox key / counters, scalings, optional Kronecker roots, the message alphabet
+// and the ground-truth outputs the Loss needs.
+struct GenArgs {
+    unsigned long long seed;     // Philox key
+    long long counter_base;      // global number of frame 0 of the call (Philox counter), so shards and chunks draw disjoint frames
+    float h_std;                 // std of Re / Im of an i.i.d. channel entry: sqrt(1 / Nr / 2) (channel.py:55)
+    float noise_std;             // sqrt(sigma^2 / 2) (channel.py:113-115)
+    const float2* Rr_root;       // [n][n] or nullptr;  H = Rr_root G Rt_root (BASELINE config 5)
+    const float2* Rt_root;       // [N][N] or nullptr
+    int real_roots;              // both roots have zero imaginary parts (the exponential correlation model): half the products
+    int K;
+    float2 sym[AMPSM_MAX_K];     // config.symbols as complex64
+    long long gray[AMPSM_MAX_K];
+    float2* x_out;               // [frames][N] the transmitted vectors (data.py:88)
+    long long* idx_out;          // [frames][L] flat non-zero positions (data.py:90)
+    long long* sym_out;          // [frames][L] Gray labels (data.py:89)
+};
+
 int launch_bamp_generic(const BampArgs& a, bool exp64, cudaStream_t stream);
 int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENOFIT when the shape has no fast path
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
@@ -127,6 +145,10 @@ int launch_shrink(const ShrinkArgs& a, int kind, cudaStream_t stream);   // kind
 int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U, float* S, float2* Vh, int* sweeps, const float2* y,
                       float2* yrot, cudaStream_t stream);      // y != nullptr: yrot = U^H y instead of U
 int launch_identity(float2* I, int n, cudaStream_t stream);
+// gen != nullptr: the frames are generated inside the kernel (H == y == nullptr): s, Vh, yrot and gen's ground truth come out
+int launch_svd_jacobi_gen(const GenArgs& gen, const Geom& g, long long frames, float* S, float2* Vh, float2* yrot, cudaStream_t stream);
+// the same frames written out: H [frames][n][N], y [frames][n] (either may be nullptr) and gen's ground truth
+int launch_generate_frames(const GenArgs& gen, const Geom& g, long long frames, float2* H, float2* y, cudaStream_t stream);
 int probe_fp32(int device, double* tflops);
 int probe_fp32x2(int device, double* tflops);
 int probe_fp64(int device, double* tflops);

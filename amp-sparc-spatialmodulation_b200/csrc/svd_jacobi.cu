@@ -15,6 +15,7 @@
 // already orthogonal to 4e-7 (relative) is skipped; the sweep loop ends when a whole sweep rotated nothing.
 #include <cstdlib>
 
+#include "framegen.cuh"
 #include "kernels.h"
 
 namespace ampsm {
@@ -97,10 +98,17 @@ __device__ __forceinline__ bool svd_grot(float (&gd)[4], float2 (&go)[4][4], flo
 // WITHY: the caller only needs U^H y (VAMP's y~ = diag(s) U^H y, vamp.py:22): the rotations are applied to the vector y
 // instead of the n x n matrix Q = U^H -- a third less shared-memory traffic per rotation, no U written or read later.
 // BLOCK: the four-rows-per-group sweep above instead of the pairwise one.
-template <int NC, bool WITHY, bool BLOCK>
+// GEN: the frame is drawn inside the kernel (framegen.cuh) straight into W and z -- H never exists in HBM (WITHY only).
+struct SvdGen {
+    GenArgs ga;
+    Geom g;
+};
+template <int NC, bool WITHY, bool BLOCK, bool GEN = false>
 __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2* __restrict__ H, long long frames, int n, float2* __restrict__ U,
                                                                    float* __restrict__ S, float2* __restrict__ Vh, int* __restrict__ sweeps_out,
-                                                                   const float2* __restrict__ yin, float2* __restrict__ yrot) {
+                                                                   const float2* __restrict__ yin, float2* __restrict__ yrot,
+                                                                   const __grid_constant__ SvdGen gen) {
+    static_assert(!GEN || WITHY, "in-kernel generation feeds the fused VAMP path");
     using Sh = SvdShape<NC, WITHY>;
     constexpr int HC = NC / 2, HQ = kSvdRows / 2;             // columns of W / Q per lane
     extern __shared__ __align__(16) unsigned char smem[];
@@ -113,12 +121,17 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
 
     for (long long f = (long long)blockIdx.x * kSvdWarps + wic; f < frames; f += (long long)gridDim.x * kSvdWarps) {
         // ---- load: W = H (rows >= n are zero), Q = I
-        const float2* Hf = H + f * (long long)n * NC;
-        for (int e = lane; e < kSvdRows * NC; e += 32) {
-            const int r = e / NC, c = e - r * NC;
-            W[r * Sh::wstride + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
+        if constexpr (GEN) {
+            gen_frame<NC>(gen.ga, gen.g, f, n, W, Sh::wstride, Q, lane);
+        } else {
+            const float2* Hf = H + f * (long long)n * NC;
+            for (int e = lane; e < kSvdRows * NC; e += 32) {
+                const int r = e / NC, c = e - r * NC;
+                W[r * Sh::wstride + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
+            }
         }
-        if constexpr (WITHY) {
+        if constexpr (GEN) {
+        } else if constexpr (WITHY) {
             Q[lane] = lane < n ? __ldg(yin + f * n + lane) : make_float2(0.f, 0.f);      // z = y (rows >= n are zero)
         } else {
             for (int e = lane; e < kSvdRows * kSvdRows; e += 32) {
@@ -373,9 +386,76 @@ int launch_svd_nc_b(const float2* H, long long frames, int n, float2* U, float* 
     const long long need = (frames + kSvdWarps - 1) / kSvdWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(H, frames, n, U, S, Vh, sweeps, y, yrot);
+    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(H, frames, n, U, S, Vh, sweeps, y, yrot, SvdGen{});
     count_launch();
     return check_cuda(cudaGetLastError(), "svd_jacobi_kernel launch");
+}
+
+template <int NC>
+int launch_svd_gen_nc(const GenArgs& ga, const Geom& g, long long frames, float* S, float2* Vh, float2* yrot, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = svd_jacobi_kernel<NC, true, false, true>;
+    const size_t smem = (size_t)SvdShape<NC, true>::warp_bytes * kSvdWarps;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(svd gen)"))
+        return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSvdWarps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (frames + kSvdWarps - 1) / kSvdWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    SvdGen sg{ga, g};
+    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(nullptr, frames, g.n, nullptr, S, Vh, nullptr, nullptr, yrot, sg);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "svd_jacobi_kernel (generated frames) launch");
+}
+
+// the frames of the same stream written out (the checker of the fused path, and one-pass input generation for the detectors
+// that read H from HBM): one warp per frame, tile in shared memory, coalesced stores
+template <int NC>
+__global__ void __launch_bounds__(kSvdWarps * 32) generate_frames_kernel(const __grid_constant__ SvdGen gen, long long frames, float2* __restrict__ H,
+                                                                        float2* __restrict__ y) {
+    constexpr int wstride = NC + 1;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    float2* W = reinterpret_cast<float2*>(smem) + (size_t)wic * (kSvdRows * wstride + kSvdRows);
+    float2* yv = W + kSvdRows * wstride;
+    const int n = gen.g.n;
+    for (long long f = (long long)blockIdx.x * kSvdWarps + wic; f < frames; f += (long long)gridDim.x * kSvdWarps) {
+        gen_frame<NC>(gen.ga, gen.g, f, n, W, wstride, yv, lane);
+        if (H)
+            for (int e = lane; e < n * NC; e += 32) {
+                const int r = e / NC, c = e - r * NC;
+                H[f * (long long)n * NC + e] = W[r * wstride + c];
+            }
+        if (y && lane < n) y[f * n + lane] = yv[lane];
+        __syncwarp();
+    }
+}
+
+template <int NC>
+int launch_generate_nc(const GenArgs& ga, const Geom& g, long long frames, float2* H, float2* y, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = generate_frames_kernel<NC>;
+    const size_t smem = (size_t)(kSvdRows * (NC + 1) + kSvdRows) * 8 * kSvdWarps;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(generate)"))
+        return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSvdWarps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (frames + kSvdWarps - 1) / kSvdWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    SvdGen sg{ga, g};
+    kern<<<(unsigned)grid, kSvdWarps * 32, smem, stream>>>(sg, frames, H, y);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "generate_frames_kernel launch");
 }
 
 template <int NC, bool WITHY>
@@ -617,6 +697,41 @@ int launch_svd_jacobi(const float2* H, long long frames, int n, int N, float2* U
             return AMPSM_ENOFIT;
     }
 #undef AMPSM_SVD_NC
+}
+
+static int check_gen_shape(const Geom& g) {
+    if (g.n < 1 || g.n > kSvdRows || g.N < g.n || g.L < 1 || g.L > 32 || g.Lin != 1 || g.M * g.L != g.N) {
+        set_error("frame generation: needs 1 <= n <= 32 rows, n <= N, Lin = 1 and at most 32 sections (got n=%d N=%d L=%d Lin=%d)", g.n, g.N,
+                  g.L, g.Lin);
+        return AMPSM_ENOFIT;
+    }
+    return 0;
+}
+
+int launch_svd_jacobi_gen(const GenArgs& gen, const Geom& g, long long frames, float* S, float2* Vh, float2* yrot, cudaStream_t stream) {
+    if (int e = check_gen_shape(g)) return e;
+    switch (g.N) {
+        case 8: return launch_svd_gen_nc<8>(gen, g, frames, S, Vh, yrot, stream);
+        case 16: return launch_svd_gen_nc<16>(gen, g, frames, S, Vh, yrot, stream);
+        case 32: return launch_svd_gen_nc<32>(gen, g, frames, S, Vh, yrot, stream);
+        case 64: return launch_svd_gen_nc<64>(gen, g, frames, S, Vh, yrot, stream);
+        default:
+            set_error("frame generation: column counts 8, 16, 32, 64 are instantiated (got %d)", g.N);
+            return AMPSM_ENOFIT;
+    }
+}
+
+int launch_generate_frames(const GenArgs& gen, const Geom& g, long long frames, float2* H, float2* y, cudaStream_t stream) {
+    if (int e = check_gen_shape(g)) return e;
+    switch (g.N) {
+        case 8: return launch_generate_nc<8>(gen, g, frames, H, y, stream);
+        case 16: return launch_generate_nc<16>(gen, g, frames, H, y, stream);
+        case 32: return launch_generate_nc<32>(gen, g, frames, H, y, stream);
+        case 64: return launch_generate_nc<64>(gen, g, frames, H, y, stream);
+        default:
+            set_error("frame generation: column counts 8, 16, 32, 64 are instantiated (got %d)", g.N);
+            return AMPSM_ENOFIT;
+    }
 }
 
 int launch_identity(float2* I, int n, cudaStream_t stream) {

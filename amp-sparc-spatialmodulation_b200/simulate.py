@@ -117,8 +117,9 @@ class MonteCarlo:
     """SNR sweep of one detector over device-generated frames, sharded over the ranks of torch.distributed."""
 
     def __init__(self, config: Config, algorithm='bamp', frames_per_point=1 << 20, chunk=1 << 18, channel='iid', rho_t=0.0,
-                 rho_r=0.0, seed=1234, path=None, device=None, **detector_kw):
+                 rho_r=0.0, seed=1234, path=None, device=None, generator='torch', **detector_kw):
         self.config, self.algorithm = config, algorithm
+        self.generator = generator
         self.frames_per_point, self.chunk = int(frames_per_point), int(chunk)
         self.channel, self.rho_t, self.rho_r, self.seed = channel, rho_t, rho_r, seed
         self.path = path
@@ -135,6 +136,14 @@ class MonteCarlo:
         else:
             raise ValueError("MonteCarlo runs 'bamp' or 'vamp'; SCAMP shares a design matrix per call: see run_scamp()")
         self.loss = Loss(config)
+        # generator='kernel': the library's own Philox stream (framegen.py) -- one generation kernel for BAMP; for VAMP the frames
+        # are drawn inside the Jacobi SVD kernel and the channel matrix never exists in HBM
+        self.stream = None
+        if generator == 'kernel':
+            from .framegen import FrameStream
+            self.stream = FrameStream(config, seed=seed, channel=channel, rho_t=rho_t, rho_r=rho_r, device=self.device)
+        elif generator != 'torch':
+            raise ValueError("generator is 'torch' (torch's Philox generators, several passes) or 'kernel' (csrc/framegen.cuh)")
 
     def run_point(self, EbN0dB: float, point_index: int = 0) -> dict:
         """All frames of one SNR point: returns the GLOBAL counter dict (summed over ranks)."""
@@ -146,6 +155,17 @@ class MonteCarlo:
         f0 = lo
         while f0 < hi:
             nf = min(self.chunk, hi - f0)
+            if self.stream is not None:
+                first = point_index * self.frames_per_point + f0               # global frame number in the stream
+                if self.algorithm == 'vamp':
+                    det = self.amp.detect_generated(self.stream, first, nf, snr)
+                else:
+                    H, y, x, lab, idx = self.stream.frames(first, nf, snr)
+                    det = self.amp.detect(H, y, snr, x, lab, idx, frame_base=0)
+                total[:16] += det.counters[:16]
+                total[16:20] = (total[16:20].view(torch.float64) + det.counters[16:20].view(torch.float64)).view(torch.int64)
+                f0 += nf
+                continue
             H, y, x, lab, idx = device_frames(self.config, nf, snr, gen, self.channel, self.rho_t, self.rho_r)
             if self.algorithm == 'bamp' and H.dim() == 4:                  # ISI frames: H holds the taps
                 det = self.amp.detect_taps(H, y, snr, x, lab, idx, cyclic=self.config.trunc == 'cyclic', frame_base=0)
@@ -230,6 +250,8 @@ def main(argv=None):
     ap.add_argument("--alphabet", default="16QAM")
     ap.add_argument("--iterations", type=int, default=20)
     ap.add_argument("--frames", type=int, default=1 << 20, help="frames per SNR point (all ranks together)")
+    ap.add_argument("--generator", default="torch", choices=["torch", "kernel"],
+                    help="kernel: the library's Philox stream (VAMP: frames drawn inside the SVD kernel, H never in HBM)")
     ap.add_argument("--chunk", type=int, default=1 << 18)
     ap.add_argument("--channel", default="iid", choices=["iid", "kronecker"])
     ap.add_argument("--rho-t", type=float, default=0.0)
@@ -248,7 +270,7 @@ def main(argv=None):
     cfg = Config(a.Nt, a.Na, a.Nr, a.Lin, a.Lh, batch=a.chunk, generator_mode='sparc', iterations=a.iterations,
                  alphabet=a.alphabet, channel_profile='uniform', channel_truncation=a.truncation, device=f"cuda:{local}")
     mc = MonteCarlo(cfg, a.alg, frames_per_point=a.frames, chunk=a.chunk, channel=a.channel, rho_t=a.rho_t, rho_r=a.rho_r,
-                    seed=a.seed, path=a.path)
+                    seed=a.seed, path=a.path, generator=a.generator)
     pts = mc.simulate(final=a.final, start=a.start, step=a.step)
     if mc.rank == 0:
         print(json.dumps(pts))

@@ -84,6 +84,33 @@ class VAMP(Detector):
         _cabi.check(rc, "ampsm_vamp_detect_from_h")
         return Detection(F, counters, iters, xmap, xmmse, var, traj)
 
+    def detect_generated(self, stream, first_frame: int, frames: int, SNR, frame_base=0, return_truth=False):
+        """vamp_model.py:44-61 for ``frames`` frames of a ``framegen.FrameStream``: the Jacobi SVD kernel draws every frame
+        (channel, message, noise) straight into its shared-memory tile, factorises it and feeds the VAMP iterations -- the
+        channel matrix never exists in HBM (``ampsm_vamp_detect_generated``).  Same frames, bit for bit, as
+        ``stream.frames(first_frame, frames, SNR)`` followed by ``detect_from_channel``."""
+        cfg, dev = self.config, stream.device
+        if not torch.cuda.is_available():
+            raise _cabi.AmpsmError("no CUDA device: the detector hot path has no CPU fallback")
+        n, N, F = cfg.Nr * cfg.Lout, cfg.Nt * cfg.Lin, int(frames)
+        x, sym, idx = stream.truth_buffers(F)
+        counters = torch.zeros(_cabi.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        iters = torch.empty(F, dtype=torch.int32, device=dev)
+        xmap = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        xmmse = torch.empty(F, N, 1, dtype=torch.complex64, device=dev) if self.outputs else None
+        var = torch.empty(F, N, 1, dtype=torch.float32, device=dev) if self.outputs else None
+        prob = self._problem(F, R=min(n, N), frame_base=frame_base)
+        ws = torch.empty(int(_cabi.lib().ampsm_vamp_from_h_workspace_bytes(prob, F)), dtype=torch.uint8, device=dev)
+        gen = stream.gen_struct(first_frame)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().ampsm_vamp_detect_generated(
+                prob, self._alphabet, gen, F, float(self.E / SNR), float(self.sparsity), x.data_ptr(), sym.data_ptr(), idx.data_ptr(),
+                ptr(xmap), ptr(xmmse), ptr(var), iters.data_ptr(), counters.data_ptr(), ws.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ampsm_vamp_detect_generated")
+        det = Detection(F, counters, iters, xmap, xmmse, var, None)
+        return (det, x, sym, idx) if return_truth else det
+
 
 def svd_batched(H, return_sweeps=False):
     """Thin SVD of a batch of wide complex64 matrices on the device, ``H (F, n, N) -> U (F, n, n), s (F, n), Vh (F, n, N)``

@@ -183,6 +183,43 @@ int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, in
                              uint64_t* counters, void* workspace, void* stream);
 
 /*
+ * On-device generation of Monte-Carlo frames with a counter-based generator (Philox4x32-10,
+ * csrc/framegen.cuh) -- the throughput-sweep replacement of the reference's per-epoch draws:
+ *   channel.py:53-55   H = (N(0,1) + j N(0,1)) sqrt(h_var / 2), h_var = 1 / Nr
+ *   data.py:74-91      one active antenna per section and one constellation point each -> x, Gray labels, flat positions
+ *   channel.py:113-115 y = H x + (N(0,1) + j N(0,1)) sqrt(sigma2 / 2)
+ * and, when the roots are given, BASELINE config 5's Kronecker correlation H = Rr_root G Rt_root.  Frame f of the call is
+ * frame counter_base + f of the stream `seed`: shards and chunks that cover the same global range draw the same frames.  The
+ * draws are not the reference's numpy / torch sequences; parity subsets keep the reference's own RNG path.
+ * Shapes: Lin = 1, 1 <= n <= 32, n <= N, N in {8, 16, 32, 64}, at most 32 sections, decision = 0.
+ */
+typedef struct {
+    uint64_t seed;           /* Philox key */
+    int64_t  counter_base;   /* global number of frame 0 of this call */
+    double   h_var;          /* variance of a complex channel entry, 1 / Nr in the reference (channel.py:55) */
+    const void* Rr_root;     /* complex64 [n][n] device pointer or NULL */
+    const void* Rt_root;     /* complex64 [N][N] device pointer or NULL */
+    int32_t  real_roots;     /* 1: the imaginary parts of both roots are zero (exponential correlation): half the work */
+    int32_t  reserved0;
+} ampsm_gen;
+
+/* H : complex64 [frames][n][N] and y : complex64 [frames][n] (either may be NULL); x : complex64 [frames][N],
+ * sym / idx : int64 [frames][L] as Data.generate_message returns them (data.py:88-90; idx counts from p->frame_base). */
+int ampsm_generate_frames(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm_gen* gen, int64_t frames, double sigma2,
+                          void* H, void* y, void* x, int64_t* sym, int64_t* idx, void* stream);
+
+/*
+ * VAMP on generated frames, the channel matrix never in HBM: the Jacobi SVD kernel draws every frame straight into its
+ * shared-memory tile (the same stream as ampsm_generate_frames, bit for bit), factorises it and hands s, Vh and U^H y to
+ * ampsm_vamp_detect -- vamp_model.py:44-61 for one batch of frames in two kernels.  x / sym / idx receive the ground truth the
+ * Loss counts against (required); workspace as ampsm_vamp_from_h_workspace_bytes(p, frames).
+ */
+int ampsm_vamp_detect_generated(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm_gen* gen, int64_t frames,
+                                double sigma2, double sparsity, void* x, int64_t* sym, int64_t* idx,
+                                void* xmap, void* xmmse, float* var, int32_t* iters, uint64_t* counters,
+                                void* workspace, void* stream);
+
+/*
  * SCAMP -- replaces scamp.SCAMP.forward (scamp.py:77-108): Tracker (8-25), SCAMPLayer iterations (43-59) with
  * the mean-only denoiser (61-68), exit on psi (105), Loss on (xmap, xmmse) (107).
  *   W : float [Lout][Lin] base matrix; A : complex64 [n][N] design matrix shared by all frames of the call
