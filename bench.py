@@ -633,6 +633,19 @@ def main():
         torch.cuda.synchronize()
         ch = det.counters_dict()
         ms_fh = e0.elapsed_time(e1)
+        # the same workload with the frames drawn inside the SVD kernel (csrc/framegen.cuh): channel, message and noise from the
+        # library's Philox stream, the channel matrix never in HBM (ampsm_vamp_detect_generated)
+        stream_g = pkg.FrameStream(cfgv, seed=97 + rank, device=dev)
+        for _ in range(2):
+            vfh.detect_generated(stream_g, 0, fv, snr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        detg = vfh.detect_generated(stream_g, 0, fv, snr)
+        e1.record()
+        torch.cuda.synchronize()
+        cg = detg.counters_dict()
+        ms_gen = e0.elapsed_time(e1)
         cv, msv = vout["exit"]
         cf, msf = vout["fixed_T"]
         vbytes = 8 * NR * NT + 8 * NR * NR + 4 * NR + 8 * NR + 8 * NT            # Vh, U, s, y, x_true: 25 472 B
@@ -660,6 +673,10 @@ def main():
                              "unit": "frame-iter/s", "ms": ms_fh,
                              "what": "ampsm_vamp_detect_from_h: one-sided Jacobi SVD of every frame's H (one warp per matrix) "
                                      "+ the iterations; per-rank time, not reduced over ranks"},
+            "generated": {"frames_per_s": world * cg["frames"] / (ms_gen * 1e-3), "value": world * cg["iters"] / (ms_gen * 1e-3),
+                          "unit": "frame-iter/s", "ms": ms_gen, "ier": cg["index_err"] / max(cg["frames"], 1),
+                          "what": "ampsm_vamp_detect_generated: every frame (channel, message, noise) drawn by Philox4x32-10 inside the "
+                                  "Jacobi SVD kernel, the channel matrix never in HBM, + the iterations; per-rank time"},
         }
     # ---- BASELINE config 3: VAMP Nt=128 Nr=64 Na=4 QPSK (vamp.py:159-191), per-frame SVD factors resident in HBM, through the
     # four-warps-per-frame register-resident kernel (csrc/vamp_quad.cu); per-rank device time

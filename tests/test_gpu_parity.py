@@ -115,6 +115,7 @@ def test_vamp_matches_reference_goldens(name, double, exp):
     xmmse = np.zeros((F, N), np.complex64)
     xmap = np.zeros((F, N), np.complex128)
     iters = np.zeros(F, np.int32)
+    slow = []
     for f in range(F):          # per-frame factors with their own sigma2: one call per frame
         cfg = config_from_meta(g["meta"], batch=1, device=DEV)
         amp = pkg.VAMP(cfg, trajectory=True, exp=exp, shift="reference" if exp == "f64" else "section", kernel=kernel)
@@ -133,6 +134,12 @@ def test_vamp_matches_reference_goldens(name, double, exp):
         # (slow = more than half of the iteration budget: vamp_c2 frame 1 takes 16 iterations in the reference, 11 in the oracle)
         if int(g["iters"][f]) <= cfg.N_Layers // 2:
             assert_counts_equal(f"{name}[{f}]", d.counters_dict(), want)
+        else:
+            slow.append((f, int(g["iters"][f]), iters[f]))
+    # the frames left out of the count comparison are listed and their share is bounded (half of the fixture at most: vamp_c3 sits at
+    # 2 dB, where three of its six frames use the whole iteration budget in the reference itself)
+    print(f"{name} [{kernel}/{exp}]: frames outside the count comparison (frame, reference iterations, kernel iterations): {slow}")
+    assert len(slow) <= max(1, F // 2), slow
     tight = 5e-7 if double else 1e-4     # see tests/test_oracle_golden.py for why not 1e-10
     if name.startswith("vamp_c5"):
         tight = 1e-3        # sigma2_tilde is posterior tail mass from the first iteration on (tests/test_oracle_golden.py)
