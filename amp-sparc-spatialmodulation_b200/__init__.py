@@ -12,8 +12,10 @@ from .loss import Loss
 from .bamp import BAMP
 from .scamp import SCAMP
 from .vamp import VAMP, svd_batched
+from .vamp2 import VAMP as VAMP2
 from .shrink import Shrink
 from .framegen import FrameStream
 from .simulate import MonteCarlo, device_frames, run_scamp
 
-__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "Shrink", "svd_batched", "MonteCarlo", "device_frames", "run_scamp"]
+__all__ = ["Config", "Channel", "Data", "Loss", "BAMP", "SCAMP", "VAMP", "VAMP2", "Shrink", "svd_batched", "FrameStream", "MonteCarlo", "device_frames",
+           "run_scamp"]

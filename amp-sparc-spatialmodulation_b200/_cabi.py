@@ -23,7 +23,7 @@ EXPORTS = ["ampsm_version", "ampsm_last_error", "ampsm_device_info", "ampsm_bamp
            "ampsm_vamp_detect_from_h", "ampsm_scamp_workspace_bytes", "ampsm_scamp_detect", "ampsm_scamp_taps_workspace_bytes", "ampsm_scamp_detect_taps",
            "ampsm_scamp_detect_host", "ampsm_loss_count", "ampsm_shrink", "ampsm_probe_fp32_tflops", "ampsm_probe_fp32x2_tflops", "ampsm_probe_fp64_tflops",
            "ampsm_launch_count", "ampsm_host_alloc", "ampsm_host_free", "ampsm_host_numa_info", "ampsm_generate_frames",
-           "ampsm_vamp_detect_generated"]
+           "ampsm_vamp_detect_generated", "ampsm_vamp2_detect"]
 
 
 class Alphabet(C.Structure):
@@ -71,6 +71,7 @@ def lib():
     vamp = [PP, AP, i64, i32, vp, i64, vp, i64, vp, i64, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_vamp_detect.argtypes = vamp + [vp]
     L.ampsm_vamp_detect_host.argtypes = vamp + [i32]
+    L.ampsm_vamp2_detect.argtypes = [PP, AP, i64, vp, i64, vp, i64, vp, i64, vp, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ampsm_svd_batched.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp, vp]
     L.ampsm_vamp_from_h_workspace_bytes.argtypes = [PP, i64]
     L.ampsm_vamp_from_h_workspace_bytes.restype = i64

@@ -95,7 +95,8 @@ template <bool EXP64, typename CT>
 __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const CT* s,
                                      const typename RealOf<CT>::type* tau_vec, typename RealOf<CT>::type tau_scalar,
                                      bool halve, double global_shift, float2* xh_out, float* var_out,
-                                     typename ExpT<EXP64>::type* scr, int tau_div = 1, bool scr_per_warp = false) {
+                                     typename ExpT<EXP64>::type* scr, int tau_div = 1, bool scr_per_warp = false,
+                                     bool var_second_moment = false) {
     using E = typename ExpT<EXP64>::type;
     using RT = typename RealOf<CT>::type;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -164,6 +165,18 @@ __device__ inline void block_denoise(const Geom& g, const DevAlphabet& al, const
                 RT tau = tau_vec ? tau_vec[(base + m) / tau_div] : tau_scalar;
                 if (halve) tau = tau / (RT)2;
                 CT q = cdiv_real(s[base + m], tau);
+                if (var_second_moment) {       // vamp2.py:84-87: E|s|^2 - |E s|^2, as written there (can round below zero)
+                    double m2 = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < al.K; ++k) {
+                        E e = exp_shifted<EXP64>(sm_exponent<true>(q, al, k), smax);
+                        const double mag = hypot(al.re[k], al.im[k]);
+                        m2 += mag * mag * (double)e;
+                    }
+                    const double xa = hypot(xr, xi);
+                    var_out[base + m] = (float)(m2 / Z - xa * xa);
+                    continue;
+                }
                 double spread = 0.0;
 #pragma unroll 4
                 for (int k = 0; k < al.K; ++k) {

@@ -422,6 +422,26 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
     return launch_vamp_generic(k, is_double != 0, p->exp_f64 != 0, (cudaStream_t)stream);
 }
 
+// vamp2.py: the damped direct form (csrc/vamp2.cu); complex64, generic kernel
+int ampsm_vamp2_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, const void* U, int64_t U_frame_stride,
+                       const void* s, int64_t s_frame_stride, const void* Vh, int64_t Vh_frame_stride, const void* y, double sigma2,
+                       const float* sigma2_per_frame, double damping, const void* x_true, const int64_t* sym_true,
+                       const int64_t* idx_true, void* xmap, void* xmmse, float* var, int32_t* iters, float* traj, uint64_t* counters,
+                       void* stream) {
+    VampArgs k{};
+    if (p && p->decision == 2) { set_error("vamp2: the Shrink('bayes') denoiser of mode 'random' is ampsm_shrink; the detector runs the sectioned modes"); return AMPSM_EINVAL; }
+    if (int e = make_geom(p, a, &k.g, &k.al, true)) return e;
+    if (int e = check_loss_io(x_true, sym_true, idx_true)) return e;
+    if (frames < 0 || (frames > 0 && (!U || !s || !Vh || !y))) { set_error("vamp2: U / s / Vh / y is NULL or frames < 0"); return AMPSM_EINVAL; }
+    if (frames == 0) return 0;
+    k.U = U; k.U_stride = U_frame_stride; k.s = s; k.s_stride = s_frame_stride; k.Vh = Vh; k.Vh_stride = Vh_frame_stride;
+    k.y = y; k.sigma2_d = sigma2; k.sigma2_pf = sigma2_per_frame; k.damping = (float)damping;
+    k.io.x_true = (const float2*)x_true; k.io.sym_true = (const long long*)sym_true; k.io.idx_true = (const long long*)idx_true;
+    k.io.counters = (unsigned long long*)counters;
+    k.xmap = xmap; k.xmmse = (float2*)xmmse; k.var = var; k.iters = iters; k.traj = traj; k.frames = frames;
+    return launch_vamp2(k, p->exp_f64 != 0, (cudaStream_t)stream);
+}
+
 int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double, const void* U,
                            int64_t U_frame_stride, const void* s, int64_t s_frame_stride, const void* Vh,
                            int64_t Vh_frame_stride, const void* y, double sigma2, const float* sigma2_per_frame,

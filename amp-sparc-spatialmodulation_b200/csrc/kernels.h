@@ -66,6 +66,7 @@ struct VampArgs {
     float* traj;
     long long frames;
     int stage_Vh;
+    float damping;               // vamp2.py only: rho of VAMPLayer (vamp2.py:30, 50)
     unsigned opaque_zero;        // always 0; the kernels use it for scheduling ties the compiler cannot fold (fastops.cuh chain_tie)
 };
 
@@ -135,6 +136,7 @@ int launch_bamp_fast(const BampArgs& a, cudaStream_t stream);       // AMPSM_ENO
 int launch_vamp_generic(const VampArgs& a, bool is_double, bool exp64, cudaStream_t stream);
 int launch_vamp_fast(const VampArgs& a, cudaStream_t stream);       // complex64 32 x 64 factors, else AMPSM_ENOFIT
 int launch_vamp_quad(const VampArgs& a, cudaStream_t stream);
+int launch_vamp2(const VampArgs& a, bool exp64, cudaStream_t stream);   // vamp2.py, the damped direct form (generic kernel only)
 int launch_vamp_dbl(const VampArgs& a, cudaStream_t stream);        // complex128 64 x 128 factors in registers (FP64 pipe), else AMPSM_ENOFIT
 int launch_scamp(const ScampArgs& a, bool exp64, cudaStream_t stream);
 long long scamp_workspace_bytes(const Geom& g, long long frames);

@@ -149,6 +149,20 @@ int ampsm_vamp_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t f
                       void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
                       uint64_t* counters, void* stream);
 
+/*
+ * The reference's second VAMP -- replaces vamp2.VAMP.forward (vamp2.py:104-131: "direct implementation of Rangan (with
+ * damping)", imported by none of the reference's drivers): Tracker (12-26), VAMPLayer (52-76) with its own denoiser (78-87:
+ * variance E|s|^2 - |E s|^2), exit on var (124), Loss on (r, xmmse) (128).  complex64 factors as ampsm_vamp_detect;
+ * damping = the `damping` argument of vamp2.VAMP.  traj : float [frames][max_iters][3] = {gamma, mean var, mse}.
+ */
+int ampsm_vamp2_detect(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames,
+                       const void* U, int64_t U_frame_stride, const void* s, int64_t s_frame_stride,
+                       const void* Vh, int64_t Vh_frame_stride, const void* y,
+                       double sigma2, const float* sigma2_per_frame, double damping,
+                       const void* x_true, const int64_t* sym_true, const int64_t* idx_true,
+                       void* xmap, void* xmmse, float* var, int32_t* iters, float* traj,
+                       uint64_t* counters, void* stream);
+
 int ampsm_vamp_detect_host(const ampsm_problem* p, const ampsm_alphabet* a, int64_t frames, int is_double,
                            const void* U, int64_t U_frame_stride, const void* s, int64_t s_frame_stride,
                            const void* Vh, int64_t Vh_frame_stride, const void* y,

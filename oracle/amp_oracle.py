@@ -11,6 +11,7 @@ What it follows (reference file:line, all under /root/reference):
   * ``bamp_detect``   -> bamp.py:12-25 (state), 59-64 (one iteration), 116-143 (loop + allclose exit)
   * ``scamp_detect``  -> scamp.py:8-25, 43-59, 77-108
   * ``vamp_detect``   -> vamp.py:12-28, 66-94, 159-191
+  * ``vamp2_detect``  -> vamp2.py:12-26, 52-87, 117-127 (the damped direct form no driver of the reference imports)
 
 Frame semantics: the reference couples the frames of a batch (batch-global soft-max shift bamp.py:70, batch-global
 exit bamp.py:140, batch-pooled variance vamp.py:85) and is numerically unusable for B>1, so a
@@ -312,6 +313,94 @@ def vamp_detect(U, s, Vh, y, sigma2, sparsity, symbols, L, M, max_iters, early_e
             active = a[~done]
     return dict(xmap=r.astype(C64) if not double else r, xmmse=xmmse, var=var, iters=iters, traj=traj,
                 y_tilde=y_tilde)
+
+
+def sm_denoiser_v2(s, tau, symbols, L, M, shift='reference'):
+    """``vamp2.VAMPLayer.segmented_denoiser`` (vamp2.py:78-87): the same soft-max as vamp.py's (scalar ``tau``, not halved,
+    frame-global ``max|x|`` shift) but the variance is ``E|s|^2 - |E s|^2`` -- one difference of two nearly equal numbers
+    where the other denoisers add two non-negative terms (it can round to a negative float32).  s: (F, L*M) complex64,
+    tau: (F,) float32."""
+    F = s.shape[0]
+    K = symbols.shape[0]
+    s4 = np.ascontiguousarray(s, dtype=C64).reshape(F, L, M, 1)
+    tau4 = np.asarray(tau, dtype=F32).reshape(F, 1, 1, 1)
+    with np.errstate(all='ignore'):
+        q = (s4 / tau4).astype(C64)
+        sym = symbols.astype(np.complex128).reshape(1, 1, 1, K)
+        x = (q.astype(np.complex128) * sym.conj()).real
+        if shift == 'reference':
+            ref = np.abs(x).reshape(F, -1).max(axis=1).reshape(F, 1, 1, 1)
+        else:
+            ref = x.reshape(F, L, M * K).max(axis=2).reshape(F, L, 1, 1)
+        eta = np.exp(x - ref)
+        norm = eta.sum(axis=-1).sum(axis=2, keepdims=True)             # (F, L, 1)
+        xmmse = (sym * eta).sum(axis=-1) / norm
+        var = (np.abs(sym) ** 2 * eta).sum(axis=-1) / norm - np.abs(xmmse) ** 2
+    return xmmse.reshape(F, L * M).astype(C64), var.reshape(F, L * M).astype(F32)
+
+
+def vamp2_detect(U, s, Vh, y, sigma2, symbols, L, M, max_iters, damping=1.0, early_exit=True, shift='reference', x_true=None):
+    """The reference's second VAMP (``vamp2.py``: "direct implementation of Rangan (with damping)"), which no driver of the
+    reference imports; restated line by line: Tracker vamp2.py:12-26, one layer 52-76, loop and exit 117-127.  Frames are
+    independent batch=1 calls as everywhere in this oracle.  U: (F,n,R), s: (F,R), Vh: (F,R,N), y: (F,n); sigma2 scalar or (F,)."""
+    y = np.ascontiguousarray(y, dtype=C64)
+    F, n = y.shape
+    U = np.ascontiguousarray(U, dtype=C64)
+    Vh = np.ascontiguousarray(Vh, dtype=C64)
+    s = np.ascontiguousarray(s, dtype=F32)
+    R, N = Vh.shape[-2:]
+    sF = np.broadcast_to(s.reshape(-1, R), (F, R))
+    s2 = (sF ** 2).astype(F32)
+    noise_var = np.broadcast_to(np.asarray(sigma2, dtype=np.float64).reshape(-1), (F,)).copy()
+    eta = N / R                                                         # vamp2.py:26 (python float)
+    rho = float(damping)
+    VMIN, VMAX = F32(1.0e-11), F32(1.0e11)                              # vamp2.py:48-49
+
+    def mv(Mat, vec, adj=False):
+        Mm = np.conj(np.swapaxes(Mat, -1, -2)) if adj else Mat
+        if Mat.ndim == 2:
+            return vec @ Mm.T
+        return np.matmul(Mm, vec[..., None])[..., 0]
+
+    with np.errstate(all='ignore'):
+        y_tilde = (mv(U, y, adj=True) / sF.astype(C64)).astype(C64)     # vamp2.py:22: complex64 / float32 tensor
+    r = np.zeros((F, N), C64)
+    var = np.ones((F, N), F32)
+    xmmse = np.zeros((F, N), C64)
+    gamma = np.ones(F, F32)                                             # torch.tensor(1.0)
+    iters = np.zeros(F, np.int32)
+    active = np.arange(F)
+    traj = {k: np.full((max_iters, F), np.nan) for k in ('gamma', 'var', 'mse')}
+    for t in range(max_iters):
+        a = active
+        if a.size == 0:
+            break
+        with np.errstate(all='ignore'):
+            xm, vr = sm_denoiser_v2(r[a], gamma[a], symbols, L, M, shift)                   # vamp2.py:61
+            xd = (F32(rho) * xm + F32(1 - rho) * xmmse[a]).astype(C64)                      # vamp2.py:62 (python floats x complex64)
+            alpha = (vr.mean(axis=1, dtype=F32) * gamma[a]).astype(F32)                     # vamp2.py:63
+            al = alpha[:, None]
+            r_tilde = ((xd - al * r[a]) / (F32(1) - al)).astype(C64)                        # vamp2.py:65
+            g_tilde = (gamma[a] * (F32(1) - alpha) / alpha).astype(F32)                     # vamp2.py:66-68
+            g_tilde = np.minimum(np.maximum(g_tilde, VMIN), VMAX)
+            nv = noise_var[a].astype(F32)
+            d = (s2[a] / (s2[a] + (nv * g_tilde)[:, None])).astype(F32)                     # vamp2.py:70
+            dm = d.mean(axis=1, dtype=F32)
+            g_new = (g_tilde * dm / (F32(eta) - dm)).astype(F32)                            # vamp2.py:71
+            g_next = (F32(rho) * g_new + F32(1 - rho) * gamma[a]).astype(F32)               # vamp2.py:72 (73-74 are dead code)
+            resid = (y_tilde[a] - mv(Vh[a] if Vh.ndim == 3 else Vh, r_tilde)).astype(C64)
+            upd = mv(Vh[a] if Vh.ndim == 3 else Vh, ((d / dm[:, None]) * resid).astype(C64), adj=True)
+            r_new = (r_tilde + F32(eta) * upd).astype(C64)                                  # vamp2.py:76
+        done = _allclose_rows(vr, var[a])
+        r[a], xmmse[a], var[a], gamma[a] = r_new, xd, vr, g_next
+        iters[a] = t + 1
+        traj['gamma'][t:, a] = g_next
+        traj['var'][t:, a] = vr.mean(axis=1, dtype=np.float64)
+        if x_true is not None:
+            traj['mse'][t:, a] = _mse(xd, x_true[a])
+        if early_exit:
+            active = a[~done]
+    return dict(xmap=r, xmmse=xmmse, var=var, iters=iters, traj=traj, y_tilde=y_tilde)
 
 
 def _denoise_double(r, sig2, symbols, L, M, shift):

@@ -19,6 +19,7 @@ sys.path.insert(0, REF)
 import bamp as ref_bamp      # noqa: E402
 import scamp as ref_scamp    # noqa: E402
 import vamp as ref_vamp      # noqa: E402
+import vamp2 as ref_vamp2    # noqa: E402
 from channel import Channel  # noqa: E402
 from config import Config    # noqa: E402
 from data import Data        # noqa: E402
@@ -160,6 +161,46 @@ def run_vamp(name, args, kwargs, snrs_db, frames, seed, double=False, kronecker=
     xm32 = [np.asarray(v).astype(np.complex64) for v in out['xmap']]
     bl, gidx = batch_loss((args, kwargs), F, xm32, out['xmmse'], out['x'], out['sym'], out['idx'], N)
     save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='vamp', double=double, kronecker=kronecker))
+
+
+def run_vamp2(name, args, kwargs, snrs_db, frames, seed, damping):
+    """vamp2.py (the damped direct form of Rangan's VAMP that no driver of the reference imports): the reference's own class
+    stepped layer by layer on the reference's own draws, fed torch.linalg.svd like its sibling (vamp_model.py:56-61)."""
+    c = cfg(*args, **kwargs)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ch, da, amp = Channel(c), Data(c), ref_vamp2.VAMP(c, damping)
+    N, n, T = c.Nt * c.Lin, c.Nr * c.Lout, c.N_Layers
+    out = {k: [] for k in ('A', 'U', 's', 'Vh', 'y', 'x', 'sym', 'idx', 'sigma2', 'snr_db', 'xmap', 'xmmse', 'var', 'iters',
+                           'gamma', 'varm', 'mse', 'loss')}
+    for snr_db in snrs_db:
+        snr = 10 ** (snr_db / 10)
+        for _ in range(frames):
+            _, A = ch.generate_as_sparc()
+            U, s, Vh = torch.linalg.svd(A, full_matrices=False)
+            x, sym, i = da.generate_message()
+            y = A @ x + ch.awgn(snr)
+            tr = ref_vamp2.Tracker(U, s, Vh, y, x, amp.E / snr)
+            gam, varm, mse = (np.full(T, np.nan) for _ in range(3))
+            for t, layer in enumerate(amp.layers):
+                prev = tr.var
+                layer(tr)
+                gam[t:] = float(tr.gamma)
+                varm[t:] = float(tr.var.mean())
+                mse[t:] = mse_of(tr.xmmse, x)
+                if torch.allclose(tr.var, prev):
+                    break
+            L = amp(U, s, Vh, y, snr, x, sym, i)
+            assert L.loss['T'] == t + 1
+            for k, v in (('A', A.numpy()), ('U', U.numpy()), ('s', s.numpy()), ('Vh', Vh.numpy()), ('y', y.numpy().reshape(n)),
+                         ('x', x.numpy().reshape(N)), ('sym', sym), ('idx', i), ('sigma2', amp.E / snr), ('snr_db', snr_db),
+                         ('xmap', tr.r.numpy().reshape(N)), ('xmmse', tr.xmmse.numpy().reshape(N)),
+                         ('var', tr.var.numpy().reshape(N)), ('iters', t + 1), ('gamma', gam), ('varm', varm), ('mse', mse),
+                         ('loss', loss_vec(L))):
+                out[k].append(v)
+    F = len(out['U'])
+    bl, gidx = batch_loss((args, kwargs), F, out['xmap'], out['xmmse'], out['x'], out['sym'], out['idx'], N)
+    save(name, out, bl, gidx, dict(args=args, kwargs=kwargs, seed=seed, alg='vamp2', damping=damping))
 
 
 def run_scamp(name, args, kwargs, snrs_db, frames, seed, res):
@@ -309,6 +350,11 @@ if __name__ == "__main__":
         run_vamp('vamp_c5_rho07', (64, 1, 32, 1, 1, 'QPSK'), {}, [6, 12], 6, seed=31, kronecker=(0.7, 0.7))
     if want('vamp_c5_rho09'):
         run_vamp('vamp_c5_rho09', (64, 1, 32, 1, 1, 'QPSK'), {}, [10, 18], 6, seed=32, kronecker=(0.9, 0.9))
+    # vamp2.py: the damped direct form (undamped and damping 0.97, the layer's own default)
+    if want('vamp2_d100'):
+        run_vamp2('vamp2_d100', (64, 4, 32, 1, 1, 'QPSK'), {}, [4, 10], 4, seed=41, damping=1.0)
+    if want('vamp2_d097'):
+        run_vamp2('vamp2_d097', (32, 2, 16, 1, 1, '16QAM'), {}, [8, 16], 4, seed=42, damping=0.97)
     # 'random' mode (i.i.d. prior, random_denoiser bamp.py:79-97, random_decision loss.py:252-280; B=1 only in the reference)
     if want('bamp_random'):
         run_bamp('bamp_random', (32, 4, 16, 1, 1, 'QPSK'), dict(mode='random'), [0, 6, 12], 8, seed=10)
