@@ -629,3 +629,54 @@ def test_vamp_complex128_register_kernel_matches_generic_double_kernel(monkeypat
     pf = pkg.VAMP(cfg, outputs=True).detect(U[:1].expand(70, -1, -1).contiguous(), s[:1].expand(70, -1).contiguous(),
                                             Vh[:1].expand(70, -1, -1).contiguous(), yd[:70], snr, x[:70], lab[:70 * cfg.L], idx[:70 * cfg.L])
     assert torch.equal(sh.xmmse, pf.xmmse)
+
+
+def test_full_size_snr_point_is_the_sum_of_its_frames():
+    """BASELINE config 2 at its full size -- 1 048 576 frames in ONE call (17.9 GB of channel matrices drawn by the generator
+    kernel) -- through size-independent properties: the call is deterministic, every frame's estimate, exit iteration and decision
+    equal what the same frame gives in a 4 096-frame call of its own (frames are independent: nothing may depend on the launch
+    size, the grid-stride assignment or the position in the batch), and the counters of the whole point equal the sum over 16
+    chunk calls.  The oracle meets these kernels on 10 k-frame subsets in tests/test_gpu_oracle_scale.py."""
+    F, snr = 1 << 20, 10 ** 1.5
+    cfg = c2(F)
+    st = pkg.FrameStream(cfg, seed=2024)
+    H, y, x, lab, idx = st.frames(0, F, snr)
+    amp = pkg.BAMP(cfg, outputs=True)
+    whole = amp.detect(H, y, snr, x, lab, idx)
+    cw = whole.counters_dict()
+    assert cw["frames"] == F and cw["nan_frames"] == 0 and F <= cw["iters"] <= 20 * F
+    again = amp.detect(H, y, snr, x, lab, idx)
+    assert torch.equal(again.xmmse, whole.xmmse) and torch.equal(again.iters, whole.iters) and ints(again.counters_dict()) == ints(cw)
+    for lo in (0, 123_456, F - 4096):                  # windows at both ends and at an odd offset
+        sl = slice(lo, lo + 4096)
+        small = amp.detect(H[sl], y[sl], snr, x[sl], lab[sl], idx[sl] - lo * cfg.N)
+        assert torch.equal(small.xmmse, whole.xmmse[sl]) and torch.equal(small.xmap, whole.xmap[sl])
+        assert torch.equal(small.iters, whole.iters[sl]) and torch.equal(small.var, whole.var[sl])
+    tot = {k: 0 for k in INT_KEYS + ["iters"]}
+    step = F // 16
+    quiet = pkg.BAMP(cfg, outputs=False)
+    for lo in range(0, F, step):
+        sl = slice(lo, lo + step)
+        c = quiet.detect(H[sl], y[sl], snr, x[sl], lab[sl], idx[sl], frame_base=lo).counters_dict()
+        for k in tot:
+            tot[k] += c[k]
+    for k in tot:
+        if k != "index_bit_err":                        # its truncation follows the frames of the CALL (loss.py:20)
+            assert tot[k] == cw[k], k
+    del H, whole, again
+    # VAMP at the same size with the frames drawn inside the SVD kernel: the point is the sum of its chunks, and a window of it
+    # equals the same frame numbers detected on their own
+    vamp = pkg.VAMP(cfg, outputs=False)
+    vw = vamp.detect_generated(st, 0, F, snr).counters_dict()
+    assert vw["frames"] == F and vw["nan_frames"] == 0
+    vt = {k: 0 for k in INT_KEYS + ["iters"]}
+    for lo in range(0, F, step):
+        c = vamp.detect_generated(st, lo, step, snr, frame_base=lo).counters_dict()
+        for k in vt:
+            vt[k] += c[k]
+    for k in vt:
+        if k != "index_bit_err":
+            assert vt[k] == vw[k], k
+    a = pkg.VAMP(cfg, outputs=True).detect_generated(st, 0, 1 << 17, snr)
+    b = pkg.VAMP(cfg, outputs=True).detect_generated(st, 100_000, 2048, snr)
+    assert torch.equal(b.xmmse, a.xmmse[100_000:102_048]) and torch.equal(b.iters, a.iters[100_000:102_048])
