@@ -293,7 +293,7 @@ def cpu_svd(H):
     return U.contiguous().numpy(), s.contiguous().numpy(), Vh.contiguous().numpy()
 
 
-def run_vamp_point(cfg_args, alphabet, F, snr_db, seed, extra_share):
+def run_vamp_point(cfg_args, alphabet, F, snr_db, seed, extra_share, double=False):
     Nt, Na, Nr = cfg_args
     cfg = pkg.Config(Nt, Na, Nr, 1, 1, batch=F, generator_mode='sparc', iterations=20, alphabet=alphabet,
                      channel_profile='uniform', device=DEV)
@@ -305,21 +305,24 @@ def run_vamp_point(cfg_args, alphabet, F, snr_db, seed, extra_share):
         sl = slice(None) if frames is None else frames
         Vf = jitter(Vh[sl], *mjit) if mjit else Vh[sl]
         return ao.vamp_detect(U[sl], s[sl], Vf, yy, float(sigma2), cfg.Na / cfg.Nt, cfg.symbols, cfg.L, cfg.M, cfg.N_Layers,
-                              shift='section')
+                              shift='section', double=double)
     ref = run_oracle(y)
     dU, ds, dV, dy, dx = t(U), t(s), t(Vh), t(y), t(x)
+    if double:                      # the reference fed with upcast inputs (vamp.py:12-28 in float64; xmmse / var still float32, vamp.py:119)
+        dU, ds, dV, dy = dU.to(torch.complex128), ds.to(torch.float64), dV.to(torch.complex128), dy.to(torch.complex128)
     idx = (pos + (np.arange(F) * cfg.N)[:, None]).reshape(-1)
-    det = pkg.VAMP(cfg, kernel='fast', outputs=True).detect(dU, ds, dV, dy, snr, dx, lab, idx)
+    kern = 'auto' if double else 'fast'            # complex128: 'auto' takes the register-resident DFMA kernel at this shape
+    det = pkg.VAMP(cfg, kernel=kern, outputs=True).detect(dU, ds, dV, dy, snr, dx, lab, idx)
 
     def rerun(keep, idx_k, lab_k):
         ck = pkg.Config(Nt, Na, Nr, 1, 1, batch=len(keep), generator_mode='sparc', iterations=20, alphabet=alphabet,
                         channel_profile='uniform', device=DEV)
         kk = torch.as_tensor(keep, device=DEV)
-        return pkg.VAMP(ck, kernel='fast', outputs=False).detect(dU[kk], ds[kk], dV[kk], dy[kk], snr, dx[kk], lab_k,
+        return pkg.VAMP(ck, kernel=kern, outputs=False).detect(dU[kk], ds[kk], dV[kk], dy[kk], snr, dx[kk], lab_k,
                                                                  idx_k).counters_dict()
     # VAMP only: at most one frame in 10^4 may stay uncertified by the 24 perturbed oracle runs (it is listed like the others and
     # removed from the counter comparison); BAMP and SCAMP allow none
-    return finish(f"VAMP {Nt}x{Nr} {alphabet} Na={Na} @ {snr_db} dB", cfg, gpu_result(det, F, cfg.N), ref, run_oracle, y, rerun,
+    return finish(f"VAMP{' complex128' if double else ''} {Nt}x{Nr} {alphabet} Na={Na} @ {snr_db} dB", cfg, gpu_result(det, F, cfg.N), ref, run_oracle, y, rerun,
                   x, lab, pos, extra_share, mjit=True, max_unexplained=max(1, F // 10000))
 
 
@@ -339,13 +342,22 @@ def test_vamp_c3_quad_kernel_counts_equal_oracle(snr_db):
     run_vamp_point((128, 4, 64), 'QPSK', 2000, snr_db, seed=3100 + int(snr_db), extra_share=3e-3)
 
 
+@pytest.mark.parametrize("snr_db", [0.0, 4.0])
+def test_vamp_c3_complex128_kernel_counts_equal_oracle(snr_db):
+    """BASELINE config 3 with complex128 factors (the reference fed with upcast inputs) through the register-resident DFMA kernel
+    (csrc/vamp_dbl.cu), 1 k frames per point, against the oracle's float64 linear stage."""
+    run_vamp_point((128, 4, 64), 'QPSK', 1000, snr_db, seed=3200 + int(snr_db), extra_share=3e-3, double=True)
+
+
 # ------------------------------------------------------------------------------------------------------------- SCAMP
 @pytest.mark.parametrize("exp", ["f64", "f32"])
-@pytest.mark.parametrize("shape,F,ebn0_db", [((64, 2, 8, 8, 3), 256, 5.0), ((128, 8, 32, 16, 3), 256, 6.0), ((64, 2, 8, 8, 3), 200, 8.0)])
+@pytest.mark.parametrize("shape,F,ebn0_db", [((64, 2, 8, 8, 3), 256, 5.0), ((128, 8, 32, 16, 3), 256, 6.0), ((64, 2, 8, 8, 3), 200, 8.0),
+                                             ((512, 8, 32, 32, 3), 128, 6.0)])
 def test_scamp_tensor_core_path_matches_oracle(shape, F, ebn0_db, exp):
     """The tcgen05 SCAMP path (batches >= 128 frames; scamp.py:43-59, 77-108) against ``ao.scamp_detect`` on the reference's
     own coupled design matrix (channel.py:76-96) -- a C4-lite instance (Nt = 128, Na = 8, Nr = 32, Lin = 16, Lh = 3, tail:
-    A 576 x 2048) included; ragged frame count in the third case.  SCAMP's exit test compares psi = 1 - sum|x|^2/Na, a
+    A 576 x 2048) and BASELINE config 4 itself (Nt = 512, Na = 8, Nr = 32, Lin = 32, Lh = 3: A 1088 x 16384, 128 frames -- the
+    oracle needs ~20 s per run at this size) included; ragged frame count in the third case.  SCAMP's exit test compares psi = 1 - sum|x|^2/Na, a
     difference of two numbers near 1, at 1e-8 + 1e-5 psi: it sits on float32 resolution, so exit iterations are compared
     against the oracle's own perturbed runs (see the module docstring) with ``exp='f64'`` (the denoiser evaluated in float64 like
     the reference's, scamp.py:61-68).  The default ``exp='f32'`` denoiser differs from the float64 one in the last bit of the
@@ -353,6 +365,8 @@ def test_scamp_tensor_core_path_matches_oracle(shape, F, ebn0_db, exp):
     80 % equal, 99 % within one iteration, the mean within 1 %; with ``exp='f64'`` 88 % / 99 % (the 3xTF32 tensor-core products
     carry ~4 ulps of error against the oracle's float32 dot products; the oracle agrees with its own 8-ulp run on 95-97 %)."""
     Nt, Na, Nr, Lin, Lh = shape
+    if Nt == 512 and exp == "f64":
+        pytest.skip("BASELINE config 4 at full size (A 1088 x 16384, L = 256 sections of 64): the fused float32-exp path is the one the bench runs")
     cfg = pkg.Config(Nt, Na, Nr, Lin, Lh, batch=F, generator_mode='sparc', iterations=20, alphabet='QPSK',
                      channel_profile='uniform', channel_truncation='tail', device='cpu')
     np.random.seed(5)
