@@ -8,11 +8,13 @@
 //
 // Method: the rows of W = H are orthogonalised in place by plane rotations (no Gram matrix: the condition number is
 // not squared, float32 is enough also for correlated channels); the same rotations applied to Q = I give Q = U^H, so
-// that W = U^H H = diag(s) Vh at convergence.  A sweep visits all n(n-1)/2 row pairs in the round-robin (tournament)
-// order: 31 steps of 16 disjoint pairs.  Two lanes serve a pair -- lane (j,h) takes the columns c = h (mod 2) of both
-// rows: it loads them once into registers (conflict-free 8-byte accesses, padded rows), forms the three inner products,
-// combines them with its partner by one shuffle round, rotates in registers and stores back.  A pair whose rows are
-// already orthogonal to 4e-7 (relative) is skipped; the sweep loop ends when a whole sweep rotated nothing.
+// that W = U^H H = diag(s) Vh at convergence.  A sweep visits all n(n-1)/2 row pairs in 31 steps of 16 disjoint pairs.  Two
+// lanes serve a pair -- lane (j,h) takes half of the columns of both rows (conflict-free 8-byte accesses, padded rows), forms
+// the three inner products, combines them with its partner by one shuffle round and rotates in registers.  The order of the
+// pairs is a recursive halving in which one row of every pair is STATIONARY for a whole phase and lives in registers (round 2b;
+// the round-robin tournament of the first version moved both rows through shared memory every step and was bound by exactly
+// that traffic: +34 % matrices/s).  A pair whose rows are already orthogonal to 4e-7 (relative) is skipped; the sweep loop ends
+// when a whole sweep rotated nothing.
 #include <cstdlib>
 
 #include "framegen.cuh"
@@ -251,71 +253,81 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                     __syncwarp();
                 }
             } else {
-            for (int step = 0; step < kSvdRows - 1; ++step) {
-                // tournament pairing: position 31 stays, the others rotate
-                int p, q;
-                if (j == 0) {
-                    p = kSvdRows - 1;
-                    q = step;
-                } else {
-                    p = step + j;
-                    if (p >= kSvdRows - 1) p -= kSvdRows - 1;
-                    q = step - j;
-                    if (q < 0) q += kSvdRows - 1;
-                }
+            // Pair ordering: recursive halving with a STATIONARY row.  Phase G = 16, 8, 4, 2, 1: the 32 rows form super-blocks of
+            // 2G rows; lane pair j = (sb, i) keeps row p = 2G sb + i of the first half in REGISTERS for the whole phase and meets
+            // the rows q = 2G sb + G + (i + s) mod G of the second half, s = 0 .. G-1 -- 16 + 8 + 4 + 2 + 1 = 31 steps of 16
+            // disjoint pairs that cover every pair once, like the round-robin tournament of the first version, but only ONE row
+            // of a pair crosses shared memory per step (the kernel is bound by exactly that traffic: ncu, data pipe 91 % busy).
+            // Neighbouring lane pairs still touch rows that differ mod 16, so the accesses stay conflict-free.
+            for (int G = kSvdRows / 2; G >= 1; G >>= 1) {
+                const int sb = j / G, i = j - sb * G;
+                const int p = sb * 2 * G + i;
                 float2* wa = W + p * Sh::wstride;
-                float2* wb = W + q * Sh::wstride;
-                float2 a[HC], b[HC];
-                float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
+                float2 a[HC];
 #pragma unroll
-                for (int c = 0; c < HC; ++c) {
-                    a[c] = wa[svd_col<NC>(c, h)];
-                    b[c] = wb[svd_col<NC>(c, h)];
-                    alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
-                    beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
-                    gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
-                    gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
-                }
-                alpha += __shfl_xor_sync(0xffffffffu, alpha, 1);
-                beta += __shfl_xor_sync(0xffffffffu, beta, 1);
-                gr += __shfl_xor_sync(0xffffffffu, gr, 1);
-                gi += __shfl_xor_sync(0xffffffffu, gi, 1);
-                const float g2 = gr * gr + gi * gi;
-                const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
-                if (rot) {
-                    // b~ = e^{-i phi} b makes <a, b~> = |gamma| real; then the real Jacobi rotation:
-                    // zeta = (beta - alpha) / (2 |gamma|), t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), c = 1/sqrt(1+t^2), s = c t
-                    const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
-                    const float pr = gr * ginv, pi = -gi * ginv;                    // e^{-i phi} = conj(gamma) / |gamma|
-                    const float zeta = (beta - alpha) * (0.5f * ginv);
-                    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
-                    const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
-                    const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
-                    // a' = c a - (s p) b ; b' = s a + (c p) b
+                for (int c = 0; c < HC; ++c) a[c] = wa[svd_col<NC>(c, h)];
+                bool a_dirty = false;
+                for (int s = 0; s < G; ++s) {
+                    const int q = sb * 2 * G + G + ((i + s) & (G - 1));
+                    float2* wb = W + q * Sh::wstride;
+                    float2 b[HC];
+                    float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
 #pragma unroll
                     for (int c = 0; c < HC; ++c) {
-                        const float2 x = a[c], y = b[c];
-                        wa[svd_col<NC>(c, h)] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                        wb[svd_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        b[c] = wb[svd_col<NC>(c, h)];
+                        alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
+                        beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
+                        gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
+                        gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
                     }
-                    if constexpr (WITHY) {
-                        if (h == 0) {           // the same rotation on the two entries of z = Q y
-                            const float2 x = Q[p], y = Q[q];
-                            Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                            Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
-                        }
-                    } else {
-                        float2* qa = Q + p * Sh::qstride;
-                        float2* qb = Q + q * Sh::qstride;
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, 1);
+                    beta += __shfl_xor_sync(0xffffffffu, beta, 1);
+                    gr += __shfl_xor_sync(0xffffffffu, gr, 1);
+                    gi += __shfl_xor_sync(0xffffffffu, gi, 1);
+                    const float g2 = gr * gr + gi * gi;
+                    const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
+                    if (rot) {
+                        // b~ = e^{-i phi} b makes <a, b~> = |gamma| real; then the real Jacobi rotation:
+                        // zeta = (beta - alpha) / (2 |gamma|), t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), c = 1/sqrt(1+t^2), s = c t
+                        const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
+                        const float pr = gr * ginv, pi = -gi * ginv;                    // e^{-i phi} = conj(gamma) / |gamma|
+                        const float zeta = (beta - alpha) * (0.5f * ginv);
+                        const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+                        const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
+                        const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
+                        // a' = c a - (s p) b ; b' = s a + (c p) b
 #pragma unroll
-                        for (int c = 0; c < HQ; ++c) {
-                            const int cq = svd_col<kSvdRows>(c, h);
-                            const float2 x = qa[cq], y = qb[cq];
-                            qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                            qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        for (int c = 0; c < HC; ++c) {
+                            const float2 x = a[c], y = b[c];
+                            a[c] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            wb[svd_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
                         }
+                        a_dirty = true;
+                        if constexpr (WITHY) {
+                            if (h == 0) {           // the same rotation on the two entries of z = Q y
+                                const float2 x = Q[p], y = Q[q];
+                                Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                                Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                            }
+                        } else {
+                            // (keeping this row of Q in registers as well was measured: 252 registers or spills, slower)
+                            float2* qa = Q + p * Sh::qstride;
+                            float2* qb = Q + q * Sh::qstride;
+#pragma unroll
+                            for (int c = 0; c < HQ; ++c) {
+                                const int cq = svd_col<kSvdRows>(c, h);
+                                const float2 x = qa[cq], y = qb[cq];
+                                qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                                qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                            }
+                        }
+                        rotated = true;
                     }
-                    rotated = true;
+                    __syncwarp();
+                }
+                if (a_dirty) {
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) wa[svd_col<NC>(c, h)] = a[c];
                 }
                 __syncwarp();
             }
@@ -520,71 +532,77 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
         int sweeps = 0;
         for (; sweeps < kSvd64MaxSweeps; ++sweeps) {
             bool rotated = false;
-            for (int step = 0; step < kSvd64Rows - 1; ++step) {
-                int p, q;                                      // tournament pairing: position 63 stays, the others rotate
-                if (j == 0) {
-                    p = kSvd64Rows - 1;
-                    q = step;
-                } else {
-                    p = step + j;
-                    if (p >= kSvd64Rows - 1) p -= kSvd64Rows - 1;
-                    q = step - j;
-                    if (q < 0) q += kSvd64Rows - 1;
-                }
+            // the stationary-row ordering of the one-warp kernel: phases G = 32, 16, ..., 1; thread group j = (sb, i) keeps row
+            // p = 2G sb + i in registers for the phase and meets q = 2G sb + G + (i + s) mod G, s = 0 .. G-1 (63 steps per sweep)
+            for (int G = kSvd64Rows / 2; G >= 1; G >>= 1) {
+                const int sb = j / G, i = j - sb * G;
+                const int p = sb * 2 * G + i;
                 float2* wa = W + p * Sh::wstride;
-                float2* wb = W + q * Sh::wstride;
-                float2 a[QC], b[QC];
-                float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
+                float2 a[QC];
 #pragma unroll
-                for (int c = 0; c < QC; ++c) {
-                    a[c] = wa[svd64_col<NC>(c, h)];
-                    b[c] = wb[svd64_col<NC>(c, h)];
-                    alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
-                    beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
-                    gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
-                    gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
-                }
-#pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-                    beta += __shfl_xor_sync(0xffffffffu, beta, o);
-                    gr += __shfl_xor_sync(0xffffffffu, gr, o);
-                    gi += __shfl_xor_sync(0xffffffffu, gi, o);
-                }
-                const float g2 = gr * gr + gi * gi;
-                const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
-                if (rot) {
-                    const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
-                    const float pr = gr * ginv, pi = -gi * ginv;                    // e^{-i phi} = conj(gamma) / |gamma|
-                    const float zeta = (beta - alpha) * (0.5f * ginv);
-                    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
-                    const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
-                    const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
-                    // a' = c a - (s p) b ; b' = s a + (c p) b
+                for (int c = 0; c < QC; ++c) a[c] = wa[svd64_col<NC>(c, h)];
+                bool a_dirty = false;
+                for (int s = 0; s < G; ++s) {
+                    const int q = sb * 2 * G + G + ((i + s) & (G - 1));
+                    float2* wb = W + q * Sh::wstride;
+                    float2 b[QC];
+                    float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
 #pragma unroll
                     for (int c = 0; c < QC; ++c) {
-                        const float2 x = a[c], y = b[c];
-                        wa[svd64_col<NC>(c, h)] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                        wb[svd64_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        b[c] = wb[svd64_col<NC>(c, h)];
+                        alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
+                        beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
+                        gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
+                        gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
                     }
-                    if constexpr (WITHY) {
-                        if (h == 0) {
-                            const float2 x = Q[p], y = Q[q];
-                            Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                            Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
-                        }
-                    } else {
-                        float2* qa = Q + p * Sh::qstride;
-                        float2* qb = Q + q * Sh::qstride;
 #pragma unroll
-                        for (int c = 0; c < QQ; ++c) {
-                            const int cq = svd64_col<kSvd64Rows>(c, h);
-                            const float2 x = qa[cq], y = qb[cq];
-                            qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
-                            qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
-                        }
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+                        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+                        gr += __shfl_xor_sync(0xffffffffu, gr, o);
+                        gi += __shfl_xor_sync(0xffffffffu, gi, o);
                     }
-                    rotated = true;
+                    const float g2 = gr * gr + gi * gi;
+                    const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
+                    if (rot) {
+                        const float gabs = sqrtf(g2), ginv = 1.0f / gabs;
+                        const float pr = gr * ginv, pi = -gi * ginv;                    // e^{-i phi} = conj(gamma) / |gamma|
+                        const float zeta = (beta - alpha) * (0.5f * ginv);
+                        const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+                        const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
+                        const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
+                        // a' = c a - (s p) b ; b' = s a + (c p) b
+#pragma unroll
+                        for (int c = 0; c < QC; ++c) {
+                            const float2 x = a[c], y = b[c];
+                            a[c] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                            wb[svd64_col<NC>(c, h)] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                        }
+                        a_dirty = true;
+                        if constexpr (WITHY) {
+                            if (h == 0) {
+                                const float2 x = Q[p], y = Q[q];
+                                Q[p] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                                Q[q] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                            }
+                        } else {
+                            float2* qa = Q + p * Sh::qstride;
+                            float2* qb = Q + q * Sh::qstride;
+#pragma unroll
+                            for (int c = 0; c < QQ; ++c) {
+                                const int cq = svd64_col<kSvd64Rows>(c, h);
+                                const float2 x = qa[cq], y = qb[cq];
+                                qa[cq] = make_float2(fmaf(cs, x.x, fmaf(-spr, y.x, spi * y.y)), fmaf(cs, x.y, fmaf(-spr, y.y, -spi * y.x)));
+                                qb[cq] = make_float2(fmaf(sn, x.x, fmaf(cpr, y.x, -cpi * y.y)), fmaf(sn, x.y, fmaf(cpr, y.y, cpi * y.x)));
+                            }
+                        }
+                        rotated = true;
+                    }
+                    __syncthreads();
+                }
+                if (a_dirty) {
+#pragma unroll
+                    for (int c = 0; c < QC; ++c) wa[svd64_col<NC>(c, h)] = a[c];
                 }
                 __syncthreads();
             }
