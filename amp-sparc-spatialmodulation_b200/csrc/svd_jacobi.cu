@@ -14,7 +14,9 @@
 // pairs is a recursive halving in which one row of every pair is STATIONARY for a whole phase and lives in registers (round 2b;
 // the round-robin tournament of the first version moved both rows through shared memory every step and was bound by exactly
 // that traffic: +34 % matrices/s).  A pair whose rows are already orthogonal to 4e-7 (relative) is skipped; the sweep loop ends
-// when a whole sweep rotated nothing.
+// when a whole sweep rotated nothing.  (Packed fp32x2 inner products and rotations -- half the FP instructions -- were measured
+// after that change and bought nothing, +2 % / -5 % on the two entry points: the FMA pipe and the register file, not the issue
+// slots, carry the 20 flops per element pair.)
 #include <cstdlib>
 
 #include "framegen.cuh"
