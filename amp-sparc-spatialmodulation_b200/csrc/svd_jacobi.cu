@@ -108,7 +108,7 @@ struct SvdGen {
     Geom g;
 };
 template <int NC, bool WITHY, bool BLOCK, bool GEN = false>
-__global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2* __restrict__ H, long long frames, int n, float2* __restrict__ U,
+__global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) svd_jacobi_kernel(const float2* __restrict__ H, long long frames, int n, float2* __restrict__ U,
                                                                    float* __restrict__ S, float2* __restrict__ Vh, int* __restrict__ sweeps_out,
                                                                    const float2* __restrict__ yin, float2* __restrict__ yrot,
                                                                    const __grid_constant__ SvdGen gen) {
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
     float2* Q = W + kSvdRows * Sh::wstride;
     int* perm = reinterpret_cast<int*>(Q + Sh::q_elems);
     float* sinv = reinterpret_cast<float*>(perm + kSvdRows);
+    float* nrm = sinv;                                        // squared row norms during the sweeps
     const int j = lane >> 1, h = lane & 1;
 
     for (long long f = (long long)blockIdx.x * kSvdWarps + wic; f < frames; f += (long long)gridDim.x * kSvdWarps) {
@@ -261,6 +262,21 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
             // disjoint pairs that cover every pair once, like the round-robin tournament of the first version, but only ONE row
             // of a pair crosses shared memory per step (the kernel is bound by exactly that traffic: ncu, data pipe 91 % busy).
             // Neighbouring lane pairs still touch rows that differ mod 16, so the accesses stay conflict-free.
+            // The squared row norms are kept in `nrm` (the 1/s scratch, free until the output stage): exact at the start of every
+            // sweep, then carried through the rotations (alpha' = alpha - t |gamma|, beta' = beta + t |gamma|).  Only gamma is
+            // formed from the rows: 4 instead of 8 FMAs per element pair, half the work of a pair that does not rotate.  The
+            // carried norms drift by a few ulps per rotation (<= 31 per sweep); they enter the skip test and the rotation angle
+            // only -- convergence is decided by the exact gamma, the singular values by exact norms at the end.
+            {
+                float nn = 0.f;
+#pragma unroll 8
+                for (int c = 0; c < NC; ++c) {
+                    const float2 wv = W[lane * Sh::wstride + c];
+                    nn = fmaf(wv.x, wv.x, fmaf(wv.y, wv.y, nn));
+                }
+                nrm[lane] = nn;
+                __syncwarp();
+            }
             for (int G = kSvdRows / 2; G >= 1; G >>= 1) {
                 const int sb = j / G, i = j - sb * G;
                 const int p = sb * 2 * G + i;
@@ -268,22 +284,20 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                 float2 a[HC];
 #pragma unroll
                 for (int c = 0; c < HC; ++c) a[c] = wa[svd_col<NC>(c, h)];
+                float alpha = nrm[p];
                 bool a_dirty = false;
                 for (int s = 0; s < G; ++s) {
                     const int q = sb * 2 * G + G + ((i + s) & (G - 1));
                     float2* wb = W + q * Sh::wstride;
                     float2 b[HC];
-                    float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
+                    float gr = 0.f, gi = 0.f;
+                    const float beta = nrm[q];
 #pragma unroll
                     for (int c = 0; c < HC; ++c) {
                         b[c] = wb[svd_col<NC>(c, h)];
-                        alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
-                        beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
                         gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
                         gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
                     }
-                    alpha += __shfl_xor_sync(0xffffffffu, alpha, 1);
-                    beta += __shfl_xor_sync(0xffffffffu, beta, 1);
                     gr += __shfl_xor_sync(0xffffffffu, gr, 1);
                     gi += __shfl_xor_sync(0xffffffffu, gi, 1);
                     const float g2 = gr * gr + gi * gi;
@@ -297,6 +311,8 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                         const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
                         const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
                         const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
+                        alpha = fmaf(-t, gabs, alpha);
+                        if (h == 0) nrm[q] = fmaf(t, gabs, beta);
                         // a' = c a - (s p) b ; b' = s a + (c p) b
 #pragma unroll
                         for (int c = 0; c < HC; ++c) {
@@ -330,6 +346,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32) svd_jacobi_kernel(const float2
                 if (a_dirty) {
 #pragma unroll
                     for (int c = 0; c < HC; ++c) wa[svd_col<NC>(c, h)] = a[c];
+                    if (h == 0) nrm[p] = alpha;
                 }
                 __syncwarp();
             }
