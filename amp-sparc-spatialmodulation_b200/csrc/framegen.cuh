@@ -46,8 +46,10 @@ __device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
 // Frame `fg` (global number) of the stream described by `ga` into the warp's tile W (32 rows of `wstride` complex elements,
 // rows >= n zeroed) and yv (32 entries, rows >= n zeroed); ground truth of the frame with call-local index `f` to ga.x_out /
 // idx_out / sym_out.  NC columns (compile time), n <= 32 rows, L <= 32 sections.  All 32 lanes call it.
-template <int NC>
+// SWZ: the consumer's swizzled row placement (svd_jacobi.cu, SvdShape::swz): row r starts at r wstride + rho(r).
+template <int NC, bool SWZ>
 __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long long f, int n, float2* W, int wstride, float2* yv, int lane) {
+    auto row = [&](int r) { return SWZ ? r * wstride + ((r & 7) ^ ((r & 8) ? 7 : 0)) : r * wstride; };
     const unsigned long long fg = (unsigned long long)(ga.counter_base + f);
     const uint2 key = make_uint2((unsigned)ga.seed, (unsigned)(ga.seed >> 32));
     const unsigned flo = (unsigned)fg, fhi = (unsigned)(fg >> 32);
@@ -62,8 +64,8 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
             v0 = make_float2(v0.x * ga.h_std, v0.y * ga.h_std);
             v1 = make_float2(v1.x * ga.h_std, v1.y * ga.h_std);
         }
-        W[r * wstride + c] = v0;
-        W[r * wstride + c + 1] = v1;
+        W[row(r) + c] = v0;
+        W[row(r) + c + 1] = v1;
     }
     __syncwarp();
     // ---- Kronecker correlation (BASELINE config 5): H = Rr_root G Rt_root, lane = column(s) c = lane + 32 j
@@ -87,7 +89,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
                 if (ga.real_roots) {                             // real roots (exponential correlation): half the products
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        const float2 gv = W[(r0 + r) * wstride + k];                // broadcast
+                        const float2 gv = W[row(r0 + r) + k];                        // broadcast
 #pragma unroll
                         for (int j = 0; j < CJ; ++j) {
                             acc[j][r].x = fmaf(gv.x, t[j].x, acc[j][r].x);
@@ -97,7 +99,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
                 } else {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        const float2 gv = W[(r0 + r) * wstride + k];                // broadcast
+                        const float2 gv = W[row(r0 + r) + k];                        // broadcast
 #pragma unroll
                         for (int j = 0; j < CJ; ++j) {
                             acc[j][r].x = fmaf(gv.x, t[j].x, fmaf(-gv.y, t[j].y, acc[j][r].x));
@@ -112,7 +114,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
                 const int c = lane + 32 * j;
                 if (c < NC)
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) W[(r0 + r) * wstride + c] = acc[j][r];
+                    for (int r = 0; r < 16; ++r) W[row(r0 + r) + c] = acc[j][r];
             }
         }
         __syncwarp();
@@ -125,7 +127,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
             if (c < NC) {
                 float2 tc[32];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) tc[k] = W[k * wstride + c];            // rows >= n are zero
+                for (int k = 0; k < 32; ++k) tc[k] = W[row(k) + c];                 // rows >= n are zero
 #pragma unroll 1
                 for (int r = 0; r < n; ++r) {
                     float ax = 0.f, ay = 0.f;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
                             ay = fmaf(rv.x, tc[k].y, fmaf(rv.y, tc[k].x, ay));
                         }
                     }
-                    W[r * wstride + c] = make_float2(ax, ay);
+                    W[row(r) + c] = make_float2(ax, ay);
                 }
             }
         }
@@ -176,7 +178,7 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
     }
     for (int s = 0; s < g.L; ++s) {
         const int ps = __shfl_sync(0xffffffffu, pos, s), kk = __shfl_sync(0xffffffffu, ks, s);
-        const float2 hv = W[lane * wstride + ps], sv = ga.sym[kk];
+        const float2 hv = W[row(lane) + ps], sv = ga.sym[kk];
         yr.x = fmaf(hv.x, sv.x, fmaf(-hv.y, sv.y, yr.x));
         yr.y = fmaf(hv.x, sv.y, fmaf(hv.y, sv.x, yr.y));
     }

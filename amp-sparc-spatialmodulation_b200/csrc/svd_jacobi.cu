@@ -33,11 +33,21 @@ constexpr float kSvdTol = 4.0e-7f;
 
 template <int NC, bool WITHY = false>
 struct SvdShape {
-    static constexpr int wstride = NC + 1;                    // complex elements per row of W (odd: conflict-free columns)
+    // Row placement of W.  NC = 64 (round 2b): rows 72 elements apart, row r shifted by rho(r) = (r & 7) ^ (r & 8 ? 7 : 0) elements --
+    // every set of eight rows a half-warp touches in one access of the stationary-row ordering (a 3-dimensional subcube of the
+    // row index: one of its low four bits fixed) then has eight distinct shifts, and with the two column halves 8 elements apart
+    // the sixteen lanes hit sixteen distinct bank pairs.  (With rows NC + 1 apart the phases G <= 4 had two-way conflicts: 20 % of
+    // all wavefronts of a kernel whose shared-memory pipe is 78 % busy.)  Other widths keep the odd stride.
+    static constexpr bool swz = NC == 64 && WITHY;          // (with the n x n matrix Q next to W the wider rows would cost a CTA per SM)
+    static constexpr int wstride = swz ? NC + 8 : NC + 1;     // complex elements per row of W
     static constexpr int qstride = kSvdRows + 1;
     static constexpr int q_elems = WITHY ? kSvdRows : kSvdRows * qstride;      // WITHY: the vector z = Q y instead of Q
-    static constexpr int warp_bytes = (kSvdRows * wstride + q_elems) * 8 + 2 * kSvdRows * 4;   // + perm, 1/s
+    static constexpr int warp_bytes = (kSvdRows * wstride + (swz ? 8 : 0) + q_elems) * 8 + 2 * kSvdRows * 4;   // + perm, 1/s
 };
+template <bool SWZ>
+__device__ __forceinline__ int svd_row(int r, int wstride) {
+    return SWZ ? r * wstride + ((r & 7) ^ ((r & 8) ? 7 : 0)) : r * wstride;
+}
 // column k of a lane's share: lane half h takes the columns whose index mod 16 lies in [8h, 8h+8), so that the 16 lanes
 // of a half-warp (8 consecutive rows x 2 halves, row stride = 1 mod 16 in 8-byte units) hit 16 distinct bank pairs
 template <int NC>
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     float2* W = reinterpret_cast<float2*>(smem + (size_t)wic * Sh::warp_bytes);
-    float2* Q = W + kSvdRows * Sh::wstride;
+    float2* Q = W + kSvdRows * Sh::wstride + (Sh::swz ? 8 : 0);      // the shifted last row ends up to 7 elements later
     int* perm = reinterpret_cast<int*>(Q + Sh::q_elems);
     float* sinv = reinterpret_cast<float*>(perm + kSvdRows);
     float* nrm = sinv;                                        // squared row norms during the sweeps
@@ -127,12 +137,12 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
     for (long long f = (long long)blockIdx.x * kSvdWarps + wic; f < frames; f += (long long)gridDim.x * kSvdWarps) {
         // ---- load: W = H (rows >= n are zero), Q = I
         if constexpr (GEN) {
-            gen_frame<NC>(gen.ga, gen.g, f, n, W, Sh::wstride, Q, lane);
+            gen_frame<NC, Sh::swz>(gen.ga, gen.g, f, n, W, Sh::wstride, Q, lane);
         } else {
             const float2* Hf = H + f * (long long)n * NC;
             for (int e = lane; e < kSvdRows * NC; e += 32) {
                 const int r = e / NC, c = e - r * NC;
-                W[r * Sh::wstride + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
+                W[svd_row<Sh::swz>(r, Sh::wstride) + c] = r < n ? __ldg(Hf + e) : make_float2(0.f, 0.f);
             }
         }
         if constexpr (GEN) {
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int c = 0; c < QC; ++c) a[i][c] = W[rows[i] * Sh::wstride + svd_bcol<NC>(c, hb)];
+                        for (int c = 0; c < QC; ++c) a[i][c] = W[svd_row<Sh::swz>(rows[i], Sh::wstride) + svd_bcol<NC>(c, hb)];
 #pragma unroll
                     for (int c = 0; c < QC; ++c) {
 #pragma unroll
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
                                 float2 r = cmulf(T[i][0], x0);
                                 const float2 r1 = cmulf(T[i][1], x1), r2 = cmulf(T[i][2], x2), r3 = cmulf(T[i][3], x3);
                                 r = make_float2((r.x + r1.x) + (r2.x + r3.x), (r.y + r1.y) + (r2.y + r3.y));
-                                W[rows[i] * Sh::wstride + svd_bcol<NC>(c, hb)] = r;
+                                W[svd_row<Sh::swz>(rows[i], Sh::wstride) + svd_bcol<NC>(c, hb)] = r;
                             }
                         }
                         if constexpr (WITHY) {
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
                 float nn = 0.f;
 #pragma unroll 8
                 for (int c = 0; c < NC; ++c) {
-                    const float2 wv = W[lane * Sh::wstride + c];
+                    const float2 wv = W[svd_row<Sh::swz>(lane, Sh::wstride) + c];
                     nn = fmaf(wv.x, wv.x, fmaf(wv.y, wv.y, nn));
                 }
                 nrm[lane] = nn;
@@ -280,15 +290,15 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
             for (int G = kSvdRows / 2; G >= 1; G >>= 1) {
                 const int sb = j / G, i = j - sb * G;
                 const int p = sb * 2 * G + i;
-                float2* wa = W + p * Sh::wstride;
+                float2* wa = W + svd_row<Sh::swz>(p, Sh::wstride);
                 float2 a[HC];
 #pragma unroll
                 for (int c = 0; c < HC; ++c) a[c] = wa[svd_col<NC>(c, h)];
                 float alpha = nrm[p];
                 bool a_dirty = false;
                 for (int s = 0; s < G; ++s) {
-                    const int q = sb * 2 * G + G + ((i + s) & (G - 1));
-                    float2* wb = W + q * Sh::wstride;
+                    const int q = sb * 2 * G + G + (i ^ s);              // XOR, not a rotation: every access set is a subcube of the row index
+                    float2* wb = W + svd_row<Sh::swz>(q, Sh::wstride);
                     float2 b[HC];
                     float gr = 0.f, gi = 0.f;
                     const float beta = nrm[q];
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
         float nrm = 0.f;
 #pragma unroll 8
         for (int c = 0; c < NC; ++c) {
-            const float2 w = W[lane * Sh::wstride + c];
+            const float2 w = W[svd_row<Sh::swz>(lane, Sh::wstride) + c];
             nrm = fmaf(w.x, w.x, fmaf(w.y, w.y, nrm));
         }
         const float sv = sqrtf(nrm);
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
             const float sc = sinv[k];
             float2* out = Vh + (f * n + k) * (long long)NC;
             for (int c = lane; c < NC; c += 32) {
-                const float2 w = W[row * Sh::wstride + c];
+                const float2 w = W[svd_row<Sh::swz>(row, Sh::wstride) + c];
                 out[c] = make_float2(w.x * sc, w.y * sc);
             }
         }
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32) generate_frames_kernel(const _
     float2* yv = W + kSvdRows * wstride;
     const int n = gen.g.n;
     for (long long f = (long long)blockIdx.x * kSvdWarps + wic; f < frames; f += (long long)gridDim.x * kSvdWarps) {
-        gen_frame<NC>(gen.ga, gen.g, f, n, W, wstride, yv, lane);
+        gen_frame<NC, false>(gen.ga, gen.g, f, n, W, wstride, yv, lane);
         if (H)
             for (int e = lane; e < n * NC; e += 32) {
                 const int r = e / NC, c = e - r * NC;
