@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
     float2* Q = W + kSvd64Rows * Sh::wstride;
     int* perm = reinterpret_cast<int*>(Q + Sh::q_elems);
     float* sinv = reinterpret_cast<float*>(perm + kSvd64Rows);
+    float* nrm = sinv;                                         // squared row norms during the sweeps
     const int tid = threadIdx.x;
     const int j = tid >> 2, h = tid & 3;
 
@@ -563,6 +564,17 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
             bool rotated = false;
             // the stationary-row ordering of the one-warp kernel: phases G = 32, 16, ..., 1; thread group j = (sb, i) keeps row
             // p = 2G sb + i in registers for the phase and meets q = 2G sb + G + (i + s) mod G, s = 0 .. G-1 (63 steps per sweep)
+            {   // squared row norms, exact at the start of the sweep and carried through its rotations (see the one-warp kernel)
+                const int r = tid >> 1, half = tid & 1;
+                float nn = 0.f;
+                for (int c = half; c < NC; c += 2) {
+                    const float2 wv = W[r * Sh::wstride + c];
+                    nn = fmaf(wv.x, wv.x, fmaf(wv.y, wv.y, nn));
+                }
+                nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+                if (half == 0) nrm[r] = nn;
+            }
+            __syncthreads();
             for (int G = kSvd64Rows / 2; G >= 1; G >>= 1) {
                 const int sb = j / G, i = j - sb * G;
                 const int p = sb * 2 * G + i;
@@ -570,24 +582,22 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
                 float2 a[QC];
 #pragma unroll
                 for (int c = 0; c < QC; ++c) a[c] = wa[svd64_col<NC>(c, h)];
+                float alpha = nrm[p];
                 bool a_dirty = false;
                 for (int s = 0; s < G; ++s) {
-                    const int q = sb * 2 * G + G + ((i + s) & (G - 1));
+                    const int q = sb * 2 * G + G + (i ^ s);
                     float2* wb = W + q * Sh::wstride;
                     float2 b[QC];
-                    float alpha = 0.f, beta = 0.f, gr = 0.f, gi = 0.f;
+                    float gr = 0.f, gi = 0.f;
+                    const float beta = nrm[q];
 #pragma unroll
                     for (int c = 0; c < QC; ++c) {
                         b[c] = wb[svd64_col<NC>(c, h)];
-                        alpha = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, alpha));
-                        beta = fmaf(b[c].x, b[c].x, fmaf(b[c].y, b[c].y, beta));
                         gr = fmaf(a[c].x, b[c].x, fmaf(a[c].y, b[c].y, gr));          // gamma = sum conj(a) b
                         gi = fmaf(a[c].x, b[c].y, fmaf(-a[c].y, b[c].x, gi));
                     }
 #pragma unroll
                     for (int o = 1; o <= 2; o <<= 1) {
-                        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-                        beta += __shfl_xor_sync(0xffffffffu, beta, o);
                         gr += __shfl_xor_sync(0xffffffffu, gr, o);
                         gi += __shfl_xor_sync(0xffffffffu, gi, o);
                     }
@@ -600,6 +610,8 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
                         const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
                         const float cs = rsqrtf(fmaf(t, t, 1.0f)), sn = cs * t;
                         const float spr = sn * pr, spi = sn * pi, cpr = cs * pr, cpi = cs * pi;
+                        alpha = fmaf(-t, gabs, alpha);
+                        if (h == 0) nrm[q] = fmaf(t, gabs, beta);
                         // a' = c a - (s p) b ; b' = s a + (c p) b
 #pragma unroll
                         for (int c = 0; c < QC; ++c) {
@@ -632,6 +644,7 @@ __global__ void __launch_bounds__(kSvd64Threads) svd_jacobi64_kernel(const float
                 if (a_dirty) {
 #pragma unroll
                     for (int c = 0; c < QC; ++c) wa[svd64_col<NC>(c, h)] = a[c];
+                    if (h == 0) nrm[p] = alpha;
                 }
                 __syncthreads();
             }
