@@ -39,7 +39,7 @@ class Problem(C.Structure):
 
 class Gen(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("counter_base", C.c_int64), ("h_var", C.c_double), ("Rr_root", C.c_void_p), ("Rt_root", C.c_void_p),
-                ("real_roots", C.c_int32), ("reserved0", C.c_int32)]
+                ("real_roots", C.c_int32), ("reserved0", C.c_int32), ("rho_r", C.c_double), ("rho_t", C.c_double)]
 
 
 class AmpsmError(RuntimeError):

@@ -542,6 +542,10 @@ static int make_gen(const ampsm_problem* p, const ampsm_alphabet* a, const ampsm
     ga->Rr_root = (const float2*)gen->Rr_root;
     ga->Rt_root = (const float2*)gen->Rt_root;
     ga->real_roots = gen->real_roots != 0;
+    if (!(gen->rho_t > -1.0 && gen->rho_t < 1.0 && gen->rho_r > -1.0 && gen->rho_r < 1.0)) { set_error("frame generation: |rho| must be below 1"); return AMPSM_EINVAL; }
+    if ((gen->rho_t != 0.0 && gen->Rt_root) || (gen->rho_r != 0.0 && gen->Rr_root)) { set_error("frame generation: give rho or the root of a side, not both"); return AMPSM_EINVAL; }
+    ga->ar_t = (float)gen->rho_t; ga->ar_t_c = (float)sqrt(1.0 - gen->rho_t * gen->rho_t);
+    ga->ar_r = (float)gen->rho_r; ga->ar_r_c = (float)sqrt(1.0 - gen->rho_r * gen->rho_r);
     ga->K = a->K;
     for (int k = 0; k < AMPSM_MAX_K; ++k) {
         ga->sym[k] = make_float2(al.ref[k], al.imf[k]);

@@ -5,7 +5,8 @@
 //   channel.py:53-55   H = (N(0,1) + j N(0,1)) sqrt(1 / Nr / 2)          -> stream 0, Box-Muller on Philox words
 //   data.py:74-91      one active antenna per section, one symbol each   -> stream 2
 //   channel.py:113-115 w = (N(0,1) + j N(0,1)) sqrt(sigma^2 / 2), y = H x + w -> stream 1
-// plus BASELINE config 5's Kronecker correlation H = Rr^(1/2) G Rt^(1/2) (no generator of the reference draws such channels).
+// plus BASELINE config 5's Kronecker correlation H = Rr^(1/2) G Rt^(1/2) (no generator of the reference draws such channels):
+// for the exponential model by two AR(1) recursions, for arbitrary correlation matrices from their roots.
 // The draws are NOT the reference's (numpy MT19937 / torch Philox in another order): parity subsets keep the reference's
 // own RNG path (tests/golden), this path is pinned by a numpy restatement of the same counter layout (tests/test_framegen.py)
 // and by "generate to HBM, then detect" == "generate inside the SVD kernel" bit for bit.
@@ -68,7 +69,33 @@ __device__ __forceinline__ void gen_frame(const GenArgs& ga, const Geom& g, long
         W[row(r) + c + 1] = v1;
     }
     __syncwarp();
-    // ---- Kronecker correlation (BASELINE config 5): H = Rr_root G Rt_root, lane = column(s) c = lane + 32 j
+    // ---- exponential Kronecker correlation (BASELINE config 5), fast form: R[i][j] = rho^|i-j| is the covariance of the AR(1)
+    // sequence x_0 = w_0, x_k = rho x_{k-1} + sqrt(1 - rho^2) w_k, so running that recursion along the columns (transmit side) and
+    // then along the rows (receive side) of G gives H = A G B with A A^H = Rr, B^H B = Rt -- the distribution of
+    // Rr^(1/2) G Rt^(1/2) (G is unitarily invariant) for 6 instead of ~380 FMAs per entry.
+    if (ga.ar_t != 0.f) {                                        // lane = row, along the columns
+        const float rho = ga.ar_t, cc = ga.ar_t_c;
+        float2 prev = W[row(lane)];
+        for (int c = 1; c < NC; ++c) {
+            const float2 w = W[row(lane) + c];
+            prev = make_float2(fmaf(rho, prev.x, cc * w.x), fmaf(rho, prev.y, cc * w.y));
+            W[row(lane) + c] = prev;
+        }
+        __syncwarp();
+    }
+    if (ga.ar_r != 0.f) {                                        // lane = column(s), along the rows
+        const float rho = ga.ar_r, cc = ga.ar_r_c;
+        for (int c = lane; c < NC; c += 32) {
+            float2 prev = W[row(0) + c];
+            for (int r = 1; r < n; ++r) {
+                const float2 w = W[row(r) + c];
+                prev = make_float2(fmaf(rho, prev.x, cc * w.x), fmaf(rho, prev.y, cc * w.y));
+                W[row(r) + c] = prev;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- Kronecker correlation with arbitrary roots: H = Rr_root G Rt_root, lane = column(s) c = lane + 32 j
     if (ga.Rt_root) {
         constexpr int CJ = (NC + 31) / 32;
 #pragma unroll 1

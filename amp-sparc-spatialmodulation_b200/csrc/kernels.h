@@ -122,7 +122,8 @@ struct GenArgs {
     float noise_std;             // sqrt(sigma^2 / 2) (channel.py:113-115)
     const float2* Rr_root;       // [n][n] or nullptr;  H = Rr_root G Rt_root (BASELINE config 5)
     const float2* Rt_root;       // [N][N] or nullptr
-    int real_roots;              // both roots have zero imaginary parts (the exponential correlation model): half the products
+    int real_roots;              // both roots have zero imaginary parts: half the products
+    float ar_t, ar_t_c, ar_r, ar_r_c;   // exponential correlation as AR(1) recursions: rho and sqrt(1 - rho^2), transmit / receive side (0: off)
     int K;
     float2 sym[AMPSM_MAX_K];     // config.symbols as complex64
     long long gray[AMPSM_MAX_K];

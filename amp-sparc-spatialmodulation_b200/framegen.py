@@ -24,7 +24,7 @@ class FrameStream:
     """A reproducible stream of frames for ``config`` (Lin = Lh = 1, sectioned messages): frame ``k`` of the stream is the same
     whatever chunk, shard or call draws it."""
 
-    def __init__(self, config: Config, seed: int = 0, channel='iid', rho_t=0.0, rho_r=0.0, device=None):
+    def __init__(self, config: Config, seed: int = 0, channel='iid', rho_t=0.0, rho_r=0.0, device=None, method='ar1'):
         if config.Lin != 1 or config.Lh != 1 or config.mode == 'random':
             raise _cabi.AmpsmError("FrameStream draws sectioned messages on memoryless channels (Lin = Lh = 1)")
         self.config = config
@@ -34,11 +34,18 @@ class FrameStream:
             raise _cabi.AmpsmError("FrameStream runs on the GPU only (no CPU fallback)")
         self.Rr = self.Rt = None
         self.real_roots = False
-        if channel == 'kronecker':
+        self.rho_r = self.rho_t = 0.0
+        if channel == 'kronecker' and method == 'ar1':
+            # exponential correlation by two AR(1) recursions inside the kernel: H = A G B with A A^H = Rr, B^H B = Rt, the
+            # distribution of Rr^(1/2) G Rt^(1/2) at a sixtieth of the arithmetic
+            self.rho_r, self.rho_t = float(rho_r), float(rho_t)
+        elif channel == 'kronecker' and method == 'roots':
             self.Rr = exp_corr_root(config.n, rho_r, self.device)
             self.Rt = exp_corr_root(config.N, rho_t, self.device)
             self.real_roots = True                              # rho is real: so are the roots
-        elif channel != 'iid':
+        elif channel == 'kronecker':
+            raise ValueError("method is 'ar1' or 'roots'")
+        elif channel not in ('iid', 'kronecker'):
             raise ValueError(f"unknown channel model {channel!r}")
         self._alphabet = _cabi.make_alphabet(config)
 
@@ -48,6 +55,7 @@ class FrameStream:
         g.Rr_root = self.Rr.data_ptr() if self.Rr is not None else None
         g.Rt_root = self.Rt.data_ptr() if self.Rt is not None else None
         g.real_roots = 1 if self.real_roots else 0
+        g.rho_r, g.rho_t = self.rho_r, self.rho_t
         return g
 
     def truth_buffers(self, frames: int):

@@ -202,7 +202,8 @@ int ampsm_vamp_detect_from_h(const ampsm_problem* p, const ampsm_alphabet* a, in
  *   channel.py:53-55   H = (N(0,1) + j N(0,1)) sqrt(h_var / 2), h_var = 1 / Nr
  *   data.py:74-91      one active antenna per section and one constellation point each -> x, Gray labels, flat positions
  *   channel.py:113-115 y = H x + (N(0,1) + j N(0,1)) sqrt(sigma2 / 2)
- * and, when the roots are given, BASELINE config 5's Kronecker correlation H = Rr_root G Rt_root.  Frame f of the call is
+ * and BASELINE config 5's Kronecker correlation: H = Rr_root G Rt_root when the roots are given, or the exponential model
+ * from rho_r / rho_t alone.  Frame f of the call is
  * frame counter_base + f of the stream `seed`: shards and chunks that cover the same global range draw the same frames.  The
  * draws are not the reference's numpy / torch sequences; parity subsets keep the reference's own RNG path.
  * Shapes: Lin = 1, 1 <= n <= 32, n <= N, N in {8, 16, 32, 64}, at most 32 sections, decision = 0.
@@ -215,6 +216,9 @@ typedef struct {
     const void* Rt_root;     /* complex64 [N][N] device pointer or NULL */
     int32_t  real_roots;     /* 1: the imaginary parts of both roots are zero (exponential correlation): half the work */
     int32_t  reserved0;
+    double   rho_r, rho_t;   /* exponential correlation R[i][j] = rho^|i-j| on the receive / transmit side, generated by AR(1)
+                                recursions (same distribution as the Hermitian roots, ~60x cheaper); 0 = none; not together with
+                                the root of the same side */
 } ampsm_gen;
 
 /* H : complex64 [frames][n][N] and y : complex64 [frames][n] (either may be NULL); x : complex64 [frames][N],

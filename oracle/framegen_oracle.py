@@ -41,7 +41,8 @@ def box_muller(a, b):
     return (rad * np.cos(th)).astype(np.float32), (rad * np.sin(th)).astype(np.float32)
 
 
-def frames(seed, first_frame, count, n, N, M, L, symbols, gray, h_var, sigma2, Rr_root=None, Rt_root=None, frame_base=0):
+def frames(seed, first_frame, count, n, N, M, L, symbols, gray, h_var, sigma2, Rr_root=None, Rt_root=None, frame_base=0, rho_r=0.0,
+           rho_t=0.0):
     """Frames first_frame .. first_frame + count - 1 of stream `seed`: (H (F, n, N) c64, y (F, n) c64, x (F, N) c64,
     labels (F L,) int64, flat positions (F L,) int64)."""
     key = (seed & MASK, (seed >> 32) & MASK)
@@ -63,6 +64,16 @@ def frames(seed, first_frame, count, n, N, M, L, symbols, gray, h_var, sigma2, R
         G[0::2] = (r0 * h_std) + 1j * (i0 * h_std)
         G[1::2] = (r1 * h_std) + 1j * (i1 * h_std)
         H = G.reshape(n, N)
+        if rho_t:                                                   # AR(1) along the columns, then along the rows (float32 FMAs)
+            H = H.copy()
+            r32, c32 = np.float32(rho_t), np.float32(np.sqrt(1.0 - rho_t * rho_t))
+            for c in range(1, N):
+                H[:, c] = (r32 * H[:, c - 1].real + c32 * H[:, c].real) + 1j * (r32 * H[:, c - 1].imag + c32 * H[:, c].imag)
+        if rho_r:
+            H = H.copy()
+            r32, c32 = np.float32(rho_r), np.float32(np.sqrt(1.0 - rho_r * rho_r))
+            for r in range(1, n):
+                H[r] = (r32 * H[r - 1].real + c32 * H[r].real) + 1j * (r32 * H[r - 1].imag + c32 * H[r].imag)
         if Rt_root is not None:
             H = (H.astype(np.complex128) @ np.asarray(Rt_root, dtype=np.complex128)).astype(np.complex64)
         if Rr_root is not None:

@@ -47,19 +47,20 @@ def test_oracle_frames_have_the_reference_distribution():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,alphabet,channel", [((64, 1, 32), '16QAM', 'iid'), ((64, 1, 32), 'QPSK', 'kronecker'), ((16, 2, 8), 'QPSK', 'iid'),
-                                                   ((32, 4, 24), 'QPSK', 'kronecker')])
-def test_generator_kernel_matches_its_numpy_restatement(shape, alphabet, channel):
+@pytest.mark.parametrize("shape,alphabet,channel,method", [((64, 1, 32), '16QAM', 'iid', 'ar1'), ((64, 1, 32), 'QPSK', 'kronecker', 'ar1'),
+                                                          ((64, 1, 32), 'QPSK', 'kronecker', 'roots'), ((16, 2, 8), 'QPSK', 'iid', 'ar1'),
+                                                          ((32, 4, 24), 'QPSK', 'kronecker', 'roots'), ((32, 4, 24), 'QPSK', 'kronecker', 'ar1')])
+def test_generator_kernel_matches_its_numpy_restatement(shape, alphabet, channel, method):
     Nt, Na, Nr = shape
     F, snr = 37, 10 ** 1.2
     cfg = pkg.Config(Nt, Na, Nr, 1, 1, batch=F, generator_mode='sparc', alphabet=alphabet, channel_profile='uniform', device=DEV)
-    st = pkg.FrameStream(cfg, seed=0x1234567890ABCDEF, channel=channel, rho_t=0.7, rho_r=0.9)
+    st = pkg.FrameStream(cfg, seed=0x1234567890ABCDEF, channel=channel, rho_t=0.7, rho_r=0.9, method=method)
     H, y, x, lab, idx = st.frames(1000, F, snr, frame_base=5)
     sigma2 = (cfg.Na / cfg.Nr) / snr
     Rr = st.Rr.cpu().numpy() if st.Rr is not None else None
     Rt = st.Rt.cpu().numpy() if st.Rt is not None else None
     Ho, yo, xo, labo, idxo = fo.frames(st.seed, 1000, F, cfg.n, cfg.N, cfg.M, cfg.L, cfg.symbols, cfg.gray, 1 / cfg.Nr, sigma2, Rr, Rt,
-                                       frame_base=5)
+                                       frame_base=5, rho_r=st.rho_r, rho_t=st.rho_t)
     # integers exactly; floats to the accuracy of the device's fast log / sin / cos (2^-21 absolute on O(1) numbers)
     assert np.array_equal(lab.cpu().numpy(), labo) and np.array_equal(idx.cpu().numpy(), idxo)
     assert np.array_equal(x.cpu().numpy(), xo)
@@ -72,7 +73,7 @@ def test_generator_kernel_matches_its_numpy_restatement(shape, alphabet, channel
     assert torch.equal(torch.cat([Ha, Hb]), H) and torch.equal(torch.cat([ya, yb]), y) and torch.equal(torch.cat([xa, xb]), x)
     assert torch.equal(torch.cat([laba, labb]), lab) and torch.equal(torch.cat([idxa, idxb]), idx)
     # another seed is another stream
-    other = pkg.FrameStream(cfg, seed=1, channel=channel, rho_t=0.7, rho_r=0.9).frames(1000, F, snr)[0]
+    other = pkg.FrameStream(cfg, seed=1, channel=channel, rho_t=0.7, rho_r=0.9, method=method).frames(1000, F, snr)[0]
     assert not torch.equal(other, H)
 
 
@@ -107,7 +108,12 @@ def test_generated_channel_moments_and_kronecker_covariance():
     assert abs(float((H.abs() ** 2).mean()) * cfg.Nr - 1) < 5e-3 and float(H.mean().abs()) < 1e-3
     C = torch.einsum('fij,fkj->ik', H, H.conj()) / (F * cfg.N) * cfg.Nr
     assert float((C - torch.eye(cfg.n, device=DEV)).abs().max()) < 0.03
-    st = pkg.FrameStream(cfg, seed=3, channel='kronecker', rho_t=0.7, rho_r=0.9)
+    for method in ('ar1', 'roots'):
+        check_kronecker_covariance(cfg, F, method)
+
+
+def check_kronecker_covariance(cfg, F, method):
+    st = pkg.FrameStream(cfg, seed=3, channel='kronecker', rho_t=0.7, rho_r=0.9, method=method)
     H = st.frames(0, F, 10.0)[0]
     i = torch.arange(cfg.n, device=DEV)
     Rr = 0.9 ** (i[:, None] - i[None, :]).abs().float()
