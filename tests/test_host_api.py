@@ -137,6 +137,32 @@ def test_cabi_struct_layout_matches_header():
     assert ctypes.sizeof(_cabi.Problem) == 16 * 4 + 8
 
 
+def test_cabi_struct_layout_matches_a_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct of include/ampsm_b200.h as gcc lays them out against the ctypes mirrors."""
+    import ctypes
+    import subprocess
+    fields = {"ampsm_alphabet": (_cabi.Alphabet, ["K", "gray", "re", "im"]),
+              "ampsm_problem": (_cabi.Problem, ["n", "R", "max_iters", "decision", "kernel", "frame_base"]),
+              "ampsm_gen": (_cabi.Gen, ["seed", "counter_base", "h_var", "Rr_root", "Rt_root", "real_roots", "rho_r", "rho_t"])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "ampsm_b200.h"', 'int main(void) {']
+    for name, (_, fl) in fields.items():
+        src.append(f'printf("{name} %zu", sizeof({name}));')
+        for f in fl:
+            src.append(f'printf(" %zu", offsetof({name}, {f}));')
+        src.append('printf("\\n");')
+    src.append('return 0; }')
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        name, size, *offs = line.split()
+        ct, fl = fields[name]
+        assert ctypes.sizeof(ct) == int(size), name
+        assert [getattr(ct, f).offset for f in fl] == [int(o) for o in offs], name
+
+
 def test_device_frames_generator_is_consistent_on_cpu():
     """simulate.device_frames (the on-device input generator of the Monte-Carlo driver) with a CPU generator: labels and
     flat indices describe x as Data.generate_message does (data.py:88-90), y - H x is noise of variance Na/Nr/SNR, and
