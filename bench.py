@@ -698,7 +698,7 @@ def main():
             Vs.append(((V.mH @ Hd) / sv3.unsqueeze(-1)).to(torch.complex64))
             del Hd, wv, V, sv3
         U3, s3, V3 = torch.cat(Us).contiguous(), torch.cat(ss).contiguous(), torch.cat(Vs).contiguous()
-        del Us, ss, Vs, H3
+        del Us, ss, Vs
         flop3 = 16 * 64 * 128 + 18 * 128 * 4 + 40 * 128 + 10 * 64               # 146 048 flop per frame-iteration
         c3out = {}
         for tag, ee in (("exit", True), ("fixed_T", False)):
@@ -713,6 +713,18 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             c3out[tag] = (det.counters_dict(), e0.elapsed_time(e1) / 3)
+        # the same frames from their channel matrices: per-frame Jacobi SVD (one CTA per 64 x 128 matrix) + iterations in one call
+        v3h = pkg.VAMP(cfg3, outputs=False)
+        for _ in range(2):
+            v3h.detect_from_channel(H3, y3, snr3, x3, l3, i3)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        det3h = v3h.detect_from_channel(H3, y3, snr3, x3, l3, i3)
+        e1.record()
+        torch.cuda.synchronize()
+        c3h, ms3h = det3h.counters_dict(), e0.elapsed_time(e1)
+        del H3
         (ce, mse), (cf3, msf3) = c3out["exit"], c3out["fixed_T"]
         tf32 = out.get("fixed_T", {}).get("roofline_fp32", {}).get("peak") or 0.0
         out["vamp_c3"] = {
@@ -726,6 +738,10 @@ def main():
                               "algorithmic_flop_per_frame_iter": flop3},
             "fixed_T": {"value": cf3["iters"] / (msf3 * 1e-3), "unit": "frame-iter/s",
                         "tflops": cf3["iters"] * flop3 / (msf3 * 1e-3) / 1e12},
+            "from_channel": {"frames_per_s": c3h["frames"] / (ms3h * 1e-3), "value": c3h["iters"] / (ms3h * 1e-3), "unit": "frame-iter/s",
+                             "ms": ms3h, "ier": c3h["index_err"] / (4 * f3),
+                             "what": "ampsm_vamp_detect_from_h at config 3: one-sided Jacobi SVD of every frame's 64 x 128 matrix (one CTA "
+                                     "per matrix) + the iterations: the per-frame decomposition of BASELINE config 3; per-rank time"},
         }
         del U3, s3, V3
     # ---- BASELINE config 1: BAMP 8 x 4 QPSK (the reference's own CPU-runnable case) through the same entry point
