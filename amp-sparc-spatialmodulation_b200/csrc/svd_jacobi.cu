@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
         __syncwarp();
 
         int sweeps = 0;
+        int clean = 0;                                         // consecutive steps in which no pair of the warp rotated
+        bool done = false;
         for (; sweeps < kSvdMaxSweeps; ++sweeps) {
             bool rotated = false;
             if constexpr (BLOCK) {
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
                     gi += __shfl_xor_sync(0xffffffffu, gi, 1);
                     const float g2 = gr * gr + gi * gi;
                     const bool rot = g2 > kSvdTol * kSvdTol * alpha * beta && g2 > 0.f;
+                    clean = __any_sync(0xffffffffu, rot) ? 0 : clean + 1;
                     if (rot) {
                         // b~ = e^{-i phi} b makes <a, b~> = |gamma| real; then the real Jacobi rotation:
                         // zeta = (beta - alpha) / (2 |gamma|), t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), c = 1/sqrt(1+t^2), s = c t
@@ -359,22 +362,28 @@ __global__ void __launch_bounds__(kSvdWarps * 32, BLOCK ? 1 : (WITHY ? 4 : 3)) s
                     if (h == 0) nrm[p] = alpha;
                 }
                 __syncwarp();
+                // any 31 consecutive steps of the schedule visit every pair once: 31 steps without a rotation anywhere in the warp
+                // certify the matrix, wherever in a sweep they end (checked between phases, when the stationary rows are home)
+                if (clean >= kSvdRows - 1) {
+                    done = true;
+                    break;
+                }
             }
             }
-            if (!__any_sync(0xffffffffu, rotated)) {
+            if (done || !__any_sync(0xffffffffu, rotated)) {
                 ++sweeps;
                 break;
             }
         }
 
         // ---- singular values = row norms of W (lane r owns row r), descending order by rank counting
-        float nrm = 0.f;
+        float rn2 = 0.f;
 #pragma unroll 8
         for (int c = 0; c < NC; ++c) {
             const float2 w = W[svd_row<Sh::swz>(lane, Sh::wstride) + c];
-            nrm = fmaf(w.x, w.x, fmaf(w.y, w.y, nrm));
+            rn2 = fmaf(w.x, w.x, fmaf(w.y, w.y, rn2));
         }
-        const float sv = sqrtf(nrm);
+        const float sv = sqrtf(rn2);
         int rank = 0;
 #pragma unroll
         for (int o = 0; o < 32; ++o) {
